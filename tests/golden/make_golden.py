@@ -1,0 +1,289 @@
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference) on seeded inputs.
+
+Run in the build container only (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference is imported unmodified with the stubs of SURVEY.md 8c for modules that are
+off the hot path and absent here (matplotlib, zarr, ruamel.yaml; np.unicode_).
+Outputs are small .npz files committed next to this script.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "zarr", "ruamel", "ruamel.yaml"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["ruamel.yaml"].YAML = object
+    sys.modules["ruamel"].yaml = sys.modules["ruamel.yaml"]
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if not hasattr(np, "unicode_"):
+        np.unicode_ = np.str_
+    sys.path.insert(0, "/root/reference")
+    import yogo  # noqa: F401
+    from yogo.model import YOGO
+    from yogo.model_defns import get_model_func
+    from yogo.yogo_loss import YOGOLoss
+    from yogo.utils import format_preds
+    from yogo.infer import get_prediction_class_counts, count_cells_for_formatted_preds
+
+    return dict(
+        YOGO=YOGO,
+        get_model_func=get_model_func,
+        YOGOLoss=YOGOLoss,
+        format_preds=format_preds,
+        get_prediction_class_counts=get_prediction_class_counts,
+        count_cells_for_formatted_preds=count_cells_for_formatted_preds,
+    )
+
+
+def golden_loss(ref, out):
+    from oracle.yogo_oracle import synth_labels
+
+    cases = {}
+    for ci, (N, C, Sy, Sx, K, seed) in enumerate(
+        [(2, 7, 10, 14, 30, 11), (3, 4, 13, 9, 40, 12), (1, 7, 97, 129, 300, 13), (2, 7, 6, 5, 0, 14)]
+    ):
+        g = torch.Generator().manual_seed(seed)
+        lab = synth_labels(N, Sy, Sx, C, K, seed=seed)
+        # predictions in head-output space: centres/sizes near the labels for some cells,
+        # arbitrary elsewhere; logits random
+        pred = torch.zeros(N, 5 + C, Sy, Sx)
+        pred[:, 0] = torch.rand(N, Sy, Sx, generator=g)
+        pred[:, 1] = torch.rand(N, Sy, Sx, generator=g)
+        pred[:, 2] = 0.02 + 0.1 * torch.rand(N, Sy, Sx, generator=g)
+        pred[:, 3] = 0.02 + 0.1 * torch.rand(N, Sy, Sx, generator=g)
+        near = torch.rand(N, Sy, Sx, generator=g) < 0.6
+        cxl = (lab[:, 1] + lab[:, 3]) / 2
+        cyl = (lab[:, 2] + lab[:, 4]) / 2
+        pred[:, 0] = torch.where(near, cxl + 0.01 * torch.randn(N, Sy, Sx, generator=g), pred[:, 0])
+        pred[:, 1] = torch.where(near, cyl + 0.01 * torch.randn(N, Sy, Sx, generator=g), pred[:, 1])
+        pred[:, 4] = torch.rand(N, Sy, Sx, generator=g)
+        pred[:, 5:] = 2 * torch.randn(N, C, Sy, Sx, generator=g)
+        if ci == 1:
+            # edge cases: boxes leaving the image (clamp), a degenerate zero-width box
+            pred[0, 0, 0, 0] = 0.001
+            pred[0, 2, 0, 0] = 0.2
+            lab[0, :, 0, 0] = torch.tensor([1.0, 0.0, 0.0, 0.05, 0.06, 1.0])
+            pred[1, 2, 3, 3] = 0.0  # x1 == x2 -> dropped from the box term
+            lab[1, :, 3, 3] = torch.tensor([1.0, 0.3, 0.3, 0.35, 0.36, 2.0])
+            pred[2, 0, 5, 5] = 0.999
+            pred[2, 1, 5, 5] = 0.999
+            pred[2, 2, 5, 5] = 0.3
+            pred[2, 3, 5, 5] = 0.3
+            lab[2, :, 5, 5] = torch.tensor([1.0, 0.9, 0.9, 0.97, 0.99, 3.0])
+        pred.requires_grad_(True)
+        loss_fn = ref["YOGOLoss"]()
+        loss, comps = loss_fn(pred, lab)
+        loss.backward()
+        cases[f"loss{ci}_pred"] = pred.detach().numpy()
+        cases[f"loss{ci}_label"] = lab.numpy()
+        cases[f"loss{ci}_loss"] = np.array(
+            [loss.item(), comps["iou_loss"], comps["objectness_loss"], comps["classification_loss"]],
+            dtype=np.float64,
+        )
+        cases[f"loss{ci}_dpred"] = pred.grad.numpy()
+    # non-default weights
+    g = torch.Generator().manual_seed(99)
+    lab = synth_labels(2, 8, 8, 5, 20, seed=99)
+    pred = torch.rand(2, 10, 8, 8, generator=g)
+    pred[:, 2:4] = 0.03 + 0.05 * pred[:, 2:4]
+    pred.requires_grad_(True)
+    loss_fn = ref["YOGOLoss"](no_obj_weight=0.3, iou_weight=2.5, classify_weight=0.7, label_smoothing=0.1)
+    loss, comps = loss_fn(pred, lab)
+    loss.backward()
+    cases["lossw_pred"] = pred.detach().numpy()
+    cases["lossw_label"] = lab.numpy()
+    cases["lossw_loss"] = np.array(
+        [loss.item(), comps["iou_loss"], comps["objectness_loss"], comps["classification_loss"]], dtype=np.float64
+    )
+    cases["lossw_dpred"] = pred.grad.numpy()
+    np.savez_compressed(os.path.join(out, "loss.npz"), **cases)
+
+
+def golden_nms(ref, out):
+    from oracle.yogo_oracle import synth_sparse_preds
+
+    cases = {}
+    configs = [
+        # (B, Sy, Sx, C, K, seed, obj, iou, fmt, mincls)
+        (3, 20, 28, 7, 40, 21, 0.5, 0.5, "cxcywh", 0.0),
+        (2, 20, 28, 7, 60, 22, 0.5, 0.3, "xyxy", 0.0),
+        (2, 97, 129, 7, 300, 23, 0.5, 0.5, "cxcywh", 0.0),
+        (2, 12, 12, 4, 30, 24, 0.6, 0.0, "cxcywh", 0.0),  # iou_thresh 0 = NMS disabled
+        (2, 16, 16, 7, 50, 25, 0.5, 0.5, "xyxy", 0.6),  # class-confidence filter
+        (1, 8, 8, 7, 0, 26, 0.5, 0.5, "cxcywh", 0.0),  # nothing above threshold
+    ]
+    for ci, (B, Sy, Sx, C, K, seed, obj, iou, fmt, mincls) in enumerate(configs):
+        p = synth_sparse_preds(B, Sy, Sx, C, K, seed=seed)
+        if ci == 0:
+            # tie-heavy + degenerate: duplicate boxes with equal scores, zero-area boxes
+            p[0, :, 3, 3] = p[0, :, 3, 4]
+            p[0, :, 3, 5] = p[0, :, 3, 4]
+            p[0, 4, 7, 7] = 0.9
+            p[0, 2:4, 7, 7] = 0.0
+            p[0, :, 7, 8] = p[0, :, 7, 7]
+        cases[f"nms{ci}_pred"] = p.numpy()
+        cases[f"nms{ci}_cfg"] = np.array([obj, iou, 1.0 if fmt == "xyxy" else 0.0, mincls], dtype=np.float64)
+        offs = [0]
+        rows = []
+        for b in range(B):
+            r = ref["format_preds"](
+                p[b].clone(), obj_thresh=obj, iou_thresh=iou, box_format=fmt, min_class_confidence_threshold=mincls
+            )
+            rows.append(r.numpy())
+            offs.append(offs[-1] + r.shape[0])
+        cases[f"nms{ci}_rows"] = np.concatenate(rows, axis=0)
+        cases[f"nms{ci}_offsets"] = np.array(offs, dtype=np.int64)
+        cases[f"nms{ci}_counts"] = (
+            ref["get_prediction_class_counts"](p.clone(), obj_thresh=obj, iou_thresh=iou, min_class_confidence_threshold=mincls)
+            .numpy()
+            .astype(np.int64)
+        )
+    # dense-adversarial: many overlapping boxes on a small grid
+    g = torch.Generator().manual_seed(31)
+    B, C, Sy, Sx = 2, 7, 24, 32
+    p = torch.rand(B, 5 + C, Sy, Sx, generator=g)
+    p[:, 2:4] = 0.05 + 0.2 * p[:, 2:4]
+    p[:, 5:] = torch.softmax(4 * p[:, 5:], dim=1)
+    cases["nmsD_pred"] = p.numpy()
+    cases["nmsD_cfg"] = np.array([0.5, 0.5, 0.0, 0.0])
+    offs, rows = [0], []
+    for b in range(B):
+        r = ref["format_preds"](p[b].clone())
+        rows.append(r.numpy())
+        offs.append(offs[-1] + r.shape[0])
+    cases["nmsD_rows"] = np.concatenate(rows, axis=0)
+    cases["nmsD_offsets"] = np.array(offs, dtype=np.int64)
+    cases["nmsD_counts"] = ref["get_prediction_class_counts"](p.clone()).numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(out, "nms.npz"), **cases)
+
+
+GRAD_STRIDE = 5
+
+
+def _run_model(ref, name, sd_from, img, lab, train, inference=False, normalize=True):
+    torch.manual_seed(0)
+    H, W = img.shape[-2:]
+    net = ref["YOGO"](
+        img_size=(H, W),
+        anchor_w=0.0425,
+        anchor_h=0.0555,
+        num_classes=7,
+        model_func=ref["get_model_func"](name),
+        inference=inference,
+        clip_value=1.0,
+    )
+    if sd_from is not None:
+        net.load_state_dict(sd_from)
+    else:
+        # tame the head so w/h stay O(anchor) and give BN non-trivial affine
+        with torch.no_grad():
+            head = list(net.model.children())[-1]
+            head.weight.mul_(0.05)
+            for m in net.model.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.weight.uniform_(0.5, 1.5)
+                    m.bias.uniform_(-0.2, 0.2)
+                if isinstance(m, torch.nn.Conv2d) and m.bias is not None:
+                    m.bias.uniform_(-0.1, 0.1)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    keeps = {}
+
+    def mk_hook(idx):
+        def hook(mod, inp, outp):
+            x = inp[0]
+            keeps[idx] = ((outp.abs().sum(dim=(2, 3)) > 0) | (x.abs().sum(dim=(2, 3)) == 0)).float()
+
+        return hook
+
+    for i, blk in enumerate(net.model.children()):
+        for m in blk.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.register_forward_hook(mk_hook(i))
+    net.train(train)
+    x = img.float() / 255.0 if normalize else img.float()
+    res = {}
+    if train:
+        out = net(x)
+        loss, comps = ref["YOGOLoss"]()(out, lab)
+        loss.backward()
+        res["loss"] = np.array(
+            [loss.item(), comps["iou_loss"], comps["objectness_loss"], comps["classification_loss"]], dtype=np.float64
+        )
+        for k, p in net.named_parameters():
+            gflat = p.grad.numpy().reshape(-1)
+            res["gradnorm." + k] = np.array([np.linalg.norm(gflat.astype(np.float64))])
+            # big tensors: keep every GRAD_STRIDE-th element (plus the norm) to keep fixtures small
+            res["grad." + k] = gflat[::GRAD_STRIDE].copy() if gflat.size > 16384 else gflat.copy()
+        for k, v in net.state_dict().items():
+            if "running_" in k:
+                res["after." + k] = v.numpy().copy()
+    else:
+        with torch.no_grad():
+            out = net(x)
+    res["out"] = out.detach().numpy().copy()
+    for i, kk in keeps.items():
+        res[f"keep.{i}"] = kk.numpy()
+    return sd0, res
+
+
+def golden_model(ref, out):
+    from oracle.yogo_oracle import synth_images, synth_labels
+
+    img = synth_images(2, 80, 112, seed=5)
+    lab = synth_labels(2, 10, 14, 7, 25, seed=6)
+    cases = {"img": img.numpy(), "label": lab.numpy()}
+    sd_base, res = _run_model(ref, "base_model", None, img, lab, train=True)
+    for k, v in sd_base.items():
+        cases["sd." + k] = v.numpy()
+    for k, v in res.items():
+        cases["base_train." + k] = v
+    _, res = _run_model(ref, "base_model", sd_base, img, lab, train=False)
+    cases["base_eval.out"] = res["out"]
+    _, res = _run_model(ref, "base_model", sd_base, img, lab, train=False, inference=True)
+    cases["base_infer.out"] = res["out"]
+    _, res = _run_model(ref, "silu_model", sd_base, img, lab, train=True)
+    for k, v in res.items():
+        cases["silu_train." + k] = v
+    _, res = _run_model(ref, "silu_model", sd_base, img, lab, train=False)
+    cases["silu_eval.out"] = res["out"]
+    np.savez_compressed(os.path.join(out, "model_base.npz"), **cases)
+
+    # small-width and odd-topology definitions: weights are small enough to commit
+    for name in ("quarter_filters", "depth_ver_0"):
+        img = synth_images(3, 52, 68, seed=7)  # odd intermediate sizes: 26x34 -> 13x17 -> 7x9
+        sd, res = _run_model(ref, name, None, img, None, train=False)
+        Sy, Sx = res["out"].shape[-2:]
+        lab = synth_labels(3, Sy, Sx, 7, 12, seed=8)
+        sd, res = _run_model(ref, name, sd, img, lab, train=True)
+        cases = {"img": img.numpy(), "label": lab.numpy()}
+        for k, v in sd.items():
+            cases["sd." + k] = v.numpy()
+        for k, v in res.items():
+            cases["train." + k] = v
+        _, res = _run_model(ref, name, sd, img, lab, train=False)
+        cases["eval.out"] = res["out"]
+        np.savez_compressed(os.path.join(out, f"model_{name}.npz"), **cases)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    torch.use_deterministic_algorithms(True)
+    ref = import_reference()
+    golden_loss(ref, HERE)
+    golden_nms(ref, HERE)
+    golden_model(ref, HERE)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
