@@ -1,0 +1,184 @@
+/*
+ * yogo_b200 - C ABI of the B200-native YOGO hot path (libyogo_b200.so).
+ *
+ * The reference (czbiohub-sf/yogo) has no native boundary of its own: its hot path calls
+ * torch / torchvision library kernels from Python.  This header is
+ * the boundary a maintainer binds instead; each entry point cites the reference call
+ * site it replaces.  Conventions:
+ *   - extern "C", plain pointers and sizes, no torch types.  All data pointers are DEVICE
+ *     pointers unless the name ends in _host.  The library never owns tensor memory.
+ *   - every function returns 0 on success or a negative yg_status; yg_last_error()
+ *     returns a thread-local message.  No C++ exception crosses the ABI.
+ *   - every launch is asynchronous on the caller's stream (last argument, a cudaStream_t
+ *     passed as void*).
+ *   - activations are NHWC; `dtype` selects their storage: YG_F32 or YG_BF16 (accumulation
+ *     is always fp32).  Parameters and parameter gradients are fp32 in the reference's
+ *     OIHW layout (state_dict compatible, model.py:94-147).
+ */
+#ifndef YOGO_B200_H
+#define YOGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  YG_OK = 0,
+  YG_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  YG_ERR_CUDA = -2,      /* CUDA runtime / driver error (message has the string) */
+  YG_ERR_ARCH = -3,      /* device is not sm_100 */
+  YG_ERR_WORKSPACE = -4  /* workspace too small */
+} yg_status;
+
+enum { YG_F32 = 0, YG_BF16 = 1, YG_U8 = 2 };
+enum { YG_ACT_NONE = 0, YG_ACT_LRELU = 1, YG_ACT_SILU = 2 }; /* LeakyReLU(0.01) / SiLU */
+enum { YG_IMPL_AUTO = 0, YG_IMPL_SIMT = 1, YG_IMPL_TCGEN05 = 2 };
+
+int yg_version(void);
+const char* yg_last_error(void);
+/* 0 if the current device is compute capability 10.x, YG_ERR_ARCH otherwise. */
+int yg_device_check(void);
+/* Process-wide implementation switch for the 3x3 convolutions (AUTO = tcgen05 where the
+ * shape qualifies, SIMT otherwise).  Used by the parity tests to cross-check both. */
+int yg_set_conv_impl(int impl);
+int yg_get_conv_impl(void);
+
+/* ---- epilogue descriptor shared by the convolution entry points -------------------- */
+typedef struct {
+  const float* scale;      /* [Cout] or NULL (=1): folded BatchNorm scale in eval mode   */
+  const float* shift;      /* [Cout] or NULL (=0): conv bias, or folded BN shift         */
+  int act;                 /* YG_ACT_*                                                   */
+  const float* dropscale;  /* [N*Cout] or NULL: Dropout2d keep/(1-p) per (n, c)          */
+  double* stats;           /* [2*Cout] or NULL: += sum(v), sum(v*v) of v = acc*scale+shift
+                              (BatchNorm batch statistics, taken before act)             */
+  void* preact;            /* NHWC, same dtype as y, or NULL: v before the activation    */
+} yg_fwd_epilogue;
+
+typedef struct {
+  const void* saved;       /* NHWC tensor of the layer that produced this input:
+                              post-activation output (lrelu, no BN), pre-activation
+                              (silu, no BN) or raw conv output (BN); NULL = no act bwd  */
+  int act;                 /* YG_ACT_* of that layer                                     */
+  const float* dropscale;  /* [N*Cin] or NULL                                            */
+  const float* bn_scale;   /* [Cin] gamma*invstd, NULL if that layer has no BN           */
+  const float* bn_shift;   /* [Cin] beta - mean*gamma*invstd                             */
+  const float* bn_mean;    /* [Cin]                                                      */
+  const float* bn_invstd;  /* [Cin]                                                      */
+  double* bn_sums;         /* [2*Cin]: += sum(g), sum(g*xhat)                            */
+} yg_bwd_epilogue;
+
+/* ---- first layer: direct stencil on the NCHW image (Cin = 1 or 3) -------------------
+ * replaces nn.Conv2d(input_channels, C1, 3, stride=2, padding=1) (+BatchNorm2d+act),
+ * /root/reference/yogo/model_defns.py:33-37.  x is (N,Cin,H,W) in x_dtype (YG_U8 or
+ * YG_F32; YOGO.forward's `x.float()` of model.py:272-273 is folded in), w is OIHW fp32.
+ * If ep->stats is set and y is NULL only the statistics are accumulated (pass 1 of
+ * train-mode BN); otherwise y (NHWC, dtype) is written. */
+int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, void* y, int dtype,
+                      int N, int H, int W, int Cin, int Cout, int stride,
+                      const yg_fwd_epilogue* ep, void* stream);
+/* backward of the first layer from da = grad wrt its (post-activation) output.
+ * pass 1 (bn_sums != NULL in `be`, dw == NULL): accumulate BN backward sums.
+ * pass 2 (dw != NULL): dW (OIHW fp32, overwritten) and, if dshift, d(bias or beta);
+ *   bn_dy_mean/bn_dyx_mean = sums/M from pass 1 (NULL when no BN). */
+int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, const void* da, int dtype,
+                      int N, int H, int W, int Cin, int Cout, int stride,
+                      const yg_bwd_epilogue* be, const float* fwd_shift,
+                      const float* bn_dy_mean, const float* bn_dyx_mean,
+                      float* dw, float* dshift, float clip, void* workspace, size_t workspace_bytes,
+                      void* stream);
+size_t yg_conv_first_bwd_workspace(int Cin, int Cout);
+
+/* ---- generic convolution (3x3 pad 1 or 1x1 pad 0, stride 1 or 2), NHWC -------------
+ * replaces nn.Conv2d fprop / dgrad / wgrad (cuDNN) at model_defns.py:34-67 and the
+ * elementwise BatchNorm/LeakyReLU/SiLU/Dropout2d kernels that follow each conv. */
+int yg_conv_fwd(const void* x, const float* w_oihw, void* y, int dtype,
+                int N, int H, int W, int Cin, int Cout, int ksize, int stride,
+                const yg_fwd_epilogue* ep, void* stream);
+/* dx = conv_transpose(dz, w); the epilogue turns it into the gradient wrt the previous
+ * layer's conv output (activation / dropout / BN-sum fusion), see yg_bwd_epilogue. */
+int yg_conv_dgrad(const void* dz, const float* w_oihw, void* dx, int dtype,
+                  int N, int H, int W, int Cin, int Cout, int ksize, int stride,
+                  const yg_bwd_epilogue* be, void* stream);
+/* dw (OIHW fp32) = sum over pixels dz * x ; dbias[Cout] = sum dz (NULL to skip).
+ * Both are clamped to [-clip, clip] (YOGO's per-parameter grad hook, model.py:76-77);
+ * clip <= 0 disables.  Deterministic split-K through `workspace`. */
+size_t yg_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ksize, int stride);
+int yg_conv_wgrad(const void* x, const void* dz, float* dw, float* dbias, int dtype,
+                  int N, int H, int W, int Cin, int Cout, int ksize, int stride,
+                  float clip, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- BatchNorm2d pieces (nn.BatchNorm2d, model_defns.py:35,55,60) ------------------ */
+/* from stats (sum, sumsq over M = N*H*W values per channel): mean, invstd, fused
+ * scale/shift, and the running-stat update (momentum 0.1, unbiased variance). */
+int yg_bn_finalize(const double* stats, double count, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float momentum, float eps,
+                   float* mean, float* invstd, float* scale, float* shift, int C, void* stream);
+/* eval mode: scale = gamma/sqrt(rv+eps), shift = beta - rm*scale (+ conv_bias*scale). */
+int yg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, const float* conv_bias, float eps,
+                    float* scale, float* shift, int C, void* stream);
+/* a = act(y*scale[c] + shift[c]) * dropscale[n,c]   (elementwise, NHWC) */
+int yg_bn_act_apply(const void* y, void* a, int dtype, int N, int HW, int C,
+                    const float* scale, const float* shift, int act, const float* dropscale,
+                    void* stream);
+/* dz = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M) in place over g (batch_stats != 0), or
+ * dz = gamma*invstd*g when the layer ran with running statistics (batch_stats == 0, BN in
+ * eval mode inside a training graph: YOGO(tuning=True), model.py:69-70).  Also writes
+ * dgamma = clamp(sum_gx), dbeta = clamp(sum_g). y = raw conv output (for xhat). */
+int yg_bn_bwd_apply(void* g, const void* y, int dtype, int N, int HW, int C,
+                    const double* sums, const float* gamma, const float* mean, const float* invstd,
+                    float* dgamma, float* dbeta, float clip, int batch_stats, void* stream);
+
+/* ---- head: 1x1 conv to 5+C channels fused with YOGO.forward's transform -------------
+ * replaces model_defns.py:67 + model.py:277-313.  x NHWC (N,Sy,Sx,Cin) -> out (N,5+C,Sy,Sx)
+ * fp32 NCHW; t_raw (N,Sy,Sx,5+C) fp32 keeps the raw logits for the backward (or NULL).
+ * cxs/cys: the module's _Cxs/_Cys buffers (Sy*Sx fp32, model.py:48-59) or NULL to recompute. */
+int yg_head_fwd(const void* x, int dtype, const float* w, const float* bias, float* out, float* t_raw,
+                int N, int Sy, int Sx, int Cin, int num_classes,
+                float anchor_w, float anchor_h, float width_mult, float height_mult,
+                int inference, const float* cxs, const float* cys, void* stream);
+/* dpred (N,5+C,Sy,Sx) fp32 + t_raw -> dx NHWC (with the previous block's bwd epilogue),
+ * dw (OIHW [5+C,Cin,1,1]) and dbias, clamped. Training head only (inference == 0). */
+size_t yg_head_bwd_workspace(int N, int Sy, int Sx, int Cin, int num_classes);
+int yg_head_bwd(const float* dpred, const float* t_raw, const void* x, const float* w, void* dx, int dtype,
+                float* dw, float* dbias, int N, int Sy, int Sx, int Cin, int num_classes,
+                float anchor_w, float anchor_h, float width_mult, float height_mult,
+                const yg_bwd_epilogue* be, float clip, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ---- YOGOLoss forward + backward in one pass -----------------------------------------
+ * replaces yogo_loss.py:38-129 (+ torchvision box_convert / complete_box_iou_loss).
+ * pred (N,5+C,Sy,Sx) fp32, label (N,6,Sy,Sx) fp32.  out4 (device, 4 floats) =
+ * [loss, iou_loss, objectness_loss, classification_loss]; dpred may be NULL. */
+size_t yg_yogo_loss_workspace(int N, int Sy, int Sx);
+int yg_yogo_loss_fwd_bwd(const float* pred, const float* label, float* out4, float* dpred,
+                         int N, int num_classes, int Sy, int Sx,
+                         float no_obj_weight, float iou_weight, float classify_weight,
+                         float label_smoothing, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- threshold + NMS + per-class counts, whole batch ----------------------------------
+ * replaces format_preds (utils/prediction_formatting.py:23-93, torchvision.ops.nms) and
+ * get_prediction_class_counts (infer.py:60-124).  preds (B,5+C,Sy,Sx) fp32.
+ * Outputs: keep_count[B] (int32), rows (B, Sy*Sx, 5+C) fp32 - image b's kept rows packed
+ * at rows[b][0..keep_count[b]) in the reference's output order - keep_index (B, Sy*Sx)
+ * int32 grid-cell index of each kept row, class_counts[C] (int64, summed over the batch,
+ * overwritten).  xyxy != 0 returns converted boxes (box_format="xyxy"). */
+size_t yg_format_preds_workspace(int B, int num_classes, int Sy, int Sx);
+int yg_format_preds_batch(const float* preds, int B, int num_classes, int Sy, int Sx,
+                          float obj_thresh, double iou_thresh, int xyxy, float min_class_conf,
+                          int* keep_count, float* rows, int* keep_index, long long* class_counts,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- optimizer: fused AdamW over one flat fp32 buffer ---------------
+ * replaces torch.optim.AdamW.step (train.py:213-217, 324). grads are pre-scaled by
+ * grad_scale (1/world_size after an all-reduce SUM). */
+int yg_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay,
+                  long long step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOGO_B200_H */

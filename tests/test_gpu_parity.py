@@ -1,0 +1,389 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI by the
+Python mirror of the reference API, against (a) the golden vectors produced by the real
+reference and (b) the CPU oracle on seeded inputs.  Nothing here reads /root/reference.
+
+Tolerances: fp32 storage path - 1e-3 relative (north star); bf16 storage path - per-tensor
+bounds calibrated from the reference's own bf16-autocast error."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import yogo_b200
+from yogo_b200 import _lib as L
+from oracle import yogo_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ----------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("case", ["loss0", "loss1", "loss2", "loss3", "lossw"])
+def test_loss_matches_reference_golden(golden_dir, case):
+    z = _load(golden_dir, "loss.npz")
+    kw = dict(no_obj_weight=0.3, iou_weight=2.5, classify_weight=0.7, label_smoothing=0.1) if case == "lossw" else {}
+    pred = torch.from_numpy(z[f"{case}_pred"]).to(DEV).requires_grad_(True)
+    label = torch.from_numpy(z[f"{case}_label"]).to(DEV)
+    loss_fn = yogo_b200.YOGOLoss(**kw).to(DEV)
+    loss, comps = loss_fn(pred, label)
+    loss.backward()
+    ref = z[f"{case}_loss"]
+    got = [loss.item(), comps["iou_loss"], comps["objectness_loss"], comps["classification_loss"]]
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(pred.grad.cpu().numpy(), z[f"{case}_dpred"], rtol=1e-3, atol=2e-6)
+
+
+def test_loss_full_size_vs_oracle_and_scaling_property():
+    # BASELINE size: 12,513 cells per image, 300 labels per image
+    N = 8
+    lab = O.synth_labels(N)
+    g = torch.Generator().manual_seed(3)
+    pred = torch.rand(N, 12, 97, 129, generator=g)
+    pred[:, 2:4] = 0.02 + 0.08 * pred[:, 2:4]
+    pred[:, 5:] = 3 * torch.randn(N, 7, 97, 129, generator=g)
+    ref_loss, ref_comps, ref_d = O.yogo_loss_np(pred.numpy(), lab.numpy())
+    p = pred.to(DEV).requires_grad_(True)
+    loss, comps = yogo_b200.YOGOLoss().to(DEV)(p, lab.to(DEV))
+    (3.0 * loss).backward()  # upstream gradient scaling must pass through linearly
+    assert abs(loss.item() - ref_loss) <= 2e-5 * abs(ref_loss)
+    for k in ref_comps:
+        assert abs(comps[k] - ref_comps[k]) <= 2e-5 * abs(ref_comps[k]) + 1e-6
+    np.testing.assert_allclose(p.grad.cpu().numpy() / 3.0, ref_d, rtol=1e-3, atol=2e-6)
+    # batch-replication property: duplicating the batch leaves the loss unchanged (sum / N)
+    loss2, _ = yogo_b200.YOGOLoss().to(DEV)(torch.cat([p.detach(), p.detach()]), torch.cat([lab, lab]).to(DEV))
+    assert abs(loss2.item() - loss.item()) <= 1e-5 * abs(loss.item())
+
+
+# ----------------------------------------------------------------------------- format_preds / NMS
+@pytest.mark.parametrize("case", ["nms0", "nms1", "nms2", "nms3", "nms4", "nms5", "nmsD"])
+def test_format_preds_bit_exact_vs_reference_golden(golden_dir, case):
+    z = _load(golden_dir, "nms.npz")
+    obj, iou, xyxy, mincls = z[f"{case}_cfg"]
+    pred = torch.from_numpy(z[f"{case}_pred"]).to(DEV)
+    offs, rows = z[f"{case}_offsets"], z[f"{case}_rows"]
+    fmt = "xyxy" if xyxy else "cxcywh"
+    out_rows, keep_count, keep_index, counts = yogo_b200.format_preds_batch(pred, obj, iou, fmt, mincls)
+    kc = keep_count.cpu().numpy()
+    for b in range(pred.shape[0]):
+        exp = rows[offs[b]: offs[b + 1]]
+        assert kc[b] == exp.shape[0]
+        got = out_rows[b, : kc[b]].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+        single = yogo_b200.format_preds(pred[b], obj, iou, fmt, mincls).cpu().numpy()
+        assert np.array_equal(single.view(np.uint32), exp.view(np.uint32))
+    assert np.array_equal(counts.cpu().numpy(), z[f"{case}_counts"])
+    cc = yogo_b200.get_prediction_class_counts(pred, obj, iou, mincls)
+    assert cc.device.type == "cpu" and np.array_equal(cc.numpy(), z[f"{case}_counts"])
+
+
+def test_format_preds_reference_known_answers():
+    # /root/reference/tests/test_utils_tensor_formatting.py:9-68 through the CUDA path
+    none = torch.zeros(12, 4, 4, device=DEV)
+    assert tuple(yogo_b200.format_preds(none).shape) == (0, 12)
+    single = torch.zeros(12, 4, 4, device=DEV)
+    single[4, 0, 0] = 1.0
+    single[5] = 1.0
+    torch.testing.assert_close(yogo_b200.format_preds(single), single[:, 0, 0].unsqueeze(0))
+    box = torch.zeros(12, 4, 4, device=DEV)
+    box[5] = 1.0
+    box[4, 1, 1] = 1.0
+    box[0:2, 1, 1] = 0.5
+    box[2:4, 1, 1] = 0.1
+    torch.testing.assert_close(yogo_b200.format_preds(box), box[:, 1, 1].unsqueeze(0))
+    actual = box[:, 1, 1].unsqueeze(0).clone()
+    actual[:, 0] = actual[:, 0] - actual[:, 2] / 2
+    actual[:, 1] = actual[:, 1] - actual[:, 3] / 2
+    actual[:, 2] = actual[:, 0] + actual[:, 2]
+    actual[:, 3] = actual[:, 1] + actual[:, 3]
+    torch.testing.assert_close(yogo_b200.format_preds(box, box_format="xyxy"), actual)
+    # two identical zero-area boxes: 0/0 = NaN never suppresses
+    two = torch.zeros(12, 4, 4, device=DEV)
+    two[4, 0, 0] = two[4, 0, 1] = 0.9
+    two[5] = 1.0
+    assert yogo_b200.format_preds(two).shape[0] == 2
+
+
+@pytest.mark.parametrize("K,B", [(50, 8), (300, 8), (1000, 4)])
+def test_format_preds_full_size_sparse_vs_oracle(K, B):
+    p = O.synth_sparse_preds(B, K=K, seed=100 + K)
+    rows, kc, kidx, counts = yogo_b200.format_preds_batch(p.to(DEV))
+    kc = kc.cpu().numpy()
+    tot = np.zeros(7, np.int64)
+    for b in range(B):
+        exp, idx = O.format_preds_np(p[b].numpy(), return_index=True)
+        assert kc[b] == exp.shape[0]
+        assert np.array_equal(rows[b, : kc[b]].cpu().numpy().view(np.uint32), exp.view(np.uint32))
+        assert np.array_equal(kidx[b, : kc[b]].cpu().numpy(), idx)
+        tot += O.count_cells_np(exp[:, 5:])
+    assert np.array_equal(counts.cpu().numpy(), tot)
+
+
+def test_format_preds_dense_full_size_and_idempotence():
+    # dense-adversarial case: ~all 12,513 cells are candidates
+    g = torch.Generator().manual_seed(7)
+    p = torch.rand(2, 12, 97, 129, generator=g)
+    p[:, 2:4] = 0.01 + 0.05 * p[:, 2:4]
+    p[:, 4] = 0.5 + 0.5 * p[:, 4]
+    p[:, 5:] = torch.softmax(4 * p[:, 5:], dim=1)
+    rows, kc, kidx, counts = yogo_b200.format_preds_batch(p.to(DEV))
+    kc = kc.cpu().numpy()
+    for b in range(2):
+        exp = O.format_preds_np(p[b].numpy())
+        assert kc[b] == exp.shape[0]
+        assert np.array_equal(rows[b, : kc[b]].cpu().numpy().view(np.uint32), exp.view(np.uint32))
+    # torchvision (installed library on the GPU box, CPU kernel) agrees on keep indices
+    import torchvision.ops as ops
+    pb = p[0].reshape(12, -1).T
+    m = pb[:, 4] > 0.5
+    c = pb[m]
+    keep = ops.nms(ops.box_convert(c[:, :4], "cxcywh", "xyxy"), c[:, 5:].max(1).values * c[:, 4], 0.5)
+    cells = torch.nonzero(m)[:, 0][keep]
+    assert np.array_equal(kidx[0, : kc[0]].cpu().numpy(), cells.numpy())
+    # idempotence: the kept boxes, scattered back on an empty grid, all survive a second pass
+    q = torch.zeros_like(p[0])
+    q[:, :, :] = 0
+    flat = q.reshape(12, -1)
+    flat[:, kidx[0, : kc[0]].cpu().long()] = rows[0, : kc[0]].cpu().T
+    rows2, kc2, _, _ = yogo_b200.format_preds_batch(q.unsqueeze(0).to(DEV))
+    assert int(kc2[0]) == int(kc[0])
+    assert np.array_equal(rows2[0, : kc[0]].cpu().numpy().view(np.uint32), rows[0, : kc[0]].cpu().numpy().view(np.uint32))
+
+
+# ----------------------------------------------------------------------------- conv kernels vs oracle
+def _conv_case(N, H, W, Cin, Cout, k, s, dtype, act, with_stats, seed=0):
+    import ctypes as C
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    keep = (torch.rand(N, Cout, generator=g) > 0.2).float() / 0.8
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).to(dtype)
+    x_ref = xd.float().permute(0, 3, 1, 2).cpu()
+    y_ref = torch.nn.functional.conv2d(x_ref, w, b, stride=s, padding=k // 2)
+    Ho, Wo = y_ref.shape[-2:]
+    lib = L.lib()
+    y = torch.empty(N, Ho, Wo, Cout, device=DEV, dtype=dtype)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV) if with_stats else None
+    wd, bd, kd = w.to(DEV), b.to(DEV), keep.to(DEV).contiguous()
+    ep = L.FwdEpilogue(None, bd.data_ptr(), act, kd.data_ptr(), L.ptr(stats), None)
+    L.check(lib.yg_conv_fwd(xd.data_ptr(), wd.data_ptr(), y.data_ptr(), L.dtype_code(dtype), N, H, W, Cin, Cout, k, s,
+                            C.byref(ep), L.stream()))
+    a_ref = O._act(y_ref, {0: None, 1: "lrelu", 2: "silu"}[act]) * keep[:, :, None, None]
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    assert _rel(got, a_ref) < tol, ("fwd", _rel(got, a_ref))
+    if with_stats:
+        s_ref = torch.stack([y_ref.double().sum((0, 2, 3)), (y_ref.double() ** 2).sum((0, 2, 3))]).reshape(-1)
+        assert _rel(stats.cpu(), s_ref) < (1e-5 if dtype == torch.float32 else 5e-3)
+    # dgrad + wgrad against autograd of the CPU conv
+    dz = torch.randn(N, Cout, Ho, Wo, generator=g)
+    dzd = dz.permute(0, 2, 3, 1).contiguous().to(DEV).to(dtype)
+    dz_ref = dzd.float().permute(0, 3, 1, 2).cpu()
+    xr = x_ref.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    torch.nn.functional.conv2d(xr, wr, br, stride=s, padding=k // 2).backward(dz_ref)
+    dx = torch.empty(N, H, W, Cin, device=DEV, dtype=dtype)
+    L.check(lib.yg_conv_dgrad(dzd.data_ptr(), wd.data_ptr(), dx.data_ptr(), L.dtype_code(dtype), N, H, W, Cin, Cout, k, s,
+                              None, L.stream()))
+    assert _rel(dx.float().permute(0, 3, 1, 2).cpu(), xr.grad) < tol, "dgrad"
+    dw = torch.empty_like(wd)
+    db = torch.empty_like(bd)
+    nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, k, s)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
+    L.check(lib.yg_conv_wgrad(xd.data_ptr(), dzd.data_ptr(), dw.data_ptr(), db.data_ptr(), L.dtype_code(dtype), N, H, W,
+                              Cin, Cout, k, s, 0.0, ws.data_ptr(), nb, L.stream()))
+    assert _rel(dw.cpu(), wr.grad) < (5e-5 if dtype == torch.float32 else 3e-3), ("wgrad", _rel(dw.cpu(), wr.grad))
+    assert _rel(db.cpu(), br.grad) < (5e-5 if dtype == torch.float32 else 3e-3), "dbias"
+
+
+SHAPES = [
+    # N, H, W, Cin, Cout, k, s
+    (2, 13, 17, 5, 12, 3, 1),
+    (2, 13, 17, 5, 12, 3, 2),
+    (1, 26, 34, 16, 32, 3, 1),
+    (3, 26, 35, 32, 64, 3, 2),
+    (2, 9, 11, 64, 128, 3, 1),
+    (2, 20, 28, 128, 128, 3, 2),
+    (1, 10, 14, 128, 128, 3, 1),
+    (2, 10, 14, 48, 96, 3, 1),
+    (2, 10, 14, 24, 12, 1, 1),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_conv_kernels_vs_oracle(shape, dtype, impl):
+    L.set_conv_impl(impl)
+    try:
+        _conv_case(*shape, dtype=dtype, act=(shape[3] % 3), with_stats=True, seed=sum(shape))
+    finally:
+        L.set_conv_impl("auto")
+
+
+# ----------------------------------------------------------------------------- whole model vs golden
+def _build_from_golden(z, name, sdprefix="sd.", dtype=torch.float32, inference=False):
+    sd = {k[len(sdprefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(sdprefix)}
+    H, W = z["img"].shape[-2:]
+    net = yogo_b200.YOGO((H, W), float(sd["anchor_w"]), float(sd["anchor_h"]), 7,
+                         model_func=yogo_b200.get_model_func(name), inference=inference)
+    net.load_state_dict(sd)
+    net.compute_dtype = dtype
+    return net.to(DEV), sd
+
+
+def _grad_check(z, prefix, net, tol_rel, tol_floor):
+    worst = {}
+    for k, p in net.named_parameters():
+        g = p.grad.detach().cpu().numpy().reshape(-1)
+        exp = z[prefix + "grad." + k]
+        if g.size > 16384:
+            g = g[::5]
+        denom = max(float(np.linalg.norm(exp)), tol_floor)
+        worst[k] = float(np.linalg.norm(g - exp)) / denom
+    bad = {k: v for k, v in worst.items() if v > tol_rel}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize(
+    "fname,prefix,name",
+    [
+        ("model_base.npz", "base_train.", "base_model"),
+        ("model_base.npz", "silu_train.", "silu_model"),
+        ("model_quarter_filters.npz", "train.", "quarter_filters"),
+        ("model_depth_ver_0.npz", "train.", "depth_ver_0"),
+    ],
+)
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_train_step_fp32_matches_reference_golden(golden_dir, fname, prefix, name, impl):
+    L.set_conv_impl(impl)
+    try:
+        z = _load(golden_dir, fname)
+        net, sd = _build_from_golden(z, name)
+        net.train()
+        runner = net._get_runner()
+        runner.drop_keep_override = {
+            int(k.split(".")[-1]): torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix + "keep.")
+        }
+        x = (torch.from_numpy(z["img"]).float() / 255.0).to(DEV)
+        out = net(x)
+        loss, comps = yogo_b200.YOGOLoss().to(DEV)(out, torch.from_numpy(z["label"]).to(DEV))
+        loss.backward()
+        assert _rel(out.detach().cpu().numpy(), z[prefix + "out"]) < 1e-3
+        ref = z[prefix + "loss"]
+        np.testing.assert_allclose(
+            [loss.item(), comps["iou_loss"], comps["objectness_loss"], comps["classification_loss"]], ref, rtol=1e-3)
+        # conv bias in front of BatchNorm has a ~0 gradient: absolute floor
+        _grad_check(z, prefix, net, tol_rel=2e-3, tol_floor=1e-3)
+        for k, v in net.state_dict().items():
+            if "running_" in k:
+                np.testing.assert_allclose(v.cpu().numpy(), z[f"{prefix}after.{k}"], rtol=1e-3, atol=1e-6)
+    finally:
+        L.set_conv_impl("auto")
+
+
+@pytest.mark.parametrize("name,prefix", [("base_model", "base_train."), ("silu_model", "silu_train.")])
+def test_train_step_bf16_within_calibrated_tolerance(golden_dir, name, prefix):
+    """bf16 storage path.  Bounds = ~1.5x the reference's own bf16-autocast error vs its fp32
+    (SURVEY.md Appendix E): loss 1e-3 relative, head outputs 3e-2 rel-L2, last-layer grads
+    2e-2, early layers 0.4 (random-init gradients are ill-conditioned through 5+ bf16 layers)."""
+    z = _load(golden_dir, "model_base.npz")
+    net, sd = _build_from_golden(z, name, dtype=torch.bfloat16)
+    net.train()
+    net._get_runner().drop_keep_override = {
+        int(k.split(".")[-1]): torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix + "keep.")
+    }
+    x = (torch.from_numpy(z["img"]).float() / 255.0).to(DEV)
+    out = net(x)
+    loss, comps = yogo_b200.YOGOLoss().to(DEV)(out, torch.from_numpy(z["label"]).to(DEV))
+    loss.backward()
+    assert _rel(out.detach().cpu().numpy(), z[prefix + "out"]) < 3e-2
+    assert abs(loss.item() - z[prefix + "loss"][0]) < 2e-3 * abs(z[prefix + "loss"][0])
+    names = [k for k, _ in net.named_parameters()]
+    for k, p in net.named_parameters():
+        g = p.grad.detach().cpu().numpy().reshape(-1)
+        exp = z[prefix + "grad." + k]
+        if g.size > 16384:
+            g = g[::5]
+        late = k.startswith(("model.7", "model.6", "model.5"))
+        bound = 3e-2 if late else 0.4
+        denom = max(float(np.linalg.norm(exp)), 1e-3)
+        assert float(np.linalg.norm(g - exp)) / denom < bound, (k, float(np.linalg.norm(g - exp)) / denom)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 3e-2)])
+def test_eval_and_inference_forward_match_reference_golden(golden_dir, dtype, tol):
+    z = _load(golden_dir, "model_base.npz")
+    x = (torch.from_numpy(z["img"]).float() / 255.0).to(DEV)
+    for name, key, inf in (("base_model", "base_eval.out", False), ("base_model", "base_infer.out", True),
+                           ("silu_model", "silu_eval.out", False)):
+        net, _ = _build_from_golden(z, name, dtype=dtype, inference=inf)
+        net.eval()
+        with torch.no_grad():
+            out = net(x)
+        assert out.dtype == torch.float32 and out.is_contiguous()
+        assert _rel(out.cpu().numpy(), z[key]) < tol, (name, key)
+        # uint8 input path == float input path (x.float(), model.py:272-273)
+        with torch.no_grad():
+            a = net(torch.from_numpy(z["img"]).to(DEV))
+            b = net(torch.from_numpy(z["img"]).float().to(DEV))
+        assert torch.equal(a, b)
+
+
+def test_full_size_train_step_vs_oracle_fp32():
+    """BASELINE geometry (772x1032 -> 97x129 grid), small batch, fp32 path vs the CPU oracle."""
+    torch.manual_seed(0)
+    net = yogo_b200.YOGO((772, 1032), O.ANCHOR_W, O.ANCHOR_H, 7)
+    with torch.no_grad():
+        net.model[-1].weight.mul_(0.05)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV)
+    net.compute_dtype = torch.float32
+    net.train()
+    N = 2
+    img = O.synth_images(N)
+    lab = O.synth_labels(N)
+    keeps = {1: (torch.rand(N, 32) > 0.05).float(), 2: (torch.rand(N, 64) > 0.1).float(),
+             3: (torch.rand(N, 128) > 0.15).float()}
+    net._get_runner().drop_keep_override = keeps
+    out = net(img.to(DEV))  # raw uint8, un-normalised (reference default)
+    x = img.float() / 255.0
+    out = net(x.to(DEV))
+    loss, comps = yogo_b200.YOGOLoss().to(DEV)(out, lab.to(DEV))
+    loss.backward()
+    blocks = O.blocks_from_state_dict("base_model", sd)
+    for b in blocks:
+        b.weight.requires_grad_(True)
+    t = O.backbone_forward(x, blocks, train=True, drop_keep=[keeps.get(i) for i in range(len(blocks))])
+    ref_out = O.head_transform(t, O.ANCHOR_W, O.ANCHOR_H)
+    ref_loss, ref_comps, dpred = O.yogo_loss_np(ref_out.detach().numpy(), lab.numpy())
+    ref_out.backward(torch.from_numpy(dpred))
+    assert _rel(out.detach().cpu().numpy(), ref_out.detach().numpy()) < 1e-3
+    assert abs(loss.item() - ref_loss) < 1e-3 * abs(ref_loss)
+    for i, b in enumerate(blocks):
+        key = f"model.{i}.weight" if i == len(blocks) - 1 else f"model.{i}.0.weight"
+        g = dict(net.named_parameters())[key].grad.cpu()
+        r = b.weight.grad.clamp(-1, 1)
+        assert _rel(g.numpy(), r.numpy()) < 3e-3, (key, _rel(g.numpy(), r.numpy()))
+
+
+def test_variable_batch_and_3d_input():
+    net = yogo_b200.YOGO((64, 96), 0.05, 0.05, 7).to(DEV)
+    net.eval()
+    with torch.no_grad():
+        o1 = net(torch.rand(1, 64, 96, device=DEV))       # 3-D input is unsqueezed (model.py:269-270)
+        o5 = net(torch.rand(5, 1, 64, 96, device=DEV))    # ragged last batch (drop_last=False)
+    assert tuple(o1.shape) == (1, 12, 8, 12) and tuple(o5.shape) == (5, 12, 8, 12)
+    assert torch.isfinite(o5).all()

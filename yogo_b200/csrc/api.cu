@@ -1,0 +1,119 @@
+// C-ABI glue: error reporting, device check, implementation dispatch for the convolutions.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace yg {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static int g_conv_impl = YG_IMPL_AUTO;
+
+// conv_simt.cu
+int conv_fwd_simt(const void*, const float*, void*, int, int, int, int, int, int, int, int, const FwdEpi&, cudaStream_t);
+int conv_dgrad_simt(const void*, const float*, void*, int, int, int, int, int, int, int, int, const BwdEpi&, cudaStream_t);
+int conv_wgrad_simt(const void*, const void*, float*, float*, int, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
+size_t simt_wgrad_workspace(int, int, int, int, int, int, int);
+// conv_tc.cu
+bool tc_fwd_supported(int dtype, int Cin, int Cout, int ks, int stride);
+bool tc_dgrad_supported(int dtype, int Cin, int Cout, int ks, int stride);
+bool tc_wgrad_supported(int dtype, int Cin, int Cout, int ks, int stride);
+int conv_fwd_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const FwdEpi&, cudaStream_t);
+int conv_dgrad_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const BwdEpi&, cudaStream_t);
+int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
+size_t tc_wgrad_workspace(int, int, int, int, int, int, int);
+
+static int check_conv_args(const char* who, int dtype, int N, int H, int W, int Cin, int Cout, int ks, int stride) {
+  YG_CHECK_ARG(dtype == YG_F32 || dtype == YG_BF16, "%s: dtype %d", who, dtype);
+  YG_CHECK_ARG(ks == 1 || ks == 3, "%s: ksize %d (1 or 3)", who, ks);
+  YG_CHECK_ARG(stride == 1 || stride == 2, "%s: stride %d (1 or 2)", who, stride);
+  YG_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && Cin >= 1 && Cout >= 1, "%s: bad shape", who);
+  return YG_OK;
+}
+
+}  // namespace yg
+using namespace yg;
+
+extern "C" int yg_version(void) { return 100; }
+extern "C" const char* yg_last_error(void) { return g_err; }
+
+extern "C" int yg_device_check(void) {
+  int dev = 0;
+  YG_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  YG_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("yogo_b200 needs an sm_100 device, found sm_%d%d (%s)", prop.major, prop.minor, prop.name);
+    return YG_ERR_ARCH;
+  }
+  return YG_OK;
+}
+
+extern "C" int yg_set_conv_impl(int impl) {
+  YG_CHECK_ARG(impl >= YG_IMPL_AUTO && impl <= YG_IMPL_TCGEN05, "set_conv_impl: %d", impl);
+  g_conv_impl = impl;
+  return YG_OK;
+}
+extern "C" int yg_get_conv_impl(void) { return g_conv_impl; }
+
+extern "C" int yg_conv_fwd(const void* x, const float* w, void* y, int dtype, int N, int H, int W, int Cin, int Cout,
+                           int ks, int stride, const yg_fwd_epilogue* epp, void* stream) {
+  int rc = check_conv_args("conv_fwd", dtype, N, H, W, Cin, Cout, ks, stride);
+  if (rc) return rc;
+  YG_CHECK_ARG(x && w, "conv_fwd: null pointer");
+  if (N == 0) return YG_OK;
+  FwdEpi ep = make_fwd_epi(epp);
+  const bool tc_ok = tc_fwd_supported(dtype, Cin, Cout, ks, stride);
+  if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
+    set_error("conv_fwd: tcgen05 path forced but shape unsupported (dtype %d Cin %d Cout %d k %d s %d)", dtype, Cin, Cout, ks, stride);
+    return YG_ERR_INVALID;
+  }
+  if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
+    return conv_fwd_tc(x, w, y, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
+  return conv_fwd_simt(x, w, y, dtype, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
+}
+
+extern "C" int yg_conv_dgrad(const void* dz, const float* w, void* dx, int dtype, int N, int H, int W, int Cin,
+                             int Cout, int ks, int stride, const yg_bwd_epilogue* bep, void* stream) {
+  int rc = check_conv_args("conv_dgrad", dtype, N, H, W, Cin, Cout, ks, stride);
+  if (rc) return rc;
+  YG_CHECK_ARG(dz && w && dx, "conv_dgrad: null pointer");
+  if (N == 0) return YG_OK;
+  BwdEpi be = make_bwd_epi(bep);
+  const bool tc_ok = tc_dgrad_supported(dtype, Cin, Cout, ks, stride);
+  if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
+    set_error("conv_dgrad: tcgen05 path forced but shape unsupported");
+    return YG_ERR_INVALID;
+  }
+  if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
+    return conv_dgrad_tc(dz, w, dx, N, H, W, Cin, Cout, ks, stride, be, (cudaStream_t)stream);
+  return conv_dgrad_simt(dz, w, dx, dtype, N, H, W, Cin, Cout, ks, stride, be, (cudaStream_t)stream);
+}
+
+extern "C" size_t yg_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ks, int stride) {
+  size_t a = simt_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
+  size_t b = tc_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
+  return a > b ? a : b;
+}
+
+extern "C" int yg_conv_wgrad(const void* x, const void* dz, float* dw, float* dbias, int dtype, int N, int H, int W,
+                             int Cin, int Cout, int ks, int stride, float clip, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  int rc = check_conv_args("conv_wgrad", dtype, N, H, W, Cin, Cout, ks, stride);
+  if (rc) return rc;
+  YG_CHECK_ARG(x && dz && dw, "conv_wgrad: null pointer");
+  YG_CHECK_ARG(N >= 1, "conv_wgrad: empty batch");
+  const bool tc_ok = tc_wgrad_supported(dtype, Cin, Cout, ks, stride);
+  if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
+    set_error("conv_wgrad: tcgen05 path forced but shape unsupported");
+    return YG_ERR_INVALID;
+  }
+  if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
+    return conv_wgrad_tc(x, dz, dw, dbias, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);
+  return conv_wgrad_simt(x, dz, dw, dbias, dtype, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);
+}

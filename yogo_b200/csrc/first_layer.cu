@@ -1,0 +1,298 @@
+// First convolution block as a direct stencil on the NCHW image (Cin = 1 or 3, K = 9*Cin):
+// HBM-bound, not GEMM-shaped, so it is a SIMT kernel (layer 1).
+// Train-mode BatchNorm is handled by recomputation: pass 1 accumulates the batch statistics
+// without writing anything, pass 2 recomputes the 9-tap stencil and writes the normalised,
+// activated output once.  Replaces nn.Conv2d(1,16,3,stride=2,padding=1,bias=False) +
+// BatchNorm2d + LeakyReLU/SiLU at /root/reference/yogo/model_defns.py:33-37 (and x.float(),
+// model.py:272-273).
+#include "common.cuh"
+
+namespace yg {
+
+constexpr int FL_CO = 16, FL_THREADS = 128;
+
+template <typename TX>
+__device__ __forceinline__ void first_conv_pixel(const TX* __restrict__ x, const float* ws, int n, int ho, int wo,
+                                                 int H, int W, int Cin, int stride, float (&acc)[FL_CO]) {
+#pragma unroll
+  for (int c = 0; c < FL_CO; ++c) acc[c] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const TX* xp = x + ((long long)n * Cin + ci) * H * W;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = ho * stride - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = wo * stride - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        const float xv = to_f<TX>(xp[(long long)ih * W + iw]);
+        const float* wr = ws + (ci * 9 + r * 3 + s) * FL_CO;
+#pragma unroll
+        for (int c = 0; c < FL_CO; ++c) acc[c] += xv * wr[c];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void load_first_weights(float* ws, const float* __restrict__ w, int Cin, int Cout, int co0) {
+  for (int i = threadIdx.x; i < Cin * 9 * FL_CO; i += blockDim.x) {
+    int c = i % FL_CO, t = i / FL_CO;  // t = ci*9 + tap
+    int co = co0 + c;
+    ws[i] = co < Cout ? w[(long long)co * Cin * 9 + t] : 0.f;
+  }
+}
+
+template <typename TX, typename T>
+__global__ void __launch_bounds__(FL_THREADS) conv_first_fwd_kernel(
+    const TX* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
+    int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int stride, FwdEpi ep) {
+  __shared__ float ws[3 * 9 * FL_CO];
+  __shared__ float ssum[FL_CO], ssq[FL_CO];
+  const int co0 = blockIdx.y * FL_CO, n = blockIdx.z;
+  load_first_weights(ws, w, Cin, Cout, co0);
+  if (threadIdx.x < FL_CO) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int p = blockIdx.x * FL_THREADS + threadIdx.x;
+  const bool valid = p < Ho * Wo;
+  float acc[FL_CO];
+  if (valid) first_conv_pixel<TX>(x, ws, n, p / Wo, p % Wo, H, W, Cin, stride, acc);
+  else {
+#pragma unroll
+    for (int c = 0; c < FL_CO; ++c) acc[c] = 0.f;
+  }
+  float v[FL_CO];
+#pragma unroll
+  for (int c = 0; c < FL_CO; ++c) {
+    const int co = co0 + c;
+    const float sc = (ep.scale && co < Cout) ? ep.scale[co] : 1.f;
+    const float sh = (ep.shift && co < Cout) ? ep.shift[co] : 0.f;
+    v[c] = valid ? acc[c] * sc + sh : 0.f;
+  }
+  if (ep.stats) {
+#pragma unroll
+    for (int c = 0; c < FL_CO; ++c) {
+      float s1 = warp_sum(v[c]), s2 = warp_sum(v[c] * v[c]);
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&ssum[c], s1); atomicAdd(&ssq[c], s2); }
+    }
+    __syncthreads();
+    if (threadIdx.x < FL_CO && co0 + threadIdx.x < Cout) {
+      atomicAdd(&ep.stats[co0 + threadIdx.x], (double)ssum[threadIdx.x]);
+      atomicAdd(&ep.stats[Cout + co0 + threadIdx.x], (double)ssq[threadIdx.x]);
+    }
+  }
+  if (y && valid) {
+    const long long o = ((long long)n * Ho * Wo + p) * Cout + co0;
+#pragma unroll
+    for (int c = 0; c < FL_CO; ++c) {
+      const int co = co0 + c;
+      if (co < Cout) {
+        const float ds = ep.dropscale ? ep.dropscale[(long long)n * Cout + co] : 1.f;
+        if (ep.preact) ((T*)ep.preact)[o + c] = from_f<T>(v[c]);
+        y[o + c] = from_f<T>(act_fwd(v[c], ep.act) * ds);
+      }
+    }
+  }
+}
+
+// Backward.  mode 0: accumulate BN sums (sum g, sum g*xhat).  mode 1: weight gradient partials.
+// One block = (co chunk, ci) pair looping over pixels with a grid stride.
+template <typename TX, typename T, int MODE>
+__global__ void __launch_bounds__(FL_THREADS) conv_first_bwd_kernel(
+    const TX* __restrict__ x, const float* __restrict__ w, const T* __restrict__ da,
+    int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int stride, BwdEpi be,
+    const float* __restrict__ fwd_shift, const float* __restrict__ dy_mean, const float* __restrict__ dyx_mean,
+    float* __restrict__ partial, int nchunks) {
+  __shared__ float ws[3 * 9 * FL_CO];
+  __shared__ float red[9 * FL_CO + FL_CO];
+  const int chunk = blockIdx.y % nchunks, ci_sel = blockIdx.y / nchunks;
+  const int co0 = chunk * FL_CO;
+  load_first_weights(ws, w, Cin, Cout, co0);
+  for (int i = threadIdx.x; i < 9 * FL_CO + FL_CO; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  float wacc[MODE == 1 ? 9 : 1][FL_CO];
+  float s1[FL_CO], s2[FL_CO];
+#pragma unroll
+  for (int c = 0; c < FL_CO; ++c) {
+    s1[c] = 0.f; s2[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < (MODE == 1 ? 9 : 1); ++t) wacc[t][c] = 0.f;
+  }
+  float scl[FL_CO], sft[FL_CO], mean[FL_CO], istd[FL_CO], m1[FL_CO], m2[FL_CO], fsh[FL_CO];
+#pragma unroll
+  for (int c = 0; c < FL_CO; ++c) {
+    const int co = co0 + c;
+    const bool ok = co < Cout;
+    scl[c] = (be.bn_scale && ok) ? be.bn_scale[co] : 1.f;
+    sft[c] = (be.bn_shift && ok) ? be.bn_shift[co] : 0.f;
+    mean[c] = (be.bn_mean && ok) ? be.bn_mean[co] : 0.f;
+    istd[c] = (be.bn_invstd && ok) ? be.bn_invstd[co] : 1.f;
+    m1[c] = (dy_mean && ok) ? dy_mean[co] : 0.f;
+    m2[c] = (dyx_mean && ok) ? dyx_mean[co] : 0.f;
+    fsh[c] = (fwd_shift && ok) ? fwd_shift[co] : 0.f;
+  }
+  const long long total = (long long)N * Ho * Wo;
+  for (long long q = (long long)blockIdx.x * FL_THREADS + threadIdx.x; q < total;
+       q += (long long)gridDim.x * FL_THREADS) {
+    const int n = (int)(q / ((long long)Ho * Wo));
+    const int p = (int)(q % ((long long)Ho * Wo));
+    const int ho = p / Wo, wo = p % Wo;
+    float acc[FL_CO];
+    first_conv_pixel<TX>(x, ws, n, ho, wo, H, W, Cin, stride, acc);
+    float dzv[FL_CO];
+    const long long o = q * Cout + co0;
+#pragma unroll
+    for (int c = 0; c < FL_CO; ++c) {
+      const int co = co0 + c;
+      float g = 0.f, xhat = 0.f;
+      if (co < Cout) {
+        g = to_f<T>(da[o + c]);
+        if (be.dropscale) g *= be.dropscale[(long long)n * Cout + co];
+        const float yv = acc[c] + fsh[c];           // conv output (+bias when no BN)
+        float pre = yv;
+        if (be.bn_scale) { pre = yv * scl[c] + sft[c]; xhat = (yv - mean[c]) * istd[c]; }
+        g *= act_grad(pre, be.act);
+      }
+      if (MODE == 0) { s1[c] += g; s2[c] += g * xhat; }
+      else {
+        // BN backward: dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); scl = gamma*invstd
+        dzv[c] = be.bn_scale ? scl[c] * (g - m1[c] - xhat * m2[c]) : g;
+        s1[c] += dzv[c];
+      }
+    }
+    if (MODE == 1) {
+      const TX* xp = x + ((long long)n * Cin + ci_sel) * H * W;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int ih = ho * stride - 1 + r;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int iw = wo * stride - 1 + s;
+          float xv = 0.f;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) xv = to_f<TX>(xp[(long long)ih * W + iw]);
+#pragma unroll
+          for (int c = 0; c < FL_CO; ++c) wacc[r * 3 + s][c] += dzv[c] * xv;
+        }
+      }
+    }
+  }
+  // block reduction -> partials
+#pragma unroll
+  for (int c = 0; c < FL_CO; ++c) {
+    float a = warp_sum(s1[c]);
+    float b = MODE == 0 ? warp_sum(s2[c]) : 0.f;
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&red[9 * FL_CO + c], a);
+      if (MODE == 0) atomicAdd(&red[c], b);
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float v = warp_sum(wacc[t][c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&red[t * FL_CO + c], v);
+      }
+    }
+  }
+  __syncthreads();
+  if (MODE == 0) {
+    if (threadIdx.x < FL_CO && co0 + threadIdx.x < Cout && ci_sel == 0) {
+      atomicAdd(&be.bn_sums[co0 + threadIdx.x], (double)red[9 * FL_CO + threadIdx.x]);
+      atomicAdd(&be.bn_sums[Cout + co0 + threadIdx.x], (double)red[threadIdx.x]);
+    }
+  } else {
+    // partial layout per slice (= blockIdx.x): [Cout][Cin][9] then [Cout]
+    float* base = partial + (long long)blockIdx.x * ((long long)Cout * Cin * 9 + Cout);
+    for (int i = threadIdx.x; i < 9 * FL_CO; i += blockDim.x) {
+      const int c = i % FL_CO, t = i / FL_CO;
+      if (co0 + c < Cout) base[((long long)(co0 + c) * Cin + ci_sel) * 9 + t] = red[i];
+    }
+    if (threadIdx.x < FL_CO && co0 + threadIdx.x < Cout && ci_sel == 0)
+      base[(long long)Cout * Cin * 9 + co0 + threadIdx.x] = red[9 * FL_CO + threadIdx.x];
+  }
+}
+
+__global__ void wgrad_reduce_kernel2(const float* __restrict__ partial, float* __restrict__ dw,
+                                     float* __restrict__ dbias, long long nw, int Cout, int slices, float clip) {
+  const long long stride_slice = nw + Cout;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw + Cout) return;
+  float s = 0.f;
+  for (int k = 0; k < slices; ++k) s += partial[k * stride_slice + i];
+  s = clampf(s, clip);
+  if (i < nw) dw[i] = s;
+  else if (dbias) dbias[i - nw] = s;
+}
+
+constexpr int FL_BWD_BLOCKS = 296;
+
+}  // namespace yg
+
+using namespace yg;
+
+extern "C" int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, void* y, int dtype,
+                                 int N, int H, int W, int Cin, int Cout, int stride,
+                                 const yg_fwd_epilogue* epp, void* stream) {
+  YG_CHECK_ARG(x && w, "conv_first_fwd: null pointer");
+  YG_CHECK_ARG(Cin >= 1 && Cin <= 3, "conv_first_fwd: Cin must be 1..3, got %d", Cin);
+  YG_CHECK_ARG(stride == 1 || stride == 2, "conv_first_fwd: stride %d", stride);
+  YG_CHECK_ARG(x_dtype == YG_U8 || x_dtype == YG_F32, "conv_first_fwd: x_dtype %d", x_dtype);
+  YG_CHECK_ARG(dtype == YG_F32 || dtype == YG_BF16, "conv_first_fwd: dtype %d", dtype);
+  if (N == 0) return YG_OK;
+  FwdEpi ep = make_fwd_epi(epp);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  dim3 grid(cdiv((long long)Ho * Wo, FL_THREADS), cdiv(Cout, FL_CO), N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(TX, T) conv_first_fwd_kernel<TX, T><<<grid, FL_THREADS, 0, st>>>((const TX*)x, w, (T*)y, N, H, W, Cin, Ho, Wo, Cout, stride, ep)
+  if (x_dtype == YG_U8) { if (dtype == YG_BF16) LAUNCH(uint8_t, bf16); else LAUNCH(uint8_t, float); }
+  else { if (dtype == YG_BF16) LAUNCH(float, bf16); else LAUNCH(float, float); }
+#undef LAUNCH
+  YG_LAUNCH_CHECK("conv_first_fwd");
+  return YG_OK;
+}
+
+extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, const void* da, int dtype,
+                                 int N, int H, int W, int Cin, int Cout, int stride,
+                                 const yg_bwd_epilogue* bep, const float* fwd_shift,
+                                 const float* bn_dy_mean, const float* bn_dyx_mean,
+                                 float* dw, float* dshift, float clip, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  YG_CHECK_ARG(x && w && da, "conv_first_bwd: null pointer");
+  YG_CHECK_ARG(Cin >= 1 && Cin <= 3, "conv_first_bwd: Cin must be 1..3, got %d", Cin);
+  YG_CHECK_ARG(x_dtype == YG_U8 || x_dtype == YG_F32, "conv_first_bwd: x_dtype %d", x_dtype);
+  if (N == 0) return YG_OK;
+  BwdEpi be = make_bwd_epi(bep);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int nchunks = cdiv(Cout, FL_CO);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = dw ? 1 : 0;
+  YG_CHECK_ARG(mode == 1 || be.bn_sums, "conv_first_bwd: pass 1 needs bn_sums");
+  long long total = (long long)N * Ho * Wo;
+  int blocks = (int)((total + FL_THREADS - 1) / FL_THREADS);
+  if (blocks > FL_BWD_BLOCKS) blocks = FL_BWD_BLOCKS;
+  const long long nw = (long long)Cout * Cin * 9;
+  if (mode == 1) {
+    size_t need = (size_t)blocks * (nw + Cout) * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("conv_first_bwd: workspace %zu < %zu", workspace_bytes, need);
+      return YG_ERR_WORKSPACE;
+    }
+  }
+  dim3 grid(blocks, nchunks * (mode == 1 ? Cin : 1), 1);
+#define LAUNCH(TX, T, M) conv_first_bwd_kernel<TX, T, M><<<grid, FL_THREADS, 0, st>>>((const TX*)x, w, (const T*)da, N, H, W, Cin, Ho, Wo, Cout, stride, be, fwd_shift, bn_dy_mean, bn_dyx_mean, (float*)workspace, nchunks)
+#define LAUNCH_M(TX, T) do { if (mode == 1) LAUNCH(TX, T, 1); else LAUNCH(TX, T, 0); } while (0)
+  if (x_dtype == YG_U8) { if (dtype == YG_BF16) LAUNCH_M(uint8_t, bf16); else LAUNCH_M(uint8_t, float); }
+  else { if (dtype == YG_BF16) LAUNCH_M(float, bf16); else LAUNCH_M(float, float); }
+#undef LAUNCH_M
+#undef LAUNCH
+  YG_LAUNCH_CHECK("conv_first_bwd");
+  if (mode == 1) {
+    wgrad_reduce_kernel2<<<cdiv(nw + Cout, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, blocks, clip);
+    YG_LAUNCH_CHECK("conv_first_bwd reduce");
+  }
+  return YG_OK;
+}
+
+extern "C" size_t yg_conv_first_bwd_workspace(int Cin, int Cout) {
+  return (size_t)FL_BWD_BLOCKS * ((size_t)Cout * Cin * 9 + Cout) * sizeof(float);
+}

@@ -1,0 +1,272 @@
+// The 1x1 prediction head fused with YOGO.forward's output transform, and its backward.
+// Replaces nn.Conv2d(C4, 5+num_classes, 1) (/root/reference/yogo/model_defns.py:67) and the
+// ~12 elementwise kernels + torch.cat of /root/reference/yogo/model.py:277-313.
+// HBM-bound (K = Cin, N = 5+C = 12): reads the NHWC feature map once, writes the fp32 NCHW
+// prediction tensor once.
+#include "common.cuh"
+
+namespace yg {
+
+constexpr int HD_PX = 128;   // pixels per block
+constexpr int HD_KC = 32;    // input channels per smem chunk
+
+template <typename T, int DMAX>
+__global__ void __launch_bounds__(HD_PX) head_fwd_kernel(
+    const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    float* __restrict__ out, float* __restrict__ t_raw, long long npix, int Sy, int Sx, int Cin, int D,
+    float anchor_w, float anchor_h, float wmul, float hmul, int inference,
+    const float* __restrict__ cxs, const float* __restrict__ cys) {
+  extern __shared__ float smem[];
+  float* wsm = smem;                       // [D][Cin]
+  float* xs = smem + (size_t)D * Cin;      // [HD_KC][HD_PX + 1]
+  for (int i = threadIdx.x; i < D * Cin; i += HD_PX) wsm[i] = w[i];
+  const long long p0 = (long long)blockIdx.x * HD_PX;
+  const long long p = p0 + threadIdx.x;
+  float acc[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) acc[d] = (d < D && bias) ? bias[d] : 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += HD_KC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < HD_PX * HD_KC; i += HD_PX) {
+      const int c = i % HD_KC, pp = i / HD_KC;
+      const long long q = p0 + pp;
+      float v = 0.f;
+      if (q < npix && c0 + c < Cin) v = to_f<T>(x[q * Cin + c0 + c]);
+      xs[c * (HD_PX + 1) + pp] = v;
+    }
+    __syncthreads();
+    const int kc = min(HD_KC, Cin - c0);
+    for (int c = 0; c < kc; ++c) {
+      const float xv = xs[c * (HD_PX + 1) + threadIdx.x];
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d)
+        if (d < D) acc[d] += xv * wsm[d * Cin + c0 + c];
+    }
+  }
+  if (p >= npix) return;
+  const int SS = Sy * Sx;
+  const int n = (int)(p / SS), cell = (int)(p % SS);
+  const int j = cell / Sx, i = cell % Sx;
+  if (t_raw) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+      if (d < D) t_raw[p * D + d] = acc[d];
+  }
+  float* o = out + (long long)n * D * SS + cell;
+  // model.py:295-313.  _Cxs[j,i] = linspace(0, 1-1/Sx, Sx)[i] (model.py:48)
+  // the _Cxs/_Cys buffers of the module are used when given (they are part of the state_dict)
+  const float cx = cxs ? cxs[cell] : (Sx > 1 ? (float)i * ((1.f - 1.f / (float)Sx) / (float)(Sx - 1)) : 0.f);
+  const float cy = cys ? cys[cell] : (Sy > 1 ? (float)j * ((1.f - 1.f / (float)Sy) / (float)(Sy - 1)) : 0.f);
+  o[0] = (1.f / (float)Sx) * sigmoidf_(acc[0]) + cx;
+  o[(long long)SS] = (1.f / (float)Sy) * sigmoidf_(acc[1]) + cy;
+  o[2LL * SS] = anchor_w * expf(fminf(acc[2], 80.f)) * wmul;
+  o[3LL * SS] = anchor_h * expf(fminf(acc[3], 80.f)) * hmul;
+  o[4LL * SS] = sigmoidf_(acc[4]);
+  if (inference) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int d = 5; d < DMAX; ++d)
+      if (d < D) mx = fmaxf(mx, acc[d]);
+    float se = 0.f;
+#pragma unroll
+    for (int d = 5; d < DMAX; ++d)
+      if (d < D) { acc[d] = expf(acc[d] - mx); se += acc[d]; }
+    const float inv = 1.f / se;
+#pragma unroll
+    for (int d = 5; d < DMAX; ++d)
+      if (d < D) o[(long long)d * SS] = acc[d] * inv;
+  } else {
+#pragma unroll
+    for (int d = 5; d < DMAX; ++d)
+      if (d < D) o[(long long)d * SS] = acc[d];
+  }
+}
+
+// Backward.  Persistent blocks loop over 128-pixel tiles:
+//   dt[p][d] from dpred and the raw logits (model.py:287-313 differentiated);
+//   dx[p][ci] = sum_d dt[p][d] w[d][ci]  (+ the previous block's backward epilogue);
+//   dw[d][ci] += sum_p dt[p][d] x[p][ci], dbias[d] += sum_p dt[p][d]  (per-block partials).
+template <typename T, int DMAX>
+__global__ void __launch_bounds__(HD_PX) head_bwd_kernel(
+    const float* __restrict__ dpred, const float* __restrict__ t_raw, const T* __restrict__ x,
+    const float* __restrict__ w, T* __restrict__ dx, float* __restrict__ partial,
+    long long npix, int Sy, int Sx, int Cin, int D, float anchor_w, float anchor_h, float wmul, float hmul,
+    BwdEpi be) {
+  extern __shared__ float smem[];
+  float* wsm = smem;                               // [D][Cin]
+  float* dts = wsm + (size_t)D * Cin;              // [HD_PX][DMAX]
+  float* xs = dts + (size_t)HD_PX * DMAX;          // [HD_PX][HD_KC + 1]
+  float* dwacc = xs + (size_t)HD_PX * (HD_KC + 1); // [D][Cin] + [D]
+  __shared__ float ssum[HD_KC], ssq[HD_KC];
+  for (int i = threadIdx.x; i < D * Cin; i += HD_PX) { wsm[i] = w[i]; dwacc[i] = 0.f; }
+  if (threadIdx.x < D) dwacc[D * Cin + threadIdx.x] = 0.f;
+  const int SS = Sy * Sx;
+  const long long ntiles = (npix + HD_PX - 1) / HD_PX;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long p0 = tile * HD_PX;
+    const long long p = p0 + threadIdx.x;
+    __syncthreads();
+    {
+      float dt[DMAX];
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) dt[d] = 0.f;
+      if (p < npix) {
+        const int n = (int)(p / SS), cell = (int)(p % SS);
+        const float* g = dpred + (long long)n * D * SS + cell;
+        const float* t = t_raw + p * D;
+        const float s0 = sigmoidf_(t[0]), s1 = sigmoidf_(t[1]), s4 = sigmoidf_(t[4]);
+        dt[0] = g[0] * (1.f / (float)Sx) * s0 * (1.f - s0);
+        dt[1] = g[(long long)SS] * (1.f / (float)Sy) * s1 * (1.f - s1);
+        // clamp(max=80) passes gradient where t <= 80
+        dt[2] = t[2] <= 80.f ? g[2LL * SS] * anchor_w * expf(t[2]) * wmul : 0.f;
+        dt[3] = t[3] <= 80.f ? g[3LL * SS] * anchor_h * expf(t[3]) * hmul : 0.f;
+        dt[4] = g[4LL * SS] * s4 * (1.f - s4);
+#pragma unroll
+        for (int d = 5; d < DMAX; ++d)
+          if (d < D) dt[d] = g[(long long)d * SS];
+      }
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) dts[threadIdx.x * DMAX + d] = dt[d];
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {  // bias gradient
+      float s = 0.f;
+      for (int pp = 0; pp < HD_PX; ++pp) s += dts[pp * DMAX + threadIdx.x];
+      dwacc[D * Cin + threadIdx.x] += s;
+    }
+    for (int c0 = 0; c0 < Cin; c0 += HD_KC) {
+      const int kc = min(HD_KC, Cin - c0);
+      if (be.bn_sums && threadIdx.x < HD_KC) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
+      __syncthreads();
+      // stage x tile and produce dx for this channel chunk (coalesced over channels)
+      for (int i = threadIdx.x; i < HD_PX * HD_KC; i += HD_PX) {
+        const int c = i % HD_KC, pp = i / HD_KC;
+        const long long q = p0 + pp;
+        float xv = 0.f;
+        if (q < npix && c < kc) {
+          const int ci = c0 + c;
+          xv = to_f<T>(x[q * Cin + ci]);
+          float g = 0.f;
+#pragma unroll
+          for (int d = 0; d < DMAX; ++d)
+            if (d < D) g += dts[pp * DMAX + d] * wsm[d * Cin + ci];
+          if (dx) {
+            const int n = (int)(q / SS);
+            float xhat;
+            g = bwd_epi_apply<T>(be, g, q * Cin + ci, n, ci, Cin, xhat);
+            if (be.bn_sums) {
+              g = to_f<T>(from_f<T>(g));
+              atomicAdd(&ssum[c], g);
+              atomicAdd(&ssq[c], g * xhat);
+            }
+            dx[q * Cin + ci] = from_f<T>(g);
+          }
+        }
+        xs[pp * (HD_KC + 1) + c] = xv;
+      }
+      __syncthreads();
+      if (be.bn_sums && threadIdx.x < kc) {
+        atomicAdd(&be.bn_sums[c0 + threadIdx.x], (double)ssum[threadIdx.x]);
+        atomicAdd(&be.bn_sums[Cin + c0 + threadIdx.x], (double)ssq[threadIdx.x]);
+      }
+      // dw[d][c0 + c]: D*kc outputs over 128 threads
+      for (int o = threadIdx.x; o < D * kc; o += HD_PX) {
+        const int c = o % kc, d = o / kc;
+        float s = 0.f;
+#pragma unroll 8
+        for (int pp = 0; pp < HD_PX; ++pp) s += dts[pp * DMAX + d] * xs[pp * (HD_KC + 1) + c];
+        dwacc[d * Cin + c0 + c] += s;
+      }
+    }
+  }
+  __syncthreads();
+  float* base = partial + (long long)blockIdx.x * ((long long)D * Cin + D);
+  for (int i = threadIdx.x; i < D * Cin + D; i += HD_PX) base[i] = dwacc[i];
+}
+
+__global__ void head_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                   float* __restrict__ dbias, long long nw, int D, int slices, float clip) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw + D) return;
+  float s = 0.f;
+  for (int k = 0; k < slices; ++k) s += partial[k * (nw + D) + i];
+  s = clampf(s, clip);
+  if (i < nw) dw[i] = s;
+  else if (dbias) dbias[i - nw] = s;
+}
+
+constexpr int HD_BWD_BLOCKS = 296;
+
+}  // namespace yg
+using namespace yg;
+
+extern "C" int yg_head_fwd(const void* x, int dtype, const float* w, const float* bias, float* out, float* t_raw,
+                           int N, int Sy, int Sx, int Cin, int num_classes,
+                           float anchor_w, float anchor_h, float width_mult, float height_mult,
+                           int inference, const float* cxs, const float* cys, void* stream) {
+  const int D = 5 + num_classes;
+  YG_CHECK_ARG(x && w && out, "head_fwd: null pointer");
+  YG_CHECK_ARG(num_classes >= 1 && D <= 32, "head_fwd: 5+num_classes must be <= 32, got %d", D);
+  YG_CHECK_ARG(dtype == YG_F32 || dtype == YG_BF16, "head_fwd: dtype %d", dtype);
+  const long long npix = (long long)N * Sy * Sx;
+  if (npix == 0) return YG_OK;
+  const size_t smem = ((size_t)D * Cin + (size_t)HD_KC * (HD_PX + 1)) * sizeof(float);
+  YG_CHECK_ARG(smem <= 200 * 1024, "head_fwd: Cin %d too large", Cin);
+  const int blocks = cdiv(npix, HD_PX);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(T, DM)                                                                                        \
+  do {                                                                                                       \
+    YG_CUDA(cudaFuncSetAttribute(head_fwd_kernel<T, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    head_fwd_kernel<T, DM><<<blocks, HD_PX, smem, st>>>((const T*)x, w, bias, out, t_raw, npix, Sy, Sx, Cin, D, \
+                                                         anchor_w, anchor_h, width_mult, height_mult, inference, cxs, cys); \
+  } while (0)
+  if (dtype == YG_BF16) { if (D <= 16) LAUNCH(bf16, 16); else LAUNCH(bf16, 32); }
+  else { if (D <= 16) LAUNCH(float, 16); else LAUNCH(float, 32); }
+#undef LAUNCH
+  YG_LAUNCH_CHECK("head_fwd");
+  return YG_OK;
+}
+
+extern "C" size_t yg_head_bwd_workspace(int N, int Sy, int Sx, int Cin, int num_classes) {
+  const int D = 5 + num_classes;
+  return (size_t)HD_BWD_BLOCKS * ((size_t)D * Cin + D) * sizeof(float);
+}
+
+extern "C" int yg_head_bwd(const float* dpred, const float* t_raw, const void* x, const float* w, void* dx, int dtype,
+                           float* dw, float* dbias, int N, int Sy, int Sx, int Cin, int num_classes,
+                           float anchor_w, float anchor_h, float width_mult, float height_mult,
+                           const yg_bwd_epilogue* bep, float clip, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  const int D = 5 + num_classes;
+  YG_CHECK_ARG(dpred && t_raw && x && w && dw, "head_bwd: null pointer");
+  YG_CHECK_ARG(num_classes >= 1 && D <= 32, "head_bwd: 5+num_classes must be <= 32, got %d", D);
+  const long long npix = (long long)N * Sy * Sx;
+  const size_t need = yg_head_bwd_workspace(N, Sy, Sx, Cin, num_classes);
+  if (!workspace || workspace_bytes < need) {
+    set_error("head_bwd: workspace %zu < %zu", workspace_bytes, need);
+    return YG_ERR_WORKSPACE;
+  }
+  BwdEpi be = make_bwd_epi(bep);
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = cdiv(npix, HD_PX);
+  if (blocks > HD_BWD_BLOCKS) blocks = HD_BWD_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  const int DM = D <= 16 ? 16 : 32;
+  const size_t smem = ((size_t)D * Cin * 2 + D + (size_t)HD_PX * DM + (size_t)HD_PX * (HD_KC + 1)) * sizeof(float);
+  YG_CHECK_ARG(smem <= 200 * 1024, "head_bwd: Cin %d too large", Cin);
+#define LAUNCH(T, DMX)                                                                                        \
+  do {                                                                                                        \
+    YG_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, DMX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    head_bwd_kernel<T, DMX><<<blocks, HD_PX, smem, st>>>(dpred, t_raw, (const T*)x, w, (T*)dx, (float*)workspace, \
+                                                          npix, Sy, Sx, Cin, D, anchor_w, anchor_h, width_mult,  \
+                                                          height_mult, be);                                      \
+  } while (0)
+  if (dtype == YG_BF16) { if (DM == 16) LAUNCH(bf16, 16); else LAUNCH(bf16, 32); }
+  else { if (DM == 16) LAUNCH(float, 16); else LAUNCH(float, 32); }
+#undef LAUNCH
+  YG_LAUNCH_CHECK("head_bwd");
+  const long long nw = (long long)D * Cin;
+  head_reduce_kernel<<<cdiv(nw + D, 256), 256, 0, st>>>((const float*)workspace, dw, dbias, nw, D, blocks, clip);
+  YG_LAUNCH_CHECK("head_reduce");
+  return YG_OK;
+}

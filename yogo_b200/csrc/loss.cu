@@ -1,0 +1,200 @@
+// YOGOLoss forward + backward in one pass over the Sy x Sx prediction grid.
+// Replaces ~60 ATen launches, two boolean-mask gathers (host syncs) and torchvision's
+// box_convert / complete_box_iou_loss in /root/reference/yogo/yogo_loss.py:38-129
+// (torchvision/ops/ciou_loss.py, diou_loss.py, _utils.py::_loss_inter_union).
+// HBM-bound: reads (5+C)+6 floats per cell, writes 5+C floats of dpred; one thread per
+// cell, warp-shuffle + per-block partials, deterministic second-stage reduction.
+#include "common.cuh"
+
+namespace yg {
+
+constexpr int LS_THREADS = 256;
+constexpr int LS_MAXC = 27;  // 5 + C <= 32
+
+__device__ __forceinline__ float sel_gt(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
+__device__ __forceinline__ float sel_lt(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
+
+__global__ void __launch_bounds__(LS_THREADS) yogo_loss_kernel(
+    const float* __restrict__ pred, const float* __restrict__ label, float* __restrict__ dpred,
+    double* __restrict__ partial, int N, int C, int SS, float no_obj_w, float iou_w, float cls_w,
+    float smoothing) {
+  const long long cell = (long long)blockIdx.x * LS_THREADS + threadIdx.x;
+  const long long total = (long long)N * SS;
+  float l_iou = 0.f, l_obj = 0.f, l_cls = 0.f;
+  if (cell < total) {
+    const int n = (int)(cell / SS), k = (int)(cell % SS);
+    const int D = 5 + C;
+    const float* p = pred + (long long)n * D * SS + k;
+    const float* l = label + (long long)n * 6 * SS + k;
+    float* g = dpred ? dpred + (long long)n * D * SS + k : nullptr;
+    const float invN = 1.f / (float)N;
+    const float m = l[0];
+    // ---- objectness: (p4 - m)^2 * (m(1-lambda) + lambda)   (yogo_loss.py:116-119)
+    {
+      const float w = m * (1.f - no_obj_w) + no_obj_w;
+      const float d = p[4LL * SS] - m;
+      l_obj = d * d * w;
+      if (g) g[4LL * SS] = 2.f * d * w * invN;
+    }
+    // ---- classification: label-smoothed CE on raw logits, masked (yogo_loss.py:107-114)
+    {
+      float lg[LS_MAXC];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < LS_MAXC; ++c)
+        if (c < C) { lg[c] = p[(long long)(5 + c) * SS]; mx = fmaxf(mx, lg[c]); }
+      float se = 0.f, sl = 0.f;
+#pragma unroll
+      for (int c = 0; c < LS_MAXC; ++c)
+        if (c < C) { se += expf(lg[c] - mx); sl += lg[c]; }
+      const float lse = mx + logf(se);
+      int tgt = (int)l[5LL * SS];  // .long() truncation
+      tgt = tgt < 0 ? 0 : (tgt >= C ? C - 1 : tgt);
+      float lt = 0.f;
+#pragma unroll
+      for (int c = 0; c < LS_MAXC; ++c)
+        if (c == tgt) lt = lg[c];
+      const float nll = lse - lt;
+      const float smooth = lse - sl / (float)C;
+      l_cls = m * ((1.f - smoothing) * nll + smoothing * smooth);
+      if (g) {
+        const float f = m * cls_w * invN;
+#pragma unroll
+        for (int c = 0; c < LS_MAXC; ++c)
+          if (c < C) {
+            const float sm = expf(lg[c] - lse);
+            const float td = (c == tgt ? (1.f - smoothing) : 0.f) + smoothing / (float)C;
+            g[(long long)(5 + c) * SS] = f * (sm - td);
+          }
+      }
+    }
+    // ---- box term: CIoU on labelled cells (yogo_loss.py:59-105)
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    if (m != 0.f) {
+      const float p0 = p[0], p1 = p[(long long)SS], p2 = p[2LL * SS], p3 = p[3LL * SS];
+      const float X1 = l[(long long)SS], Y1 = l[2LL * SS], X2 = l[3LL * SS], Y2 = l[4LL * SS];
+      const float bx1 = p0 - 0.5f * p2, by1 = p1 - 0.5f * p3, bx2 = p0 + 0.5f * p2, by2 = p1 + 0.5f * p3;
+      if (bx1 != bx2 && by1 != by2) {  // tested before clamping (yogo_loss.py:84-90)
+        const float x1 = fminf(fmaxf(bx1, 0.f), 1.f), y1 = fminf(fmaxf(by1, 0.f), 1.f);
+        const float x2 = fminf(fmaxf(bx2, 0.f), 1.f), y2 = fminf(fmaxf(by2, 0.f), 1.f);
+        const float xk1 = fmaxf(x1, X1), yk1 = fmaxf(y1, Y1), xk2 = fminf(x2, X2), yk2 = fminf(y2, Y2);
+        const bool im = (yk2 > yk1) && (xk2 > xk1);
+        const float wI = xk2 - xk1, hI = yk2 - yk1;
+        const float inter = im ? wI * hI : 0.f;
+        const float wp = x2 - x1, hp = y2 - y1, wg = X2 - X1, hg = Y2 - Y1;
+        const float uni = wp * hp + wg * hg - inter;
+        const float eps = 1e-7f;
+        const float Ue = uni + eps;
+        const float iou = inter / Ue;
+        const float xc1 = fminf(x1, X1), yc1 = fminf(y1, Y1), xc2 = fmaxf(x2, X2), yc2 = fmaxf(y2, Y2);
+        const float cw = xc2 - xc1, ch = yc2 - yc1;
+        const float diag = cw * cw + ch * ch + eps;
+        const float xp = (x2 + x1) * 0.5f, yp = (y2 + y1) * 0.5f;
+        const float xg = (X1 + X2) * 0.5f, yg_ = (Y1 + Y2) * 0.5f;
+        const float dxc = xp - xg, dyc = yp - yg_;
+        const float cent = dxc * dxc + dyc * dyc;
+        const float kk = 0.40528473456935109f;  // 4 / pi^2
+        const float r = wp / hp;
+        const float dat = atanf(wg / hg) - atanf(r);
+        const float v = kk * dat * dat;
+        const float alpha = v / (1.f - iou + v + eps);  // no_grad
+        l_iou = 1.f - iou + cent / diag + alpha * v;
+        if (g) {
+          const float imf = im ? 1.f : 0.f;
+          float dI[4] = {-hI * sel_gt(x1, X1) * imf, -wI * sel_gt(y1, Y1) * imf,
+                         hI * sel_lt(x2, X2) * imf, wI * sel_lt(y2, Y2) * imf};
+          const float dA[4] = {-hp, -wp, hp, wp};
+          const float dD[4] = {-2.f * cw * sel_lt(x1, X1), -2.f * ch * sel_lt(y1, Y1),
+                               2.f * cw * sel_gt(x2, X2), 2.f * ch * sel_gt(y2, Y2)};
+          const float dC[4] = {dxc, dyc, dxc, dyc};
+          const float q = kk * 2.f * (-dat) * (1.f / (1.f + r * r));
+          const float dv_dw = q / hp, dv_dh = q * (-wp / (hp * hp));
+          const float dv[4] = {-dv_dw, -dv_dh, dv_dw, dv_dh};
+          const float raw[4] = {bx1, by1, bx2, by2};
+          float gg[4];
+          const float scale = iou_w * invN;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float dU = dA[i] - dI[i];
+            const float diou = (dI[i] * Ue - inter * dU) / (Ue * Ue);
+            float t = -diou + (dC[i] * diag - cent * dD[i]) / (diag * diag) + alpha * dv[i];
+            const bool pass = raw[i] >= 0.f && raw[i] <= 1.f;  // clamp backward
+            gg[i] = pass ? t * scale : 0.f;
+          }
+          d0 = gg[0] + gg[2];
+          d1 = gg[1] + gg[3];
+          d2 = 0.5f * (gg[2] - gg[0]);
+          d3 = 0.5f * (gg[3] - gg[1]);
+        }
+      }
+    }
+    if (g) { g[0] = d0; g[(long long)SS] = d1; g[2LL * SS] = d2; g[3LL * SS] = d3; }
+  }
+  // block reduction (double partials, deterministic order)
+  __shared__ double red[3][LS_THREADS / 32];
+  double a = warp_sum_d((double)l_iou), b = warp_sum_d((double)l_obj), c = warp_sum_d((double)l_cls);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = a; red[1][wid] = b; red[2][wid] = c; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0;
+    for (int i = 0; i < LS_THREADS / 32; ++i) s += red[threadIdx.x][i];
+    partial[(long long)blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void yogo_loss_finalize_kernel(const double* __restrict__ partial, int nblocks, float* out4, int N,
+                                          float iou_w, float cls_w) {
+  __shared__ double red[3][32];
+  double s[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+    s[0] += partial[(long long)i * 3];
+    s[1] += partial[(long long)i * 3 + 1];
+    s[2] += partial[(long long)i * 3 + 2];
+  }
+  for (int k = 0; k < 3; ++k) s[k] = warp_sum_d(s[k]);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = s[0]; red[1][wid] = s[1]; red[2][wid] = s[2]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[3] = {0, 0, 0};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t[0] += red[0][w]; t[1] += red[1][w]; t[2] += red[2][w]; }
+    const float iou = (float)(iou_w * t[0] / N);
+    const float obj = (float)(t[1] / N);
+    const float cls = (float)(cls_w * t[2] / N);
+    out4[0] = obj + iou + cls;  // yogo_loss.py:121
+    out4[1] = iou;
+    out4[2] = obj;
+    out4[3] = cls;
+  }
+}
+
+}  // namespace yg
+using namespace yg;
+
+extern "C" size_t yg_yogo_loss_workspace(int N, int Sy, int Sx) {
+  return (size_t)cdiv((long long)N * Sy * Sx, LS_THREADS) * 3 * sizeof(double) + 64;
+}
+
+extern "C" int yg_yogo_loss_fwd_bwd(const float* pred, const float* label, float* out4, float* dpred,
+                                    int N, int num_classes, int Sy, int Sx,
+                                    float no_obj_weight, float iou_weight, float classify_weight,
+                                    float label_smoothing, void* workspace, size_t workspace_bytes, void* stream) {
+  YG_CHECK_ARG(pred && label && out4, "yogo_loss: null pointer");
+  YG_CHECK_ARG(num_classes >= 1 && num_classes <= LS_MAXC, "yogo_loss: num_classes %d not in [1,%d]", num_classes, LS_MAXC);
+  YG_CHECK_ARG(N >= 1 && Sy >= 1 && Sx >= 1, "yogo_loss: empty batch or grid");
+  const size_t need = yg_yogo_loss_workspace(N, Sy, Sx);
+  if (!workspace || workspace_bytes < need) {
+    set_error("yogo_loss: workspace %zu < %zu", workspace_bytes, need);
+    return YG_ERR_WORKSPACE;
+  }
+  const int SS = Sy * Sx;
+  const int blocks = cdiv((long long)N * SS, LS_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  yogo_loss_kernel<<<blocks, LS_THREADS, 0, st>>>(pred, label, dpred, (double*)workspace, N, num_classes, SS,
+                                                  no_obj_weight, iou_weight, classify_weight, label_smoothing);
+  YG_LAUNCH_CHECK("yogo_loss");
+  yogo_loss_finalize_kernel<<<1, 256, 0, st>>>((const double*)workspace, blocks, out4, N, iou_weight, classify_weight);
+  YG_LAUNCH_CHECK("yogo_loss_finalize");
+  return YG_OK;
+}

@@ -1,0 +1,414 @@
+"""Plan compiler + executor: turns a YOGO backbone (an ``nn.Sequential`` produced by a
+``ModelDefn``) into a sequence of libyogo_b200 kernel launches, forward and backward.
+
+This replaces what ``self.model(x)`` + autograd + cuDNN do in the reference
+(/root/reference/yogo/model.py:275, model_defns.py:68-77).  PyTorch is used for memory
+(tensors, caching allocator), streams and RNG only; every FLOP runs in our CUDA kernels.
+
+Data layout in HBM: activations NHWC in ``compute_dtype`` (bf16 by default, fp32 for the
+tight-parity path); parameters stay fp32 OIHW ``nn.Parameter``s exactly as in the reference
+state_dict; the prediction tensor is fp32 NCHW (N, 5+C, Sy, Sx) as the reference returns it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+
+@dataclass
+class ConvBlock:
+    conv: nn.Conv2d
+    bn: Optional[nn.BatchNorm2d]
+    act: int
+    p_drop: float
+    cin: int
+    cout: int
+    ksize: int
+    stride: int
+    drop: Optional[nn.Dropout2d] = None
+
+
+@dataclass
+class Plan:
+    blocks: List[ConvBlock]
+    head: nn.Conv2d
+    params: List[nn.Parameter]  # in the order grads are returned
+
+
+def _unsupported(what: str) -> NotImplementedError:
+    return NotImplementedError(
+        f"yogo_b200: {what} cannot be compiled to the sm_100a kernel plan (supported: Conv2d 3x3 pad 1 / 1x1 "
+        "pad 0, stride 1|2, BatchNorm2d, LeakyReLU(0.01), SiLU, Dropout2d, final 1x1 Conv2d head)"
+    )
+
+
+def _check_conv(conv: nn.Conv2d) -> Tuple[int, int]:
+    k = conv.kernel_size
+    if k[0] != k[1] or k[0] not in (1, 3):
+        raise _unsupported(f"Conv2d kernel_size {k}")
+    s = conv.stride
+    if s[0] != s[1] or s[0] not in (1, 2):
+        raise _unsupported(f"Conv2d stride {s}")
+    pad = conv.padding
+    if isinstance(pad, str) or tuple(pad) != (k[0] // 2, k[0] // 2):
+        raise _unsupported(f"Conv2d padding {pad} with kernel {k}")
+    if tuple(conv.dilation) != (1, 1) or conv.groups != 1 or conv.padding_mode != "zeros":
+        raise _unsupported("dilated / grouped / non-zero-padded Conv2d")
+    return k[0], s[0]
+
+
+def compile_plan(model: nn.Module) -> Plan:
+    if not isinstance(model, nn.Sequential) or len(model) < 2:
+        raise _unsupported(f"backbone of type {type(model).__name__}")
+    children = list(model.children())
+    head = children[-1]
+    if not isinstance(head, nn.Conv2d) or head.kernel_size != (1, 1) or head.stride != (1, 1) or head.bias is None:
+        raise _unsupported("a backbone whose last module is not a biased 1x1 Conv2d head")
+    blocks: List[ConvBlock] = []
+    params: List[nn.Parameter] = []
+    for child in children[:-1]:
+        mods = list(child.children()) if isinstance(child, nn.Sequential) else [child]
+        if not mods or not isinstance(mods[0], nn.Conv2d):
+            raise _unsupported(f"block starting with {type(mods[0]).__name__ if mods else 'nothing'}")
+        conv = mods[0]
+        k, s = _check_conv(conv)
+        bn, act, p, drop = None, L.ACT_NONE, 0.0, None
+        stage = 1  # 1: expect bn/act/drop, 2: after bn, 3: after act, 4: after drop
+        for m in mods[1:]:
+            if isinstance(m, nn.BatchNorm2d) and stage == 1:
+                if not (m.affine and m.track_running_stats):
+                    raise _unsupported("BatchNorm2d without affine/running stats")
+                if m.momentum is None:
+                    raise _unsupported("BatchNorm2d(momentum=None)")
+                bn, stage = m, 2
+            elif isinstance(m, nn.LeakyReLU) and stage <= 2:
+                if abs(m.negative_slope - 0.01) > 1e-12:
+                    raise _unsupported(f"LeakyReLU slope {m.negative_slope}")
+                act, stage = L.ACT_LRELU, 3
+            elif isinstance(m, nn.SiLU) and stage <= 2:
+                act, stage = L.ACT_SILU, 3
+            elif isinstance(m, nn.Dropout2d) and stage <= 3:
+                p, stage, drop = float(m.p), 4, m
+            elif isinstance(m, nn.Identity):
+                continue
+            else:
+                raise _unsupported(f"module {type(m).__name__} at this position")
+        blocks.append(ConvBlock(conv, bn, act, p, conv.in_channels, conv.out_channels, k, s, drop))
+        params.append(conv.weight)
+        if conv.bias is not None:
+            params.append(conv.bias)
+        if bn is not None:
+            params += [bn.weight, bn.bias]
+    params += [head.weight, head.bias]
+    return Plan(blocks, head, params)
+
+
+def _out_hw(h: int, w: int, k: int, s: int) -> Tuple[int, int]:
+    pad = k // 2
+    return (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+
+
+def _fwd_ep(scale=None, shift=None, act=L.ACT_NONE, dropscale=None, stats=None, preact=None) -> L.FwdEpilogue:
+    return L.FwdEpilogue(L.ptr(scale), L.ptr(shift), act, L.ptr(dropscale), L.ptr(stats), L.ptr(preact))
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class Runner:
+    """Executes a Plan.  One instance per YOGO module; stateless between calls except for
+    scratch buffers."""
+
+    def __init__(self, owner):
+        self.owner = owner  # the YOGO module
+        self.plan = compile_plan(owner.model)
+        self.drop_keep_override: Optional[Dict[int, torch.Tensor]] = None  # tests inject masks here
+
+    # ---------------------------------------------------------------- helpers
+    def _dropscale(self, i: int, blk: ConvBlock, N: int, device, training: bool) -> Optional[torch.Tensor]:
+        if blk.p_drop <= 0 or not training:
+            return None
+        if self.drop_keep_override is not None and i in self.drop_keep_override:
+            keep = self.drop_keep_override[i].to(device=device, dtype=torch.float32)
+        else:
+            # Dropout2d: Bernoulli(1-p) per (n, c) plane (torch's Philox stream; the mask values
+            # cannot match the reference's draw, the distribution does)
+            keep = (torch.rand(N, blk.cout, device=device) >= blk.p_drop).float()
+        return (keep / (1.0 - blk.p_drop)).contiguous()
+
+    def _prep_input(self, x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        if x.ndim == 3:
+            x = x.unsqueeze(0)
+        if x.ndim != 4:
+            raise ValueError(f"expected (N,C,H,W) or (C,H,W) input, got shape {tuple(x.shape)}")
+        L.require_cuda(x, "YOGO input")
+        if x.dtype == torch.uint8:
+            code = L.YG_U8
+        else:
+            if x.dtype != torch.float32:
+                x = x.float()  # model.py:272-273
+            code = L.YG_F32
+        return x.contiguous(), code
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, x: torch.Tensor, want_grad: bool):
+        own = self.owner
+        lib = L.lib()
+        st = L.stream()
+        plan = self.plan
+        x, x_code = self._prep_input(x)
+        N, Cx, H, W = x.shape
+        dev = x.device
+        dt: torch.dtype = own.compute_dtype
+        dcode = L.dtype_code(dt)
+        if plan.blocks[0].cin != Cx:
+            raise RuntimeError(f"expected input with {plan.blocks[0].cin} channels, got {Cx}")
+        saved = {"x": x, "x_code": x_code, "blocks": [], "N": N, "dtype": dt}
+        cur: Optional[torch.Tensor] = None  # NHWC activation
+        h, w = H, W
+        for i, blk in enumerate(plan.blocks):
+            ho, wo = _out_hw(h, w, blk.ksize, blk.stride)
+            bn_train = blk.bn is not None and blk.bn.training
+            module_training = blk.drop.training if blk.drop is not None else False
+            ds = self._dropscale(i, blk, N, dev, module_training)
+            wt = _f32(blk.conv.weight)
+            bias = _f32(blk.conv.bias) if blk.conv.bias is not None else None
+            rec = {"in": cur, "h": h, "w": w, "ho": ho, "wo": wo, "dropscale": ds, "bn_train": bn_train}
+            first_direct = i == 0 and blk.ksize == 3 and blk.cin <= 3
+            rec["first_direct"] = first_direct
+            if i == 0 and not first_direct:
+                cur = x.permute(0, 2, 3, 1).contiguous().to(dt)  # plumbing: NCHW image -> NHWC
+                rec["in"] = cur
+            out = torch.empty((N, ho, wo, blk.cout), dtype=dt, device=dev)
+
+            def conv(ep: L.FwdEpilogue, y: Optional[torch.Tensor]):
+                if first_direct:
+                    L.check(lib.yg_conv_first_fwd(x.data_ptr(), x_code, wt.data_ptr(), L.ptr(y), dcode, N, h, w,
+                                                  blk.cin, blk.cout, blk.stride, C.byref(ep), st))
+                else:
+                    L.check(lib.yg_conv_fwd(cur.data_ptr(), wt.data_ptr(), L.ptr(y), dcode, N, h, w, blk.cin,
+                                            blk.cout, blk.ksize, blk.stride, C.byref(ep), st))
+
+            if blk.bn is None:
+                pre = None
+                if want_grad and blk.act == L.ACT_SILU:
+                    pre = torch.empty_like(out)
+                conv(_fwd_ep(shift=bias, act=blk.act, dropscale=ds, preact=pre), out)
+                rec["saved"] = pre if pre is not None else out
+            else:
+                bn = blk.bn
+                g, b = _f32(bn.weight), _f32(bn.bias)
+                if not want_grad and not bn_train:
+                    # inference: BN folded into the conv epilogue, nothing else touches HBM
+                    scale = torch.empty(blk.cout, dtype=torch.float32, device=dev)
+                    shift = torch.empty_like(scale)
+                    L.check(lib.yg_bn_fold_eval(g.data_ptr(), b.data_ptr(), bn.running_mean.data_ptr(),
+                                                bn.running_var.data_ptr(), L.ptr(bias), float(bn.eps),
+                                                scale.data_ptr(), shift.data_ptr(), blk.cout, st))
+                    conv(_fwd_ep(scale=scale, shift=shift, act=blk.act, dropscale=ds), out)
+                else:
+                    mean = torch.empty(blk.cout, dtype=torch.float32, device=dev)
+                    invstd, scale, shift = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
+                    if bn_train:
+                        stats = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                        y_raw = None if first_direct else torch.empty_like(out)
+                        conv(_fwd_ep(shift=bias, stats=stats), y_raw)  # pass 1: conv (+bias) and statistics
+                        L.check(lib.yg_bn_finalize(stats.data_ptr(), float(N * ho * wo), g.data_ptr(), b.data_ptr(),
+                                                   bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                                   float(bn.momentum), float(bn.eps), mean.data_ptr(),
+                                                   invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                   blk.cout, st))
+                        bn.num_batches_tracked += 1
+                    else:
+                        # BN in eval mode inside a training graph (tuning=True, model.py:69-70)
+                        L.check(lib.yg_bn_fold_eval(g.data_ptr(), b.data_ptr(), bn.running_mean.data_ptr(),
+                                                    bn.running_var.data_ptr(), None, float(bn.eps),
+                                                    scale.data_ptr(), shift.data_ptr(), blk.cout, st))
+                        mean.copy_(bn.running_mean)
+                        invstd.copy_(torch.rsqrt(bn.running_var + bn.eps))
+                        y_raw = None if first_direct else torch.empty_like(out)
+                        if y_raw is not None:
+                            conv(_fwd_ep(shift=bias), y_raw)
+                    if first_direct:
+                        # recompute the 9-tap stencil instead of storing the raw conv output
+                        sh2 = shift if bias is None else shift + bias * scale
+                        conv(_fwd_ep(scale=scale, shift=sh2, act=blk.act, dropscale=ds), out)
+                        rec["fwd_shift"] = bias
+                    else:
+                        L.check(lib.yg_bn_act_apply(y_raw.data_ptr(), out.data_ptr(), dcode, N, ho * wo, blk.cout,
+                                                    scale.data_ptr(), shift.data_ptr(), blk.act, L.ptr(ds), st))
+                    rec.update(saved=y_raw, mean=mean, invstd=invstd, scale=scale, shift=shift, gamma=g)
+            rec["out"] = out
+            saved["blocks"].append(rec)
+            cur = out
+            h, w = ho, wo
+        # head
+        D = plan.head.out_channels
+        nc = D - 5
+        outp = torch.empty((N, D, h, w), dtype=torch.float32, device=dev)
+        t_raw = torch.empty((N, h, w, D), dtype=torch.float32, device=dev) if want_grad else None
+        hw_ = _f32(plan.head.weight)
+        hb_ = _f32(plan.head.bias)
+        cxs = own._Cxs if own._Cxs.is_cuda and tuple(own._Cxs.shape) == (h, w) else None
+        cys = own._Cys if own._Cys.is_cuda and tuple(own._Cys.shape) == (h, w) else None
+        if cxs is not None:
+            cxs, cys = cxs.contiguous(), cys.contiguous()
+        L.check(lib.yg_head_fwd(cur.data_ptr(), dcode, hw_.data_ptr(), hb_.data_ptr(), outp.data_ptr(), L.ptr(t_raw),
+                                N, h, w, plan.head.in_channels, nc, float(own.anchor_w), float(own.anchor_h),
+                                float(own.width_multiplier), float(own.height_multiplier),
+                                1 if own.inference else 0, L.ptr(cxs), L.ptr(cys), st))
+        saved.update(t_raw=t_raw, head_in=cur, Sy=h, Sx=w, nc=nc,
+                     consts=(float(own.anchor_w), float(own.anchor_h), float(own.width_multiplier),
+                             float(own.height_multiplier)))
+        return outp, (saved if want_grad else None)
+
+    # ---------------------------------------------------------------- backward
+    def backward(self, saved, dpred: torch.Tensor) -> List[Optional[torch.Tensor]]:
+        own = self.owner
+        lib = L.lib()
+        st = L.stream()
+        plan = self.plan
+        N, dt = saved["N"], saved["dtype"]
+        dcode = L.dtype_code(dt)
+        dev = dpred.device
+        clip = float(own._clip_value_f)
+        recs = saved["blocks"]
+        grads: Dict[int, torch.Tensor] = {}
+        dpred = dpred.contiguous().float()
+
+        def bwd_ep(i: int) -> Tuple[Optional[L.BwdEpilogue], Optional[torch.Tensor]]:
+            """epilogue turning d(block i output) into d(conv i output) / d(BN i output)."""
+            blk, rec = plan.blocks[i], recs[i]
+            if rec["first_direct"]:
+                return None, None  # handled inside yg_conv_first_bwd (recomputation)
+            sums = None
+            if blk.bn is not None:
+                sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                ep = L.BwdEpilogue(rec["saved"].data_ptr(), blk.act, L.ptr(rec["dropscale"]),
+                                   rec["scale"].data_ptr(), rec["shift"].data_ptr(), rec["mean"].data_ptr(),
+                                   rec["invstd"].data_ptr(), sums.data_ptr())
+            else:
+                sv = rec["saved"] if blk.act != L.ACT_NONE else None
+                ep = L.BwdEpilogue(L.ptr(sv), blk.act, L.ptr(rec["dropscale"]), None, None, None, None, None)
+            return ep, sums
+
+        # ---- head
+        head = plan.head
+        Cl = head.in_channels
+        Sy, Sx, nc = saved["Sy"], saved["Sx"], saved["nc"]
+        aw, ah, wm, hm = saved["consts"]
+        last = len(plan.blocks) - 1
+        ep, sums = bwd_ep(last)
+        g = torch.empty((N, Sy, Sx, Cl), dtype=dt, device=dev)
+        dw_h = torch.empty_like(head.weight, dtype=torch.float32)
+        db_h = torch.empty_like(head.bias, dtype=torch.float32)
+        nbytes = lib.yg_head_bwd_workspace(N, Sy, Sx, Cl, nc)
+        ws = L.workspace.get("head_bwd", nbytes, dev)
+        L.check(lib.yg_head_bwd(dpred.data_ptr(), saved["t_raw"].data_ptr(), saved["head_in"].data_ptr(),
+                                _f32(head.weight).data_ptr(), g.data_ptr(), dcode, dw_h.data_ptr(), db_h.data_ptr(),
+                                N, Sy, Sx, Cl, nc, aw, ah, wm, hm, C.byref(ep) if ep is not None else None, clip,
+                                ws.data_ptr(), nbytes, st))
+        grads[id(head.weight)] = dw_h
+        grads[id(head.bias)] = db_h
+
+        # ---- conv blocks, last to first
+        for i in range(last, -1, -1):
+            blk, rec = plan.blocks[i], recs[i]
+            h, w, ho, wo = rec["h"], rec["w"], rec["ho"], rec["wo"]
+            wt = _f32(blk.conv.weight)
+            dw = torch.empty_like(wt)
+            db = torch.empty(blk.cout, dtype=torch.float32, device=dev) if blk.conv.bias is not None else None
+            if rec["first_direct"]:
+                x, x_code = saved["x"], saved["x_code"]
+                nb = lib.yg_conv_first_bwd_workspace(blk.cin, blk.cout)
+                ws = L.workspace.get("first_bwd", nb, dev)
+                m1 = m2 = None
+                if blk.bn is not None:
+                    sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                    ep1 = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), rec["scale"].data_ptr(),
+                                        rec["shift"].data_ptr(), rec["mean"].data_ptr(), rec["invstd"].data_ptr(),
+                                        sums.data_ptr())
+                    L.check(lib.yg_conv_first_bwd(x.data_ptr(), x_code, wt.data_ptr(), g.data_ptr(), dcode, N, h, w,
+                                                  blk.cin, blk.cout, blk.stride, C.byref(ep1), L.ptr(rec.get("fwd_shift")),
+                                                  None, None, None, None, clip, None, 0, st))
+                    dgam = torch.empty(blk.cout, dtype=torch.float32, device=dev)
+                    dbet = torch.empty_like(dgam)
+                    L.check(lib.yg_bn_bwd_apply(None, None, dcode, N, ho * wo, blk.cout, sums.data_ptr(),
+                                                rec["gamma"].data_ptr(), rec["mean"].data_ptr(),
+                                                rec["invstd"].data_ptr(), dgam.data_ptr(), dbet.data_ptr(), clip,
+                                                1, st))
+                    grads[id(blk.bn.weight)] = dgam
+                    grads[id(blk.bn.bias)] = dbet
+                    if rec["bn_train"]:
+                        M = float(N * ho * wo)
+                        m1 = (sums[: blk.cout] / M).float().contiguous()
+                        m2 = (sums[blk.cout :] / M).float().contiguous()
+                    ep2 = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), rec["scale"].data_ptr(),
+                                        rec["shift"].data_ptr(), rec["mean"].data_ptr(), rec["invstd"].data_ptr(), None)
+                else:
+                    ep2 = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), None, None, None, None, None)
+                L.check(lib.yg_conv_first_bwd(x.data_ptr(), x_code, wt.data_ptr(), g.data_ptr(), dcode, N, h, w,
+                                              blk.cin, blk.cout, blk.stride, C.byref(ep2), L.ptr(rec.get("fwd_shift") if blk.bn is not None else (_f32(blk.conv.bias) if blk.conv.bias is not None else None)),
+                                              L.ptr(m1), L.ptr(m2), dw.data_ptr(), L.ptr(db), clip, ws.data_ptr(), nb, st))
+                grads[id(blk.conv.weight)] = dw
+                if db is not None:
+                    grads[id(blk.conv.bias)] = db
+                continue
+            if blk.bn is not None:
+                dgam = torch.empty(blk.cout, dtype=torch.float32, device=dev)
+                dbet = torch.empty_like(dgam)
+                L.check(lib.yg_bn_bwd_apply(g.data_ptr(), rec["saved"].data_ptr(), dcode, N, ho * wo, blk.cout,
+                                            sums.data_ptr(), rec["gamma"].data_ptr(), rec["mean"].data_ptr(),
+                                            rec["invstd"].data_ptr(), dgam.data_ptr(), dbet.data_ptr(), clip,
+                                            1 if rec["bn_train"] else 0, st))
+                grads[id(blk.bn.weight)] = dgam
+                grads[id(blk.bn.bias)] = dbet
+            # g is now d(loss)/d(conv output of block i)
+            nb = lib.yg_conv_wgrad_workspace(N, h, w, blk.cin, blk.cout, blk.ksize, blk.stride)
+            ws = L.workspace.get("wgrad", nb, dev)
+            L.check(lib.yg_conv_wgrad(rec["in"].data_ptr(), g.data_ptr(), dw.data_ptr(), L.ptr(db), dcode, N, h, w,
+                                      blk.cin, blk.cout, blk.ksize, blk.stride, clip, ws.data_ptr(), nb, st))
+            grads[id(blk.conv.weight)] = dw
+            if db is not None:
+                grads[id(blk.conv.bias)] = db
+            if i > 0:
+                ep, sums = bwd_ep(i - 1)
+                gprev = torch.empty((N, h, w, blk.cin), dtype=dt, device=dev)
+                L.check(lib.yg_conv_dgrad(g.data_ptr(), wt.data_ptr(), gprev.data_ptr(), dcode, N, h, w, blk.cin,
+                                          blk.cout, blk.ksize, blk.stride, C.byref(ep) if ep is not None else None, st))
+                g = gprev
+        return [grads.get(id(p)) for p in plan.params]
+
+
+class _YOGOFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner: Runner, x: torch.Tensor, *params):
+        out, saved = runner.forward(x, want_grad=True)
+        ctx.runner = runner
+        ctx.saved = saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dpred):
+        grads = ctx.runner.backward(ctx.saved, dpred)
+        ctx.saved = None
+        return (None, None, *grads)
+
+
+def run(runner: Runner, x: torch.Tensor) -> torch.Tensor:
+    params = runner.plan.params
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if need_grad:
+        return _YOGOFunction.apply(runner, x, *params)
+    out, _ = runner.forward(x, want_grad=False)
+    return out
