@@ -172,7 +172,7 @@ def golden_nms(ref, out):
 GRAD_STRIDE = 5
 
 
-def _run_model(ref, name, sd_from, img, lab, train, inference=False, normalize=True):
+def _run_model(ref, name, sd_from, img, lab, train, inference=False, normalize=True, autocast=False):
     torch.manual_seed(0)
     H, W = img.shape[-2:]
     net = ref["YOGO"](
@@ -215,7 +215,15 @@ def _run_model(ref, name, sd_from, img, lab, train, inference=False, normalize=T
     x = img.float() / 255.0 if normalize else img.float()
     res = {}
     if train:
-        out = net(x)
+        if autocast:
+            # Dropout2d must draw the same masks as the fp32 run: same seed, same call order
+            torch.manual_seed(1234)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                out = net(x)
+            out = out.float()
+        else:
+            torch.manual_seed(1234)
+            out = net(x)
         loss, comps = ref["YOGOLoss"]()(out, lab)
         loss.backward()
         res["loss"] = np.array(
@@ -249,6 +257,20 @@ def golden_model(ref, out):
         cases["sd." + k] = v.numpy()
     for k, v in res.items():
         cases["base_train." + k] = v
+    # calibration of the bf16 tolerance: the reference's OWN bf16-autocast error against its fp32
+    # run on the same inputs, weights and dropout masks
+    for nm, pre in (("base_model", "base_train."), ("silu_model", "silu_train.")):
+        _, r32 = _run_model(ref, nm, sd_base, img, lab, train=True)
+        _, r16 = _run_model(ref, nm, sd_base, img, lab, train=True, autocast=True)
+        same_masks = all(np.array_equal(r32[k], r16[k]) for k in r32 if k.startswith("keep."))
+        assert same_masks, "dropout masks differ between fp32 and autocast runs"
+        def rel(a, b):
+            return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b.astype(np.float64)), 1e-3))
+        cases[pre + "bf16err.out"] = np.array([rel(r16["out"], r32["out"])])
+        cases[pre + "bf16err.loss"] = np.array([abs(r16["loss"][0] - r32["loss"][0]) / abs(r32["loss"][0])])
+        for k in r32:
+            if k.startswith("grad."):
+                cases[pre + "bf16err." + k] = np.array([rel(r16[k], r32[k])])
     _, res = _run_model(ref, "base_model", sd_base, img, lab, train=False)
     cases["base_eval.out"] = res["out"]
     _, res = _run_model(ref, "base_model", sd_base, img, lab, train=False, inference=True)

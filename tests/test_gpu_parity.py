@@ -296,9 +296,7 @@ def test_train_step_fp32_matches_reference_golden(golden_dir, fname, prefix, nam
 
 @pytest.mark.parametrize("name,prefix", [("base_model", "base_train."), ("silu_model", "silu_train.")])
 def test_train_step_bf16_within_calibrated_tolerance(golden_dir, name, prefix):
-    """bf16 storage path.  Bounds = ~1.5x the reference's own bf16-autocast error vs its fp32
-    (SURVEY.md Appendix E): loss 1e-3 relative, head outputs 3e-2 rel-L2, last-layer grads
-    2e-2, early layers 0.4 (random-init gradients are ill-conditioned through 5+ bf16 layers)."""
+    """bf16 storage path, tolerance calibrated per tensor from the reference."""
     z = _load(golden_dir, "model_base.npz")
     net, sd = _build_from_golden(z, name, dtype=torch.bfloat16)
     net.train()
@@ -309,18 +307,24 @@ def test_train_step_bf16_within_calibrated_tolerance(golden_dir, name, prefix):
     out = net(x)
     loss, comps = yogo_b200.YOGOLoss().to(DEV)(out, torch.from_numpy(z["label"]).to(DEV))
     loss.backward()
-    assert _rel(out.detach().cpu().numpy(), z[prefix + "out"]) < 3e-2
-    assert abs(loss.item() - z[prefix + "loss"][0]) < 2e-3 * abs(z[prefix + "loss"][0])
-    names = [k for k, _ in net.named_parameters()]
+    # acceptance: error vs the fp32 reference <= 1.5 x the reference's OWN bf16-autocast error on the
+    # same inputs/weights/masks (recorded by tests/golden/make_golden.py), with small floors
+    def bound(key, floor):
+        return max(1.5 * float(z[prefix + "bf16err." + key][0]), floor)
+
+    assert _rel(out.detach().cpu().numpy(), z[prefix + "out"]) < bound("out", 1e-2)
+    assert abs(loss.item() - z[prefix + "loss"][0]) < bound("loss", 1e-3) * abs(z[prefix + "loss"][0])
+    report = {}
     for k, p in net.named_parameters():
         g = p.grad.detach().cpu().numpy().reshape(-1)
         exp = z[prefix + "grad." + k]
         if g.size > 16384:
             g = g[::5]
-        late = k.startswith(("model.7", "model.6", "model.5"))
-        bound = 3e-2 if late else 0.4
         denom = max(float(np.linalg.norm(exp)), 1e-3)
-        assert float(np.linalg.norm(g - exp)) / denom < bound, (k, float(np.linalg.norm(g - exp)) / denom)
+        err = float(np.linalg.norm(g - exp)) / denom
+        report[k] = (err, bound("grad." + k, 2e-2))
+    bad = {k: v for k, v in report.items() if v[0] >= v[1]}
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 3e-2)])
