@@ -44,6 +44,8 @@ int yg_device_check(void);
  * shape qualifies, SIMT otherwise).  Used by the parity tests to cross-check both. */
 int yg_set_conv_impl(int impl);
 int yg_get_conv_impl(void);
+/* number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */
+unsigned long long yg_launch_count(void);
 
 /* ---- epilogue descriptor shared by the convolution entry points -------------------- */
 typedef struct {

@@ -59,6 +59,7 @@ _PROTOS = {
     "yg_device_check": (c_int, []),
     "yg_set_conv_impl": (c_int, [c_int]),
     "yg_get_conv_impl": (c_int, []),
+    "yg_launch_count": (C.c_ulonglong, []),
     "yg_conv_first_fwd": (
         c_int,
         [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(FwdEpilogue), c_void_p],

@@ -9,6 +9,7 @@
 namespace yg {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;  // kernels launched by this library (yg_launch_count)
 
 #define YG_CHECK_ARG(cond, ...)                 \
   do {                                          \
@@ -35,6 +36,7 @@ void set_error(const char* fmt, ...);
       yg::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));     \
       return YG_ERR_CUDA;                                                         \
     }                                                                             \
+    ++yg::g_launches;                                                             \
   } while (0)
 
 typedef __nv_bfloat16 bf16;

@@ -133,6 +133,10 @@ class Runner:
         self.owner = owner  # the YOGO module
         self.plan = compile_plan(owner.model)
         self.drop_keep_override: Optional[Dict[int, torch.Tensor]] = None  # tests inject masks here
+        # data-parallel trainer plumbing (yogo_b200.train): parameter gradients are written
+        # straight into views of a flat bucket, and a callback fires as each one is enqueued
+        self.grad_views: Optional[Dict[int, torch.Tensor]] = None
+        self.on_grad_ready = None
 
     # ---------------------------------------------------------------- helpers
     def _dropscale(self, i: int, blk: ConvBlock, N: int, device, training: bool) -> Optional[torch.Tensor]:
@@ -285,6 +289,17 @@ class Runner:
         recs = saved["blocks"]
         grads: Dict[int, torch.Tensor] = {}
         dpred = dpred.contiguous().float()
+        views = self.grad_views or {}
+
+        def gbuf(p: torch.Tensor) -> torch.Tensor:
+            v = views.get(id(p))
+            return v if v is not None else torch.empty(p.shape, dtype=torch.float32, device=dev)
+
+        def done(*ps):
+            if self.on_grad_ready is not None:
+                for p in ps:
+                    if p is not None:
+                        self.on_grad_ready(p)
 
         def bwd_ep(i: int) -> Tuple[Optional[L.BwdEpilogue], Optional[torch.Tensor]]:
             """epilogue turning d(block i output) into d(conv i output) / d(BN i output)."""
@@ -310,8 +325,8 @@ class Runner:
         last = len(plan.blocks) - 1
         ep, sums = bwd_ep(last)
         g = torch.empty((N, Sy, Sx, Cl), dtype=dt, device=dev)
-        dw_h = torch.empty_like(head.weight, dtype=torch.float32)
-        db_h = torch.empty_like(head.bias, dtype=torch.float32)
+        dw_h = gbuf(head.weight)
+        db_h = gbuf(head.bias)
         nbytes = lib.yg_head_bwd_workspace(N, Sy, Sx, Cl, nc)
         ws = L.workspace.get("head_bwd", nbytes, dev)
         L.check(lib.yg_head_bwd(dpred.data_ptr(), saved["t_raw"].data_ptr(), saved["head_in"].data_ptr(),
@@ -320,14 +335,15 @@ class Runner:
                                 ws.data_ptr(), nbytes, st))
         grads[id(head.weight)] = dw_h
         grads[id(head.bias)] = db_h
+        done(head.weight, head.bias)
 
         # ---- conv blocks, last to first
         for i in range(last, -1, -1):
             blk, rec = plan.blocks[i], recs[i]
             h, w, ho, wo = rec["h"], rec["w"], rec["ho"], rec["wo"]
             wt = _f32(blk.conv.weight)
-            dw = torch.empty_like(wt)
-            db = torch.empty(blk.cout, dtype=torch.float32, device=dev) if blk.conv.bias is not None else None
+            dw = gbuf(blk.conv.weight)
+            db = gbuf(blk.conv.bias) if blk.conv.bias is not None else None
             if rec["first_direct"]:
                 x, x_code = saved["x"], saved["x_code"]
                 nb = lib.yg_conv_first_bwd_workspace(blk.cin, blk.cout)
@@ -341,8 +357,8 @@ class Runner:
                     L.check(lib.yg_conv_first_bwd(x.data_ptr(), x_code, wt.data_ptr(), g.data_ptr(), dcode, N, h, w,
                                                   blk.cin, blk.cout, blk.stride, C.byref(ep1), L.ptr(rec.get("fwd_shift")),
                                                   None, None, None, None, clip, None, 0, st))
-                    dgam = torch.empty(blk.cout, dtype=torch.float32, device=dev)
-                    dbet = torch.empty_like(dgam)
+                    dgam = gbuf(blk.bn.weight)
+                    dbet = gbuf(blk.bn.bias)
                     L.check(lib.yg_bn_bwd_apply(None, None, dcode, N, ho * wo, blk.cout, sums.data_ptr(),
                                                 rec["gamma"].data_ptr(), rec["mean"].data_ptr(),
                                                 rec["invstd"].data_ptr(), dgam.data_ptr(), dbet.data_ptr(), clip,
@@ -363,10 +379,12 @@ class Runner:
                 grads[id(blk.conv.weight)] = dw
                 if db is not None:
                     grads[id(blk.conv.bias)] = db
+                done(blk.conv.weight, blk.conv.bias, blk.bn.weight if blk.bn is not None else None,
+                     blk.bn.bias if blk.bn is not None else None)
                 continue
             if blk.bn is not None:
-                dgam = torch.empty(blk.cout, dtype=torch.float32, device=dev)
-                dbet = torch.empty_like(dgam)
+                dgam = gbuf(blk.bn.weight)
+                dbet = gbuf(blk.bn.bias)
                 L.check(lib.yg_bn_bwd_apply(g.data_ptr(), rec["saved"].data_ptr(), dcode, N, ho * wo, blk.cout,
                                             sums.data_ptr(), rec["gamma"].data_ptr(), rec["mean"].data_ptr(),
                                             rec["invstd"].data_ptr(), dgam.data_ptr(), dbet.data_ptr(), clip,
@@ -381,13 +399,16 @@ class Runner:
             grads[id(blk.conv.weight)] = dw
             if db is not None:
                 grads[id(blk.conv.bias)] = db
+            done(blk.conv.weight, blk.conv.bias, blk.bn.weight if blk.bn is not None else None,
+                 blk.bn.bias if blk.bn is not None else None)
             if i > 0:
                 ep, sums = bwd_ep(i - 1)
                 gprev = torch.empty((N, h, w, blk.cin), dtype=dt, device=dev)
                 L.check(lib.yg_conv_dgrad(g.data_ptr(), wt.data_ptr(), gprev.data_ptr(), dcode, N, h, w, blk.cin,
                                           blk.cout, blk.ksize, blk.stride, C.byref(ep) if ep is not None else None, st))
                 g = gprev
-        return [grads.get(id(p)) for p in plan.params]
+        # gradients already written into trainer-owned views are not returned through autograd
+        return [None if id(p) in views else grads.get(id(p)) for p in plan.params]
 
 
 class _YOGOFunction(torch.autograd.Function):
