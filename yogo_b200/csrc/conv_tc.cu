@@ -1,12 +1,712 @@
-// tcgen05 implicit-GEMM convolution engine (placeholder until the engine lands: reports
-// "unsupported" for every shape so that dispatch goes to the SIMT kernels).
+// tcgen05 implicit-GEMM convolution engine for sm_100a (bf16 NHWC activations, fp32 accumulate).
+//
+// One persistent, warp-specialised kernel serves fprop and dgrad of the 3x3 convolutions
+// (replacing cuDNN fprop/dgrad dispatched by nn.Conv2d, /root/reference/yogo/model_defns.py:34-64):
+//   GEMM view   D[128 pixels x BN channels] += A[128 pixels x KC] * B[BN x KC]^T  per (tap, K chunk)
+//   A operand   an output tile is an 8x16 pixel patch; for filter column s the TMA fetches ONE
+//               (8+2)x16 halo box per K chunk (4-D tiled tensor map over the NHWC tensor, OOB zero
+//               fill = the conv padding) and the three filter rows r reuse it by offsetting the
+//               UMMA descriptor start by r*16 rows (swizzle-atom aligned).  Stride-2 convolutions
+//               use four parity sub-grids of the input (one tensor map each), stride-2 dgrad runs
+//               as four output-parity classes.
+//   B operand   packed bf16 weights [tap][N][K] through a 3-D tensor map.
+//   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN<=256, accumulators double-buffered
+//               in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   epilogue    tcgen05.ld 32x32b -> registers -> fused bias/BN-fold/activation/Dropout2d scale,
+//               BatchNorm batch statistics (fwd) or activation/BN backward + BN sums (dgrad),
+//               16-byte bf16 stores.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
 #include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
 namespace yg {
-bool tc_fwd_supported(int, int, int, int, int) { return false; }
-bool tc_dgrad_supported(int, int, int, int, int) { return false; }
+
+constexpr int TC_TH = 8, TC_TW = 16;          // output tile (pixels), M = 128
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_GROUPS = 9, TC_MAX_TAPS = 3;
+constexpr int TC_SMEM_BUDGET = 227 * 1024 - 6 * 1024;
+constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;   // bounded mbarrier spin: trap instead of hanging the GPU
+
+struct TcMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct TcGroup {
+  int map, dh, dw, rows, ntaps;
+  int ro[TC_MAX_TAPS];    // A row offset (in tile rows) of each tap inside the halo box
+  int widx[TC_MAX_TAPS];  // weight slice index
+};
+
+struct TcParams {
+  int N, TSH, TSW, tiles_h, tiles_w, n_ntiles, total_tiles;
+  int OH, OW, OC, os, oh0, ow0;   // output tensor (NHWC) and tile-space -> output mapping
+  int BN, kchunks, ngroups, nstages;
+  int a_stage_bytes, b_tap_bytes, tmem_cols;
+  TcGroup g[TC_MAX_GROUPS];
+  void* out;
+  // forward epilogue
+  const float* scale; const float* shift; int act; const float* dropscale; double* stats; void* preact;
+  // backward epilogue
+  const void* saved; const float* bn_scale; const float* bn_shift; const float* bn_mean; const float* bn_invstd;
+  double* bn_sums;
+  int* error_flag;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > TC_SPIN_LIMIT) {
+      if (error_flag) atomicExch(error_flag, code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled shared-memory matrix descriptor (sm_100 UMMA).  bits: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout [61,64) (2 = SWIZZLE_128B, 4 = 64B, 6 = 32B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// sum over the 32 lanes (= 32 pixels) of 16 per-lane values; afterwards lane l holds the total of
+// value index (l & 15) in v[0].  31 shuffles instead of 80.
+__device__ __forceinline__ float lane_transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int step = 8, n = 16; step >= 1; step >>= 1, n >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int KC, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+  constexpr uint32_t ROW_BYTES = KC * 2;
+  constexpr uint32_t SBO = 8 * ROW_BYTES;
+  constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
+  constexpr int KSTEPS = KC / 16;
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned stage bases: align by hand, do not trust the attribute
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = p.a_stage_bytes + TC_MAX_TAPS * p.b_tap_bytes;
+  unsigned char* tail = smem + (size_t)p.nstages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
+    prefetch_tmap(&maps.b);
+    for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // epilogue constants and statistics accumulators (the N tile is fixed per CTA only when n_ntiles == 1,
+  // so constants are indexed by absolute channel and reloaded per tile below when needed)
+  for (int i = threadIdx.x; i < 2 * 256; i += TC_THREADS) s_stat[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int items = p.kchunks * p.ngroups;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % p.n_ntiles; t /= p.n_ntiles;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int gi = 0; gi < p.ngroups; ++gi) {
+            const TcGroup& g = p.g[gi];
+            mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
+            unsigned char* sa = smem + (size_t)stage * stage_bytes;
+            unsigned char* sb = sa + p.a_stage_bytes;
+            const uint32_t bytes = (uint32_t)(g.rows * TC_TW * (int)ROW_BYTES + g.ntaps * p.b_tap_bytes);
+            mbar_expect_tx(&full_bar[stage], bytes);
+            tma_load_4d(sa, &maps.a[g.map], &full_bar[stage], kc * KC, tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
+            for (int tp = 0; tp < g.ntaps; ++tp)
+              tma_load_3d(sb + (size_t)tp * p.b_tap_bytes, &maps.b, &full_bar[stage], kc * KC, nt * BN, g.widx[tp]);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, p.error_flag, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      int item = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int gi = 0; gi < p.ngroups; ++gi, ++item) {
+          const TcGroup& g = p.g[gi];
+          mbar_wait(&full_bar[stage], phase, p.error_flag, 3);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + (uint32_t)p.a_stage_bytes;
+            for (int tp = 0; tp < g.ntaps; ++tp) {
+              const uint32_t a0 = sa + (uint32_t)(g.ro[tp] * TC_TW) * ROW_BYTES;
+              const uint32_t b0 = sb + (uint32_t)(tp * p.b_tap_bytes);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint64_t ad = umma_desc(a0 + k * 32, SBO, LAYOUT);
+                const uint64_t bd = umma_desc(b0 + k * 32, SBO, LAYOUT);
+                umma_bf16(d_tmem, ad, bd, idesc, (item > 0 || tp > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+            if (item == items - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          }
+          __syncwarp();
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    // ===================================================================== epilogue (4 warps)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;       // row of the tile = pixel
+    const int hl = m / TC_TW, wl = m % TC_TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bf16* out = reinterpret_cast<bf16*>(p.out);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int nt = t % p.n_ntiles; t /= p.n_ntiles;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int n = t / p.tiles_h;
+      const int a = th * TC_TH + hl, b = tw * TC_TW + wl;
+      const int oh = a * p.os + p.oh0, ow = b * p.os + p.ow0;
+      const bool valid = a < p.TSH && b < p.TSW && oh < p.OH && ow < p.OW;
+      const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
+      mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      for (int j = 0; j < BN / 16; ++j) {
+        uint32_t r[16];
+        tmem_ld16(taddr0 + (uint32_t)(j * 16), r);
+        tmem_ld_wait();
+        const int cl = j * 16;          // channel inside the N tile
+        const int c0 = nt * BN + cl;    // absolute output channel
+        __align__(16) bf16 ob[16];
+        if (MODE == 0) {
+          float s1[16], s2[16];
+          __align__(16) bf16 pb[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + i;
+            float x = __uint_as_float(r[i]);
+            x = x * (p.scale ? __ldg(p.scale + c) : 1.f) + (p.shift ? __ldg(p.shift + c) : 0.f);
+            if (p.stats || p.preact) x = round_bf16(x);
+            s1[i] = valid ? x : 0.f;
+            s2[i] = valid ? x * x : 0.f;
+            pb[i] = __float2bfloat16_rn(x);
+            x = act_fwd(x, p.act);
+            if (p.dropscale) x *= __ldg(p.dropscale + (long long)n * p.OC + c);
+            ob[i] = __float2bfloat16_rn(x);
+          }
+          if (valid) {
+            if (out) {
+              uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
+              dst[0] = reinterpret_cast<uint4*>(ob)[0];
+              dst[1] = reinterpret_cast<uint4*>(ob)[1];
+            }
+            if (p.preact) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.preact) + pix * p.OC + c0);
+              dst[0] = reinterpret_cast<uint4*>(pb)[0];
+              dst[1] = reinterpret_cast<uint4*>(pb)[1];
+            }
+          }
+          if (p.stats) {
+            const float t1 = lane_transpose_reduce16(s1, lane);
+            const float t2 = lane_transpose_reduce16(s2, lane);
+            if (lane < 16) {
+              atomicAdd(&s_stat[cl + lane], t1);
+              atomicAdd(&s_stat[256 + cl + lane], t2);
+            }
+          }
+        } else {
+          float s1[16], s2[16];
+          __align__(16) bf16 sv[16];
+          if (p.saved && valid) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
+            reinterpret_cast<uint4*>(sv)[0] = src[0];
+            reinterpret_cast<uint4*>(sv)[1] = src[1];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + i;
+            float g = __uint_as_float(r[i]);
+            if (p.dropscale) g *= __ldg(p.dropscale + (long long)n * p.OC + c);
+            float xhat = 0.f;
+            if (p.saved) {
+              const float s = __bfloat162float(sv[i]);
+              float pre = s;
+              if (p.bn_scale) {
+                pre = s * __ldg(p.bn_scale + c) + __ldg(p.bn_shift + c);
+                xhat = (s - __ldg(p.bn_mean + c)) * __ldg(p.bn_invstd + c);
+              }
+              g *= act_grad(pre, p.act);
+            }
+            if (p.bn_sums) g = round_bf16(g);
+            s1[i] = valid ? g : 0.f;
+            s2[i] = valid ? g * xhat : 0.f;
+            ob[i] = __float2bfloat16_rn(g);
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
+            dst[0] = reinterpret_cast<uint4*>(ob)[0];
+            dst[1] = reinterpret_cast<uint4*>(ob)[1];
+          }
+          if (p.bn_sums) {
+            const float t1 = lane_transpose_reduce16(s1, lane);
+            const float t2 = lane_transpose_reduce16(s2, lane);
+            if (lane < 16) {
+              atomicAdd(&s_stat[cl + lane], t1);
+              atomicAdd(&s_stat[256 + cl + lane], t2);
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      // with several N tiles per CTA the statistics must be flushed per tile (channels change)
+      if (p.n_ntiles > 1 && (p.stats || p.bn_sums)) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        double* dst = MODE == 0 ? p.stats : p.bn_sums;
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+          const float a1 = s_stat[i], a2 = s_stat[256 + i];
+          if (a1 != 0.f || a2 != 0.f) {
+            atomicAdd(dst + nt * BN + i, (double)a1);
+            atomicAdd(dst + p.OC + nt * BN + i, (double)a2);
+          }
+          s_stat[i] = 0.f; s_stat[256 + i] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  // ------------------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (p.n_ntiles == 1) {
+    double* dst = MODE == 0 ? p.stats : p.bn_sums;
+    if (dst) {
+      for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
+        atomicAdd(dst + i, (double)s_stat[i]);
+        atomicAdd(dst + p.OC + i, (double)s_stat[256 + i]);
+      }
+    }
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ weights
+// OIHW fp32 -> bf16 [tap][Cout][Cin] (transpose == 0, fprop) or [tap][Cin][Cout] (transpose == 1, dgrad)
+__global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int taps,
+                                    int transpose) {
+  const long long total = (long long)Cout * Cin * taps;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int inner, outer, tap;
+  if (!transpose) { inner = (int)(i % Cin); outer = (int)((i / Cin) % Cout); tap = (int)(i / ((long long)Cin * Cout)); }
+  else { inner = (int)(i % Cout); outer = (int)((i / Cout) % Cin); tap = (int)(i / ((long long)Cin * Cout)); }
+  const int co = transpose ? inner : outer, ci = transpose ? outer : inner;
+  out[i] = __float2bfloat16_rn(w[((long long)co * Cin + ci) * taps + tap]);
+}
+
+// ------------------------------------------------------------------------------------------ host
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+static int* g_error_flag = nullptr;  // device int, reports which barrier wait timed out
+
+static bool get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  });
+  return g_encode != nullptr;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int kc) {
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                        strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1],
+              box[2]);
+    return YG_ERR_CUDA;
+  }
+  return YG_OK;
+}
+
+static int pick_kc(int K) { return (K % 64 == 0) ? 64 : ((K % 32 == 0) ? 32 : ((K % 16 == 0) ? 16 : 0)); }
+static int pick_bn(int Nc) {
+  if (Nc % 16) return 0;
+  if (Nc <= 256) return Nc;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (Nc % bn == 0) return bn;
+  return 0;
+}
+
+bool tc_fwd_supported(int dtype, int Cin, int Cout, int ks, int stride) {
+  return dtype == YG_BF16 && ks == 3 && pick_kc(Cin) && pick_bn(Cout) && (stride == 1 || stride == 2);
+}
+bool tc_dgrad_supported(int dtype, int Cin, int Cout, int ks, int stride) {
+  return dtype == YG_BF16 && ks == 3 && pick_kc(Cout) && pick_bn(Cin) && (stride == 1 || stride == 2);
+}
 bool tc_wgrad_supported(int, int, int, int, int) { return false; }
-int conv_fwd_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const FwdEpi&, cudaStream_t) { set_error("tcgen05 conv not built"); return YG_ERR_INVALID; }
-int conv_dgrad_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const BwdEpi&, cudaStream_t) { set_error("tcgen05 conv not built"); return YG_ERR_INVALID; }
-int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t) { set_error("tcgen05 conv not built"); return YG_ERR_INVALID; }
 size_t tc_wgrad_workspace(int, int, int, int, int, int, int) { return 0; }
+int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t,
+                  cudaStream_t) {
+  set_error("tcgen05 wgrad not built");
+  return YG_ERR_INVALID;
+}
+
+// Launch the engine on an already described problem.
+static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_rows, cudaStream_t st) {
+  p.a_stage_bytes = max_rows * TC_TW * KCc * 2;
+  p.a_stage_bytes = (p.a_stage_bytes + 1023) & ~1023;
+  p.b_tap_bytes = p.BN * KCc * 2;
+  const int stage_bytes = p.a_stage_bytes + TC_MAX_TAPS * p.b_tap_bytes;
+  int nst = TC_SMEM_BUDGET / stage_bytes;
+  if (nst > 6) nst = 6;
+  if (nst < 2) {
+    set_error("tcgen05 conv: stage of %d bytes does not fit twice in shared memory", stage_bytes);
+    return YG_ERR_INVALID;
+  }
+  p.nstages = nst;
+  int cols = 32;
+  while (cols < 2 * p.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  if (!g_error_flag) {
+    YG_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
+    YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+  }
+  p.error_flag = g_error_flag;
+  const size_t smem = (size_t)nst * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (2 * 256 + 16) * sizeof(float) + 64;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+#define TC_LAUNCH(KCV, MODEV)                                                                                      \
+  do {                                                                                                             \
+    YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tc_kernel<KCV, MODEV><<<grid, TC_THREADS, smem, st>>>(maps, p);                                          \
+  } while (0)
+  if (mode == 0) {
+    if (KCc == 64) TC_LAUNCH(64, 0); else if (KCc == 32) TC_LAUNCH(32, 0); else TC_LAUNCH(16, 0);
+  } else {
+    if (KCc == 64) TC_LAUNCH(64, 1); else if (KCc == 32) TC_LAUNCH(32, 1); else TC_LAUNCH(16, 1);
+  }
+#undef TC_LAUNCH
+  YG_LAUNCH_CHECK("conv_tc_kernel");
+  return YG_OK;
+}
+
+// choose KC so that at least 2 stages fit
+static int fit_kc(int K, int BN, int max_rows) {
+  int kc = pick_kc(K);
+  while (kc >= 16) {
+    const int stage = ((max_rows * TC_TW * kc * 2 + 1023) & ~1023) + TC_MAX_TAPS * BN * kc * 2;
+    if (K % kc == 0 && TC_SMEM_BUDGET / stage >= 2) return kc;
+    kc >>= 1;
+  }
+  return 0;
+}
+
+static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int transpose, cudaStream_t st) {
+  const long long total = (long long)Cout * Cin * 9;
+  YG_CUDA(cudaMallocAsync((void**)out, total * sizeof(bf16), st));
+  pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, *out, Cout, Cin, 9, transpose);
+  YG_LAUNCH_CHECK("pack_weights");
+  return YG_OK;
+}
+
+int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int Cin, int Cout, int ks, int stride,
+                const FwdEpi& ep, cudaStream_t st) {
+  if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int BN = pick_bn(Cout);
+  const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
+  const int KCc = fit_kc(Cin, BN, max_rows);
+  if (!KCc) { set_error("conv_fwd_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
+  bf16* wp = nullptr;
+  int rc = pack_weights(w, &wp, Cout, Cin, 0, st);
+  if (rc) return rc;
+  // B map: [tap][Cout][Cin]
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * Cout * 2};
+    uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
+    rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
+    if (rc) return rc;
+  }
+  const bf16* xb = (const bf16*)x;
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)KCc, TC_TW, TC_TH + 2, 1};
+    rc = make_map(&maps.a[0], xb, 4, dims, str, box, KCc);
+    if (rc) return rc;
+    for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+    p.ngroups = 3;
+    for (int s = 0; s < 3; ++s) {
+      TcGroup& g = p.g[s];
+      g.map = 0; g.dh = -1; g.dw = s - 1; g.rows = TC_TH + 2; g.ntaps = 3;
+      for (int r = 0; r < 3; ++r) { g.ro[r] = r; g.widx[r] = r * 3 + s; }
+    }
+  } else {
+    // parity sub-grids: element (h2, w2) of map (ph, pw) is x[2*h2+ph][2*w2+pw]
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const int H2 = (H - ph + 1) / 2, W2 = (W - pw + 1) / 2;
+        if (H2 < 1 || W2 < 1) { set_error("conv_fwd_tc: image too small for stride 2"); return YG_ERR_INVALID; }
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W2, (uint64_t)H2, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {(uint32_t)KCc, TC_TW, (uint32_t)(ph ? TC_TH + 1 : TC_TH), 1};
+        rc = make_map(&maps.a[ph * 2 + pw], xb + ((long long)ph * W + pw) * Cin, 4, dims, str, box, KCc);
+        if (rc) return rc;
+      }
+    // input row 2*ho + r - 1: r=0 -> (ph=1, h2=ho-1), r=1 -> (ph=0, h2=ho), r=2 -> (ph=1, h2=ho)
+    p.ngroups = 6;
+    int gi = 0;
+    for (int s = 0; s < 3; ++s) {
+      const int pw = (s == 1) ? 0 : 1, dw = (s == 0) ? -1 : 0;
+      TcGroup& g1 = p.g[gi++];
+      g1.map = 2 + pw; g1.dh = -1; g1.dw = dw; g1.rows = TC_TH + 1; g1.ntaps = 2;
+      g1.ro[0] = 0; g1.widx[0] = 0 * 3 + s;
+      g1.ro[1] = 1; g1.widx[1] = 2 * 3 + s;
+      TcGroup& g0 = p.g[gi++];
+      g0.map = pw; g0.dh = 0; g0.dw = dw; g0.rows = TC_TH; g0.ntaps = 1;
+      g0.ro[0] = 0; g0.widx[0] = 1 * 3 + s;
+    }
+  }
+  p.N = N; p.TSH = Ho; p.TSW = Wo;
+  p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
+  p.n_ntiles = Cout / BN;
+  p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
+  p.OH = Ho; p.OW = Wo; p.OC = Cout; p.os = 1; p.oh0 = 0; p.ow0 = 0;
+  p.BN = BN; p.kchunks = Cin / KCc;
+  p.out = y;
+  p.scale = ep.scale; p.shift = ep.shift; p.act = ep.act; p.dropscale = ep.dropscale; p.stats = ep.stats;
+  p.preact = ep.preact;
+  rc = launch_engine(maps, p, KCc, 0, max_rows, st);
+  cudaFreeAsync(wp, st);
+  return rc;
+}
+
+int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W, int Cin, int Cout, int ks, int stride,
+                  const BwdEpi& be, cudaStream_t st) {
+  if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int BN = pick_bn(Cin);
+  const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
+  const int KCc = fit_kc(Cout, BN, max_rows);
+  if (!KCc) { set_error("conv_dgrad_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
+  bf16* wp = nullptr;
+  int rc = pack_weights(w, &wp, Cout, Cin, 1, st);
+  if (rc) return rc;
+  const bf16* gb = (const bf16*)dz;
+  const int nclass = stride == 1 ? 1 : 4;
+  for (int cls = 0; cls < nclass; ++cls) {
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    {
+      uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, 9};
+      uint64_t str[2] = {(uint64_t)Cout * 2, (uint64_t)Cin * Cout * 2};
+      uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
+      rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
+      if (rc) break;
+    }
+    const int qh = cls >> 1, qw = cls & 1;
+    int rows;
+    if (stride == 1) {
+      rows = TC_TH + 2;
+      // dx(h,w) = sum_{r,s} dz(h+1-r, w+1-s) W[r][s]^T
+      p.ngroups = 3;
+      for (int s = 0; s < 3; ++s) {
+        TcGroup& g = p.g[s];
+        g.map = 0; g.dh = -1; g.dw = 1 - s; g.rows = rows; g.ntaps = 3;
+        for (int r = 0; r < 3; ++r) { g.ro[r] = 2 - r; g.widx[r] = r * 3 + s; }
+      }
+      p.TSH = H; p.TSW = W; p.os = 1; p.oh0 = 0; p.ow0 = 0;
+    } else {
+      // output parity class (qh, qw): h = 2a+qh.  qh=0: r=1 (dz row a).  qh=1: r=0 (row a+1), r=2 (row a).
+      rows = TC_TH + qh;
+      p.TSH = (H - qh + 1) / 2; p.TSW = (W - qw + 1) / 2; p.os = 2; p.oh0 = qh; p.ow0 = qw;
+      if (p.TSH < 1 || p.TSW < 1) continue;
+      int gi = 0;
+      const int ns = qw ? 2 : 1;
+      for (int si = 0; si < ns; ++si) {
+        const int s = qw ? (si == 0 ? 0 : 2) : 1;
+        const int dw = qw ? (si == 0 ? 1 : 0) : 0;
+        TcGroup& g = p.g[gi++];
+        g.map = 0; g.dh = 0; g.dw = dw; g.rows = rows;
+        if (qh) { g.ntaps = 2; g.ro[0] = 1; g.widx[0] = 0 * 3 + s; g.ro[1] = 0; g.widx[1] = 2 * 3 + s; }
+        else { g.ntaps = 1; g.ro[0] = 0; g.widx[0] = 1 * 3 + s; }
+      }
+      p.ngroups = gi;
+    }
+    {
+      uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+      uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+      uint32_t box[4] = {(uint32_t)KCc, TC_TW, (uint32_t)rows, 1};
+      rc = make_map(&maps.a[0], gb, 4, dims, str, box, KCc);
+      if (rc) break;
+      for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+    }
+    p.N = N;
+    p.tiles_h = cdiv(p.TSH, TC_TH); p.tiles_w = cdiv(p.TSW, TC_TW);
+    p.n_ntiles = Cin / BN;
+    p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
+    p.OH = H; p.OW = W; p.OC = Cin;
+    p.BN = BN; p.kchunks = Cout / KCc;
+    p.out = dx;
+    p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
+    p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
+    rc = launch_engine(maps, p, KCc, 1, max_rows, st);
+    if (rc) break;
+  }
+  cudaFreeAsync(wp, st);
+  return rc;
+}
+
 }  // namespace yg
