@@ -26,7 +26,18 @@ CASES = [
     ("dgrad", 2, 20, 36, 32, 64, 2),
     ("dgrad", 2, 21, 37, 128, 128, 2),
     ("dgrad", 2, 19, 35, 16, 32, 1),
+    ("wgrad", 1, 8, 16, 64, 128, 1),
+    ("wgrad", 1, 8, 16, 64, 64, 1),
+    ("wgrad", 2, 19, 35, 128, 128, 1),
+    ("wgrad", 2, 19, 35, 64, 128, 1),
+    ("wgrad", 3, 20, 36, 32, 64, 2),
+    ("wgrad", 2, 21, 37, 128, 128, 2),
+    ("wgrad", 2, 19, 35, 16, 64, 1),
+    ("wgrad", 1, 16, 32, 256, 256, 1),
+    ("wgrad", 64, 97, 129, 128, 128, 1),
 ]
+if os.environ.get("TC_ONLY"):
+    CASES = [c for c in CASES if c[0] in os.environ["TC_ONLY"].split(",")]
 
 
 def run_case(kind, N, H, W, Cin, Cout, s):
@@ -50,6 +61,27 @@ def run_case(kind, N, H, W, Cin, Cout, s):
             L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(ep), L.stream()))
             torch.cuda.synchronize()
             outs[impl] = y.float()
+    elif kind == "wgrad":
+        x = torch.randn(N, H, W, Cin, generator=g).to(dev).bfloat16()
+        dz = (torch.randn(N, Ho, Wo, Cout, generator=g) / (N * Ho * Wo) ** 0.5).to(dev).bfloat16()
+        outs = {}
+        import time
+        for impl in ("simt", "tcgen05"):
+            L.set_conv_impl(impl)
+            dw = torch.full((Cout, Cin, 3, 3), float("nan"), device=dev)
+            db = torch.full((Cout,), float("nan"), device=dev)
+            nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, 3, s)
+            ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+            for rep in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                L.check(lib.yg_conv_wgrad(x.data_ptr(), dz.data_ptr(), dw.data_ptr(), db.data_ptr(), 1, N, H, W, Cin, Cout, 3, s,
+                                          0.0, ws.data_ptr(), nb, L.stream()))
+                torch.cuda.synchronize()
+                res["ms_" + impl] = round((time.perf_counter() - t0) * 1e3, 3)
+            outs[impl] = dw.permute(2, 3, 0, 1).contiguous()[None].reshape(1, 3, 3, Cout * Cin)
+            outs[impl + "_db"] = db
+        res["db_rel"] = float((outs["simt_db"] - outs["tcgen05_db"]).norm() / outs["simt_db"].norm())
     else:
         dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(dev).bfloat16()
         outs = {}

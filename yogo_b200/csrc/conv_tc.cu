@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <map>
 #include <mutex>
 
 namespace yg {
@@ -486,12 +487,360 @@ bool tc_fwd_supported(int dtype, int Cin, int Cout, int ks, int stride) {
 bool tc_dgrad_supported(int dtype, int Cin, int Cout, int ks, int stride) {
   return dtype == YG_BF16 && ks == 3 && pick_kc(Cout) && pick_bn(Cin) && (stride == 1 || stride == 2);
 }
-bool tc_wgrad_supported(int, int, int, int, int) { return false; }
-size_t tc_wgrad_workspace(int, int, int, int, int, int, int) { return 0; }
-int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t,
-                  cudaStream_t) {
-  set_error("tcgen05 wgrad not built");
-  return YG_ERR_INVALID;
+
+
+// ==========================================================================================
+// wgrad: dW[co][ci][r][s] = sum over pixels dz[p][co] * x[p + tap][ci]
+//   GEMM view  D[M = 128 couts][N = BNW cins] += A^T[K = 16 pixels x M] * B[K = 16 pixels x N], both operands
+//              MN-major straight out of the NHWC tensors (pixel rows, channels contiguous): the TMA boxes of
+//              the fprop engine are reused unchanged, only the UMMA descriptors say "MN-major".
+//   K loop     over ALL pixels a CTA owns: accumulators stay in TMEM for the whole kernel (3 taps x BNW
+//              columns), one epilogue at the end writes fp32 partials; a deterministic second kernel sums
+//              the per-CTA partials, clamps and writes OIHW fp32.
+//   work split unit = (filter column s, M tile, N tile); CTA c works on unit c % nunits and on every
+//              nslices-th pixel tile.
+// ==========================================================================================
+struct TwGroup {
+  int map, dh, dw, rows, ntaps;
+  int ro[TC_MAX_TAPS];
+  int slot[TC_MAX_TAPS];  // accumulator slot (= filter row r)
+};
+struct TwMaps {
+  CUtensorMap a;     // dz
+  CUtensorMap b[4];  // x (parity sub-grids for stride 2)
+};
+struct TwParams {
+  int N, tiles_h, tiles_w, total_tiles;
+  int Cin, Cout, BNW, n_ntiles, n_mtiles, nunits, nslices;
+  int kb, nbblocks, a_block_bytes, b_block_bytes, stage_bytes, nstages, tmem_cols;
+  int ngroups;                 // groups per filter column
+  TwGroup g[3][2];
+  float* partial;
+  int* error_flag;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+template <int KB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwParams p) {
+  constexpr uint32_t ROWB = KB * 2;                       // bytes per pixel row of a B block
+  constexpr uint32_t LAYOUT_B = KB == 64 ? 2u : (KB == 32 ? 4u : 6u);
+  constexpr uint32_t ROWA = 128;                          // A blocks are always 64 channels wide (SWIZZLE_128B)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* tail = smem + (size_t)p.nstages * p.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* done_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x % p.nunits, slice = blockIdx.x / p.nunits;
+  const int sg = unit % 3, mt = (unit / 3) % p.n_mtiles, nt = unit / (3 * p.n_mtiles);
+  const int a_blocks = min(2, (p.Cout - mt * 128) / 64);
+  const int BNW = p.BNW;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a);
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.b[i]);
+    for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&done_bar[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (a_blocks == 1) {
+    // Cout tile of 64: the upper 64 rows of the M = 128 operand are a block of zeros that TMA never touches
+    for (int st = 0; st < p.nstages; ++st) {
+      uint4* z = reinterpret_cast<uint4*>(smem + (size_t)st * p.stage_bytes + p.a_block_bytes);
+      for (int i = threadIdx.x; i < p.a_block_bytes / 16; i += TC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
+        int t = tile;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        for (int gi = 0; gi < p.ngroups; ++gi) {
+          const TwGroup& g = p.g[sg][gi];
+          mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 11);
+          unsigned char* sa = smem + (size_t)stage * p.stage_bytes;
+          unsigned char* sb = sa + 2 * p.a_block_bytes;
+          const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + p.nbblocks * g.rows * TC_TW * (int)ROWB);
+          mbar_expect_tx(&full_bar[stage], bytes);
+          for (int ab = 0; ab < a_blocks; ++ab)
+            tma_load_4d(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * 64, tw * TC_TW,
+                        th * TC_TH, n);
+          for (int bb = 0; bb < p.nbblocks; ++bb)
+            tma_load_4d(sb + (size_t)bb * p.b_block_bytes, &maps.b[g.map], &full_bar[stage], nt * BNW + bb * KB,
+                        tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D=f32, A=B=bf16, both MN-major (bits 15,16), N = BNW, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(BNW >> 3) << 17) | ((128u >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t started = 0;  // bit r set once accumulator slot r holds data
+    for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
+      for (int gi = 0; gi < p.ngroups; ++gi) {
+        const TwGroup& g = p.g[sg][gi];
+        mbar_wait(&full_bar[stage], phase, p.error_flag, 13);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + 2u * (uint32_t)p.a_block_bytes;
+          for (int tp = 0; tp < g.ntaps; ++tp) {
+            const int slot = g.slot[tp];
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BNW);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels = one 8x16 tile
+              const uint64_t ad = umma_desc_mn(sa + (uint32_t)k * 16u * ROWA, (uint32_t)p.a_block_bytes, 8 * ROWA, 2u);
+              const uint64_t bd = umma_desc_mn(sb + (uint32_t)(g.ro[tp] * TC_TW + k * 16) * ROWB,
+                                               (uint32_t)p.b_block_bytes, 8 * ROWB, LAYOUT_B);
+              umma_bf16(d_tmem, ad, bd, idesc, ((started >> slot) & 1u) | (k > 0 ? 1u : 0u));
+            }
+            started |= 1u << slot;
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        started = __shfl_sync(0xffffffffu, started, 0);
+        __syncwarp();
+        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    if (lane == 0) umma_commit(&done_bar[0]);
+    __syncwarp();
+  } else {
+    // epilogue: once, after the last MMA retired
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // cout inside the M tile
+    mbar_wait(&done_bar[0], 0, p.error_flag, 14);
+    tc_fence_after();
+    const bool any_tile = slice < p.total_tiles;
+    float* dst = p.partial + ((size_t)blockIdx.x * 3) * 128 * BNW;
+    for (int r = 0; r < 3; ++r) {
+      for (int j = 0; j < BNW / 16; ++j) {
+        uint32_t v[16];
+        if (any_tile) {
+          tmem_ld16(tmem_base + (uint32_t)(r * BNW + j * 16) + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+        float4* o = reinterpret_cast<float4*>(dst + ((size_t)r * 128 + row) * BNW + j * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                             __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
+                                       int BNW, int n_mtiles, int nunits, int nslices, float clip) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over [co][ci][r][s]
+  if (i >= (long long)Cout * Cin * 9) return;
+  const int s = (int)(i % 3), r = (int)((i / 3) % 3);
+  const int ci = (int)((i / 9) % Cin), co = (int)(i / (9LL * Cin));
+  const int mt = co / 128, nt = ci / BNW;
+  const int unit = s + 3 * (mt + n_mtiles * nt);
+  float acc = 0.f;
+  for (int sl = 0; sl < nslices; ++sl) {
+    const size_t cta = (size_t)unit + (size_t)nunits * sl;
+    acc += partial[((cta * 3 + r) * 128 + (co % 128)) * BNW + (ci % BNW)];
+  }
+  dw[i] = clampf(acc, clip);
+}
+
+// per-channel sum over pixels (conv bias gradient), deterministic two-stage
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ g, float* __restrict__ partial, long long npix, int C) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per;
+  long long p1 = p0 + per;
+  if (p1 > npix) p1 = npix;
+  float s = 0.f;
+  for (long long q = p0; q < p1; ++q) s += to_f<T>(g[q * C + c]);
+  partial[(long long)blockIdx.x * C + c] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int C, int nblk, float clip) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(long long)b * C + c];
+  out[c] = clampf(s, clip);
+}
+constexpr int COLSUM_BLOCKS = 592;
+
+static int wgrad_bnw(int Cin, int kb) {
+  if (Cin <= 128) return Cin;
+  for (int bn = 128; bn >= kb; bn -= kb)
+    if (Cin % bn == 0) return bn;
+  return 0;
+}
+
+bool tc_wgrad_supported(int dtype, int Cin, int Cout, int ks, int stride) {
+  if (dtype != YG_BF16 || ks != 3 || (stride != 1 && stride != 2)) return false;
+  if (Cout % 64 != 0) return false;
+  const int kb = pick_kc(Cin);
+  return kb != 0 && wgrad_bnw(Cin, kb) != 0;
+}
+
+static void wgrad_grid(int Cin, int Cout, int* nunits, int* nslices, int* grid, int* bnw, int* n_mtiles, int* n_ntiles) {
+  const int kb = pick_kc(Cin);
+  *bnw = wgrad_bnw(Cin, kb);
+  *n_mtiles = (Cout + 127) / 128;
+  *n_ntiles = Cin / *bnw;
+  *nunits = 3 * *n_mtiles * *n_ntiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int sl = sms / *nunits;
+  if (sl < 1) sl = 1;
+  *nslices = sl;
+  *grid = *nunits * sl;
+}
+
+size_t tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ks, int stride) {
+  if (!tc_wgrad_supported(YG_BF16, Cin, Cout, ks, stride)) return 0;
+  int nunits, nslices, grid, bnw, nm, nn;
+  wgrad_grid(Cin, Cout, &nunits, &nslices, &grid, &bnw, &nm, &nn);
+  return (size_t)grid * 3 * 128 * bnw * sizeof(float) + (size_t)COLSUM_BLOCKS * Cout * sizeof(float) + 256;
+}
+
+int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N, int H, int W, int Cin, int Cout, int ks,
+                  int stride, float clip, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  const size_t need = tc_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
+  if (!ws || ws_bytes < need) { set_error("conv_wgrad_tc: workspace %zu < %zu", ws_bytes, need); return YG_ERR_WORKSPACE; }
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  TwMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  TwParams p;
+  memset(&p, 0, sizeof(p));
+  int grid;
+  wgrad_grid(Cin, Cout, &p.nunits, &p.nslices, &grid, &p.BNW, &p.n_mtiles, &p.n_ntiles);
+  const int kb = pick_kc(Cin);
+  p.kb = kb; p.nbblocks = p.BNW / kb;
+  p.N = N; p.Cin = Cin; p.Cout = Cout;
+  p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
+  p.total_tiles = N * p.tiles_h * p.tiles_w;
+  const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
+  p.a_block_bytes = TC_TH * TC_TW * 128;
+  p.b_block_bytes = (max_rows * TC_TW * kb * 2 + 1023) & ~1023;
+  p.stage_bytes = 2 * p.a_block_bytes + p.nbblocks * p.b_block_bytes;
+  int nst = TC_SMEM_BUDGET / p.stage_bytes;
+  if (nst > 6) nst = 6;
+  if (nst < 2) { set_error("conv_wgrad_tc: stage of %d bytes does not fit twice", p.stage_bytes); return YG_ERR_INVALID; }
+  p.nstages = nst;
+  int cols = 32;
+  while (cols < 3 * p.BNW) cols <<= 1;
+  p.tmem_cols = cols;
+  int rc;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+    uint32_t box[4] = {64, TC_TW, TC_TH, 1};
+    rc = make_map(&maps.a, dz, 4, dims, str, box, 64);
+    if (rc) return rc;
+  }
+  const bf16* xb = (const bf16*)x;
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)kb, TC_TW, TC_TH + 2, 1};
+    rc = make_map(&maps.b[0], xb, 4, dims, str, box, kb);
+    if (rc) return rc;
+    for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+    p.ngroups = 1;
+    for (int s = 0; s < 3; ++s) {
+      TwGroup& g = p.g[s][0];
+      g.map = 0; g.dh = -1; g.dw = s - 1; g.rows = TC_TH + 2; g.ntaps = 3;
+      for (int r = 0; r < 3; ++r) { g.ro[r] = r; g.slot[r] = r; }
+    }
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const int H2 = (H - ph + 1) / 2, W2 = (W - pw + 1) / 2;
+        if (H2 < 1 || W2 < 1) { set_error("conv_wgrad_tc: image too small for stride 2"); return YG_ERR_INVALID; }
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W2, (uint64_t)H2, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {(uint32_t)kb, TC_TW, (uint32_t)(ph ? TC_TH + 1 : TC_TH), 1};
+        rc = make_map(&maps.b[ph * 2 + pw], xb + ((long long)ph * W + pw) * Cin, 4, dims, str, box, kb);
+        if (rc) return rc;
+      }
+    p.ngroups = 2;
+    for (int s = 0; s < 3; ++s) {
+      const int pw = (s == 1) ? 0 : 1, dw_ = (s == 0) ? -1 : 0;
+      TwGroup& g1 = p.g[s][0];
+      g1.map = 2 + pw; g1.dh = -1; g1.dw = dw_; g1.rows = TC_TH + 1; g1.ntaps = 2;
+      g1.ro[0] = 0; g1.slot[0] = 0;
+      g1.ro[1] = 1; g1.slot[1] = 2;
+      TwGroup& g0 = p.g[s][1];
+      g0.map = pw; g0.dh = 0; g0.dw = dw_; g0.rows = TC_TH; g0.ntaps = 1;
+      g0.ro[0] = 0; g0.slot[0] = 1;
+    }
+  }
+  p.partial = (float*)ws;
+  if (!g_error_flag) {
+    YG_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
+    YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+  }
+  p.error_flag = g_error_flag;
+  const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 512;
+#define TW_LAUNCH(KBV)                                                                                          \
+  do {                                                                                                          \
+    YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    wgrad_tc_kernel<KBV><<<grid, TC_THREADS, smem, st>>>(maps, p);                                              \
+  } while (0)
+  if (kb == 64) TW_LAUNCH(64); else if (kb == 32) TW_LAUNCH(32); else TW_LAUNCH(16);
+#undef TW_LAUNCH
+  YG_LAUNCH_CHECK("wgrad_tc_kernel");
+  const long long nw = (long long)Cout * Cin * 9;
+  wgrad_tc_reduce_kernel<<<cdiv(nw, 256), 256, 0, st>>>((const float*)ws, dw, Cout, Cin, p.BNW, p.n_mtiles, p.nunits,
+                                                        p.nslices, clip);
+  YG_LAUNCH_CHECK("wgrad_tc_reduce");
+  if (dbias) {
+    float* part = (float*)((char*)ws + (size_t)grid * 3 * 128 * p.BNW * sizeof(float));
+    const long long npix = (long long)N * Ho * Wo;
+    const int nblk = (int)(npix < COLSUM_BLOCKS ? npix : COLSUM_BLOCKS);
+    dim3 g2(nblk, cdiv(Cout, 128));
+    colsum_partial_kernel<bf16><<<g2, 128, 0, st>>>((const bf16*)dz, part, npix, Cout);
+    YG_LAUNCH_CHECK("colsum_partial");
+    colsum_final_kernel<<<cdiv(Cout, 128), 128, 0, st>>>(part, dbias, Cout, nblk, clip);
+    YG_LAUNCH_CHECK("colsum_final");
+  }
+  return YG_OK;
 }
 
 // Launch the engine on an already described problem.
@@ -546,9 +895,39 @@ static int fit_kc(int K, int BN, int max_rows) {
   return 0;
 }
 
+// Packed-weight scratch: one persistent device buffer per (weight pointer, layout), allocated on first
+// use and re-packed on every call (weights change every optimizer step; the pack is a ~1 us kernel).
+// Persistent buffers avoid per-call cudaMallocAsync/FreeAsync traffic on the driver's memory pool.
+// Calls for the same weight tensor must be issued on one stream (the library's single-stream contract).
+struct PackKey {
+  const void* w; int transpose; int dev;
+  bool operator<(const PackKey& o) const {
+    if (w != o.w) return w < o.w;
+    if (transpose != o.transpose) return transpose < o.transpose;
+    return dev < o.dev;
+  }
+};
+static std::map<PackKey, std::pair<void*, size_t>> g_pack_cache;
+static std::mutex g_pack_mutex;
+
 static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int transpose, cudaStream_t st) {
   const long long total = (long long)Cout * Cin * 9;
-  YG_CUDA(cudaMallocAsync((void**)out, total * sizeof(bf16), st));
+  {
+    std::lock_guard<std::mutex> lock(g_pack_mutex);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PackKey key{w, transpose, dev};
+    auto it = g_pack_cache.find(key);
+    if (it == g_pack_cache.end() || it->second.second < (size_t)total * sizeof(bf16)) {
+      void* buf = nullptr;
+      YG_CUDA(cudaMalloc(&buf, total * sizeof(bf16)));
+      if (it != g_pack_cache.end()) { cudaFree(it->second.first); it->second = {buf, (size_t)total * sizeof(bf16)}; }
+      else g_pack_cache[key] = {buf, (size_t)total * sizeof(bf16)};
+      *out = (bf16*)buf;
+    } else {
+      *out = (bf16*)it->second.first;
+    }
+  }
   pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, *out, Cout, Cin, 9, transpose);
   YG_LAUNCH_CHECK("pack_weights");
   return YG_OK;
@@ -627,7 +1006,6 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   p.scale = ep.scale; p.shift = ep.shift; p.act = ep.act; p.dropscale = ep.dropscale; p.stats = ep.stats;
   p.preact = ep.preact;
   rc = launch_engine(maps, p, KCc, 0, max_rows, st);
-  cudaFreeAsync(wp, st);
   return rc;
 }
 
@@ -705,7 +1083,6 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
     rc = launch_engine(maps, p, KCc, 1, max_rows, st);
     if (rc) break;
   }
-  cudaFreeAsync(wp, st);
   return rc;
 }
 
