@@ -164,7 +164,8 @@ extern "C" int yg_bn_act_apply(const void* y, void* a, int dtype, int N, int HW,
 extern "C" int yg_bn_bwd_apply(void* g, const void* y, int dtype, int N, int HW, int C,
                                const double* sums, const float* gamma, const float* mean, const float* invstd,
                                float* dgamma, float* dbeta, float clip, int batch_stats, void* stream) {
-  YG_CHECK_ARG(sums && mean && invstd, "bn_bwd_apply: null pointer");
+  YG_CHECK_ARG(sums != nullptr, "bn_bwd_apply: sums is null");
+  YG_CHECK_ARG(!g || (mean && invstd), "bn_bwd_apply: mean/invstd are null");
   const long long total = (long long)N * HW * C;
   cudaStream_t st = (cudaStream_t)stream;
   if (total && g) {
