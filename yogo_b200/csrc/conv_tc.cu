@@ -25,9 +25,10 @@
 namespace yg {
 
 constexpr int TC_TH = 8, TC_TW = 16;          // output tile (pixels), M = 128
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;           // 2 role warps + 8 epilogue warps
+constexpr int TC_WG_THREADS = 192;        // wgrad kernel: 2 role warps + 4 epilogue warps
 constexpr int TC_MAX_GROUPS = 9, TC_MAX_TAPS = 3;
-constexpr int TC_SMEM_BUDGET = 227 * 1024 - 6 * 1024;
+constexpr int TC_SMEM_BUDGET = 227 * 1024 - 14 * 1024;
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;   // bounded mbarrier spin: trap instead of hanging the GPU
 
 struct TcMaps {
@@ -186,7 +187,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BN]
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
+  float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
@@ -195,7 +197,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
     prefetch_tmap(&maps.b);
     for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -203,6 +205,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   // epilogue constants and statistics accumulators (the N tile is fixed per CTA only when n_ntiles == 1,
   // so constants are indexed by absolute channel and reloaded per tile below when needed)
   for (int i = threadIdx.x; i < 2 * 256; i += TC_THREADS) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < p.OC; i += TC_THREADS) {
+    if (MODE == 0) {
+      s_const[i] = p.scale ? p.scale[i] : 1.f;
+      s_const[512 + i] = p.shift ? p.shift[i] : 0.f;
+    } else if (p.bn_scale) {
+      s_const[i] = p.bn_scale[i];
+      s_const[512 + i] = p.bn_shift[i];
+      s_const[1024 + i] = p.bn_mean[i];
+      s_const[1536 + i] = p.bn_invstd[i];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -278,13 +291,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
-    // ===================================================================== epilogue (4 warps)
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    // ===================================================================== epilogue (8 warps)
+    // warp w may only touch TMEM lanes [32*(w&3), +32); two warps share a quarter and split the
+    // 16-column chunks between them (even / odd chunks).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;       // row of the tile = pixel
     const int hl = m / TC_TW, wl = m % TC_TW;
     int acc = 0;
     uint32_t acc_phase = 0;
     bf16* out = reinterpret_cast<bf16*>(p.out);
+    const float* s_k0 = s_const;             // fwd: scale      bwd: bn_scale
+    const float* s_k1 = s_const + 512;       // fwd: shift      bwd: bn_shift
+    const float* s_k2 = s_const + 1024;      //                 bwd: bn_mean
+    const float* s_k3 = s_const + 1536;      //                 bwd: bn_invstd
+    const bool has_bn = p.bn_scale != nullptr;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t = tile;
       const int nt = t % p.n_ntiles; t /= p.n_ntiles;
@@ -298,28 +319,65 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      for (int j = 0; j < BN / 16; ++j) {
+      for (int j = half; j < BN / 16; j += 2) {
         uint32_t r[16];
         tmem_ld16(taddr0 + (uint32_t)(j * 16), r);
-        tmem_ld_wait();
         const int cl = j * 16;          // channel inside the N tile
         const int c0 = nt * BN + cl;    // absolute output channel
+        // global operands of this chunk are fetched while the TMEM load is in flight
+        float ds[16];
+        if (p.dropscale) {
+          const float4* dp = reinterpret_cast<const float4*>(p.dropscale + (long long)n * p.OC + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v4 = __ldg(dp + i);
+            ds[4 * i] = v4.x; ds[4 * i + 1] = v4.y; ds[4 * i + 2] = v4.z; ds[4 * i + 3] = v4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ds[i] = 1.f;
+        }
+        __align__(16) bf16 sv[16];
+        if (MODE == 1) {
+          if (p.saved && valid) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
+            reinterpret_cast<uint4*>(sv)[0] = __ldg(src);
+            reinterpret_cast<uint4*>(sv)[1] = __ldg(src + 1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
+          }
+        }
+        tmem_ld_wait();
         __align__(16) bf16 ob[16];
+        float s1[16], s2[16];
         if (MODE == 0) {
-          float s1[16], s2[16];
           __align__(16) bf16 pb[16];
+          const bool rnd = p.stats || p.preact;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int c = c0 + i;
-            float x = __uint_as_float(r[i]);
-            x = x * (p.scale ? __ldg(p.scale + c) : 1.f) + (p.shift ? __ldg(p.shift + c) : 0.f);
-            if (p.stats || p.preact) x = round_bf16(x);
+            float x = __uint_as_float(r[i]) * s_k0[c0 + i] + s_k1[c0 + i];
+            if (rnd) x = round_bf16(x);
             s1[i] = valid ? x : 0.f;
             s2[i] = valid ? x * x : 0.f;
             pb[i] = __float2bfloat16_rn(x);
-            x = act_fwd(x, p.act);
-            if (p.dropscale) x *= __ldg(p.dropscale + (long long)n * p.OC + c);
-            ob[i] = __float2bfloat16_rn(x);
+            r[i] = __float_as_uint(x);
+          }
+          if (p.act == YG_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x = __uint_as_float(r[i]);
+              ob[i] = __float2bfloat16_rn((x > 0.f ? x : 0.01f * x) * ds[i]);
+            }
+          } else if (p.act == YG_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x = __uint_as_float(r[i]);
+              ob[i] = __float2bfloat16_rn(x * __frcp_rn(1.f + __expf(-x)) * ds[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(__uint_as_float(r[i]) * ds[i]);
           }
           if (valid) {
             if (out) {
@@ -342,35 +400,33 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
           }
         } else {
-          float s1[16], s2[16];
-          __align__(16) bf16 sv[16];
-          if (p.saved && valid) {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
-            reinterpret_cast<uint4*>(sv)[0] = src[0];
-            reinterpret_cast<uint4*>(sv)[1] = src[1];
-          } else {
+          float pre[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
+          for (int i = 0; i < 16; ++i) {
+            const float sval = __bfloat162float(sv[i]);
+            pre[i] = has_bn ? sval * s_k0[c0 + i] + s_k1[c0 + i] : sval;
+            s2[i] = has_bn ? (sval - s_k2[c0 + i]) * s_k3[c0 + i] : 0.f;  // xhat
+            s1[i] = __uint_as_float(r[i]) * ds[i];
+          }
+          if (p.saved) {
+            if (p.act == YG_ACT_LRELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) s1[i] *= pre[i] > 0.f ? 1.f : 0.01f;
+            } else if (p.act == YG_ACT_SILU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sg = __frcp_rn(1.f + __expf(-pre[i]));
+                s1[i] *= sg * (1.f + pre[i] * (1.f - sg));
+              }
+            }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int c = c0 + i;
-            float g = __uint_as_float(r[i]);
-            if (p.dropscale) g *= __ldg(p.dropscale + (long long)n * p.OC + c);
-            float xhat = 0.f;
-            if (p.saved) {
-              const float s = __bfloat162float(sv[i]);
-              float pre = s;
-              if (p.bn_scale) {
-                pre = s * __ldg(p.bn_scale + c) + __ldg(p.bn_shift + c);
-                xhat = (s - __ldg(p.bn_mean + c)) * __ldg(p.bn_invstd + c);
-              }
-              g *= act_grad(pre, p.act);
-            }
+            float g = s1[i];
             if (p.bn_sums) g = round_bf16(g);
-            s1[i] = valid ? g : 0.f;
-            s2[i] = valid ? g * xhat : 0.f;
             ob[i] = __float2bfloat16_rn(g);
+            s1[i] = valid ? g : 0.f;
+            s2[i] = valid ? g * s2[i] : 0.f;
           }
           if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
@@ -393,9 +449,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       // with several N tiles per CTA the statistics must be flushed per tile (channels change)
       if (p.n_ntiles > 1 && (p.stats || p.bn_sums)) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         double* dst = MODE == 0 ? p.stats : p.bn_sums;
-        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        for (int i = threadIdx.x - 64; i < BN; i += 256) {
           const float a1 = s_stat[i], a2 = s_stat[256 + i];
           if (a1 != 0.f || a2 != 0.f) {
             atomicAdd(dst + nt * BN + i, (double)a1);
@@ -403,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
           s_stat[i] = 0.f; s_stat[256 + i] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -482,10 +538,10 @@ static int pick_bn(int Nc) {
 }
 
 bool tc_fwd_supported(int dtype, int Cin, int Cout, int ks, int stride) {
-  return dtype == YG_BF16 && ks == 3 && pick_kc(Cin) && pick_bn(Cout) && (stride == 1 || stride == 2);
+  return dtype == YG_BF16 && ks == 3 && pick_kc(Cin) && pick_bn(Cout) && Cout <= 512 && (stride == 1 || stride == 2);
 }
 bool tc_dgrad_supported(int dtype, int Cin, int Cout, int ks, int stride) {
-  return dtype == YG_BF16 && ks == 3 && pick_kc(Cout) && pick_bn(Cin) && (stride == 1 || stride == 2);
+  return dtype == YG_BF16 && ks == 3 && pick_kc(Cout) && pick_bn(Cin) && Cin <= 512 && (stride == 1 || stride == 2);
 }
 
 
@@ -530,7 +586,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
 }
 
 template <int KB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwParams p) {
   constexpr uint32_t ROWB = KB * 2;                       // bytes per pixel row of a B block
   constexpr uint32_t LAYOUT_B = KB == 64 ? 2u : (KB == 32 ? 4u : 6u);
@@ -560,7 +616,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     // Cout tile of 64: the upper 64 rows of the M = 128 operand are a block of zeros that TMA never touches
     for (int st = 0; st < p.nstages; ++st) {
       uint4* z = reinterpret_cast<uint4*>(smem + (size_t)st * p.stage_bytes + p.a_block_bytes);
-      for (int i = threadIdx.x; i < p.a_block_bytes / 16; i += TC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < p.a_block_bytes / 16; i += TC_WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -821,7 +877,7 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
 #define TW_LAUNCH(KBV)                                                                                          \
   do {                                                                                                          \
     YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    wgrad_tc_kernel<KBV><<<grid, TC_THREADS, smem, st>>>(maps, p);                                              \
+    wgrad_tc_kernel<KBV><<<grid, TC_WG_THREADS, smem, st>>>(maps, p);                                              \
   } while (0)
   if (kb == 64) TW_LAUNCH(64); else if (kb == 32) TW_LAUNCH(32); else TW_LAUNCH(16);
 #undef TW_LAUNCH
@@ -864,7 +920,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
     YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   }
   p.error_flag = g_error_flag;
-  const size_t smem = (size_t)nst * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (2 * 256 + 16) * sizeof(float) + 64;
+  const size_t smem = (size_t)nst * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (2 * 256 + 4 * 512 + 16) * sizeof(float) + 64;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
