@@ -585,12 +585,14 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
   return d;
 }
 
-template <int KB>
+template <int KB, int KA>
 __global__ void __launch_bounds__(TC_WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwParams p) {
   constexpr uint32_t ROWB = KB * 2;                       // bytes per pixel row of a B block
   constexpr uint32_t LAYOUT_B = KB == 64 ? 2u : (KB == 32 ? 4u : 6u);
-  constexpr uint32_t ROWA = 128;                          // A blocks are always 64 channels wide (SWIZZLE_128B)
+  constexpr uint32_t ROWA = KA * 2;                       // A blocks are KA couts wide (64: SWIZZLE_128B, 32: 64B)
+  constexpr uint32_t LAYOUT_A = KA == 64 ? 2u : 4u;
+  constexpr int MBLOCKS = 128 / KA;                       // blocks that make up the M = 128 operand
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* tail = smem + (size_t)p.nstages * p.stage_bytes;
@@ -602,7 +604,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x % p.nunits, slice = blockIdx.x / p.nunits;
   const int sg = unit % 3, mt = (unit / 3) % p.n_mtiles, nt = unit / (3 * p.n_mtiles);
-  const int a_blocks = min(2, (p.Cout - mt * 128) / 64);
+  const int a_blocks = min(MBLOCKS, (p.Cout - mt * 128) / KA);
   const int BNW = p.BNW;
 
   if (warp == 0 && lane == 0) {
@@ -612,11 +614,12 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     mbar_init(&done_bar[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (a_blocks == 1) {
-    // Cout tile of 64: the upper 64 rows of the M = 128 operand are a block of zeros that TMA never touches
+  if (a_blocks < MBLOCKS) {
+    // short Cout tile: the missing rows of the M = 128 operand are blocks of zeros that TMA never touches
     for (int st = 0; st < p.nstages; ++st) {
-      uint4* z = reinterpret_cast<uint4*>(smem + (size_t)st * p.stage_bytes + p.a_block_bytes);
-      for (int i = threadIdx.x; i < p.a_block_bytes / 16; i += TC_WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      uint4* z = reinterpret_cast<uint4*>(smem + (size_t)st * p.stage_bytes + (size_t)a_blocks * p.a_block_bytes);
+      const int n16 = (MBLOCKS - a_blocks) * p.a_block_bytes / 16;
+      for (int i = threadIdx.x; i < n16; i += TC_WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -639,11 +642,11 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
           const TwGroup& g = p.g[sg][gi];
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 11);
           unsigned char* sa = smem + (size_t)stage * p.stage_bytes;
-          unsigned char* sb = sa + 2 * p.a_block_bytes;
+          unsigned char* sb = sa + MBLOCKS * p.a_block_bytes;
           const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + p.nbblocks * g.rows * TC_TW * (int)ROWB);
           mbar_expect_tx(&full_bar[stage], bytes);
           for (int ab = 0; ab < a_blocks; ++ab)
-            tma_load_4d(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * 64, tw * TC_TW,
+            tma_load_4d(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * KA, tw * TC_TW,
                         th * TC_TH, n);
           for (int bb = 0; bb < p.nbblocks; ++bb)
             tma_load_4d(sb + (size_t)bb * p.b_block_bytes, &maps.b[g.map], &full_bar[stage], nt * BNW + bb * KB,
@@ -666,13 +669,13 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + 2u * (uint32_t)p.a_block_bytes;
+          const uint32_t sb = sa + (uint32_t)MBLOCKS * (uint32_t)p.a_block_bytes;
           for (int tp = 0; tp < g.ntaps; ++tp) {
             const int slot = g.slot[tp];
             const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BNW);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels = one 8x16 tile
-              const uint64_t ad = umma_desc_mn(sa + (uint32_t)k * 16u * ROWA, (uint32_t)p.a_block_bytes, 8 * ROWA, 2u);
+              const uint64_t ad = umma_desc_mn(sa + (uint32_t)k * 16u * ROWA, (uint32_t)p.a_block_bytes, 8 * ROWA, LAYOUT_A);
               const uint64_t bd = umma_desc_mn(sb + (uint32_t)(g.ro[tp] * TC_TW + k * 16) * ROWB,
                                                (uint32_t)p.b_block_bytes, 8 * ROWB, LAYOUT_B);
               umma_bf16(d_tmem, ad, bd, idesc, ((started >> slot) & 1u) | (k > 0 ? 1u : 0u));
@@ -767,7 +770,7 @@ static int wgrad_bnw(int Cin, int kb) {
 
 bool tc_wgrad_supported(int dtype, int Cin, int Cout, int ks, int stride) {
   if (dtype != YG_BF16 || ks != 3 || (stride != 1 && stride != 2)) return false;
-  if (Cout % 64 != 0) return false;
+  if (Cout % 32 != 0) return false;
   const int kb = pick_kc(Cin);
   return kb != 0 && wgrad_bnw(Cin, kb) != 0;
 }
@@ -812,9 +815,10 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
   p.total_tiles = N * p.tiles_h * p.tiles_w;
   const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
-  p.a_block_bytes = TC_TH * TC_TW * 128;
+  const int ka = (Cout % 64 == 0) ? 64 : 32;
+  p.a_block_bytes = TC_TH * TC_TW * ka * 2;
   p.b_block_bytes = (max_rows * TC_TW * kb * 2 + 1023) & ~1023;
-  p.stage_bytes = 2 * p.a_block_bytes + p.nbblocks * p.b_block_bytes;
+  p.stage_bytes = (128 / ka) * p.a_block_bytes + p.nbblocks * p.b_block_bytes;
   int nst = TC_SMEM_BUDGET / p.stage_bytes;
   if (nst > 6) nst = 6;
   if (nst < 2) { set_error("conv_wgrad_tc: stage of %d bytes does not fit twice", p.stage_bytes); return YG_ERR_INVALID; }
@@ -826,8 +830,8 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
-    uint32_t box[4] = {64, TC_TW, TC_TH, 1};
-    rc = make_map(&maps.a, dz, 4, dims, str, box, 64);
+    uint32_t box[4] = {(uint32_t)ka, TC_TW, TC_TH, 1};
+    rc = make_map(&maps.a, dz, 4, dims, str, box, ka);
     if (rc) return rc;
   }
   const bf16* xb = (const bf16*)x;
@@ -874,12 +878,13 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   }
   p.error_flag = g_error_flag;
   const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 512;
-#define TW_LAUNCH(KBV)                                                                                          \
-  do {                                                                                                          \
-    YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    wgrad_tc_kernel<KBV><<<grid, TC_WG_THREADS, smem, st>>>(maps, p);                                              \
+#define TW_LAUNCH(KBV, KAV)                                                                                          \
+  do {                                                                                                               \
+    YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV, KAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    wgrad_tc_kernel<KBV, KAV><<<grid, TC_WG_THREADS, smem, st>>>(maps, p);                                           \
   } while (0)
-  if (kb == 64) TW_LAUNCH(64); else if (kb == 32) TW_LAUNCH(32); else TW_LAUNCH(16);
+  if (ka == 64) { if (kb == 64) TW_LAUNCH(64, 64); else if (kb == 32) TW_LAUNCH(32, 64); else TW_LAUNCH(16, 64); }
+  else { if (kb == 64) TW_LAUNCH(64, 32); else if (kb == 32) TW_LAUNCH(32, 32); else TW_LAUNCH(16, 32); }
 #undef TW_LAUNCH
   YG_LAUNCH_CHECK("wgrad_tc_kernel");
   const long long nw = (long long)Cout * Cin * 9;

@@ -11,11 +11,11 @@ namespace yg {
 
 constexpr int FL_CO = 16, FL_THREADS = 128;
 
-template <typename TX>
+template <typename TX, int CO>
 __device__ __forceinline__ void first_conv_pixel(const TX* __restrict__ x, const float* ws, int n, int ho, int wo,
-                                                 int H, int W, int Cin, int stride, float (&acc)[FL_CO]) {
+                                                 int H, int W, int Cin, int stride, float (&acc)[CO]) {
 #pragma unroll
-  for (int c = 0; c < FL_CO; ++c) acc[c] = 0.f;
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
   for (int ci = 0; ci < Cin; ++ci) {
     const TX* xp = x + ((long long)n * Cin + ci) * H * W;
 #pragma unroll
@@ -27,17 +27,18 @@ __device__ __forceinline__ void first_conv_pixel(const TX* __restrict__ x, const
         const int iw = wo * stride - 1 + s;
         if (iw < 0 || iw >= W) continue;
         const float xv = to_f<TX>(xp[(long long)ih * W + iw]);
-        const float* wr = ws + (ci * 9 + r * 3 + s) * FL_CO;
+        const float* wr = ws + (ci * 9 + r * 3 + s) * CO;
 #pragma unroll
-        for (int c = 0; c < FL_CO; ++c) acc[c] += xv * wr[c];
+        for (int c = 0; c < CO; ++c) acc[c] += xv * wr[c];
       }
     }
   }
 }
 
+template <int CO>
 __device__ __forceinline__ void load_first_weights(float* ws, const float* __restrict__ w, int Cin, int Cout, int co0) {
-  for (int i = threadIdx.x; i < Cin * 9 * FL_CO; i += blockDim.x) {
-    int c = i % FL_CO, t = i / FL_CO;  // t = ci*9 + tap
+  for (int i = threadIdx.x; i < Cin * 9 * CO; i += blockDim.x) {
+    int c = i % CO, t = i / CO;  // t = ci*9 + tap
     int co = co0 + c;
     ws[i] = co < Cout ? w[(long long)co * Cin * 9 + t] : 0.f;
   }
@@ -49,31 +50,65 @@ __global__ void __launch_bounds__(FL_THREADS) conv_first_fwd_kernel(
     int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int stride, FwdEpi ep) {
   __shared__ float ws[3 * 9 * FL_CO];
   __shared__ float ssum[FL_CO], ssq[FL_CO];
-  const int co0 = blockIdx.y * FL_CO, n = blockIdx.z;
-  load_first_weights(ws, w, Cin, Cout, co0);
+  const int co0 = blockIdx.y * FL_CO;
+  load_first_weights<FL_CO>(ws, w, Cin, Cout, co0);
   if (threadIdx.x < FL_CO) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
   __syncthreads();
-  const int p = blockIdx.x * FL_THREADS + threadIdx.x;
-  const bool valid = p < Ho * Wo;
-  float acc[FL_CO];
-  if (valid) first_conv_pixel<TX>(x, ws, n, p / Wo, p % Wo, H, W, Cin, stride, acc);
-  else {
-#pragma unroll
-    for (int c = 0; c < FL_CO; ++c) acc[c] = 0.f;
-  }
-  float v[FL_CO];
+  float sc[FL_CO], sh[FL_CO];
 #pragma unroll
   for (int c = 0; c < FL_CO; ++c) {
     const int co = co0 + c;
-    const float sc = (ep.scale && co < Cout) ? ep.scale[co] : 1.f;
-    const float sh = (ep.shift && co < Cout) ? ep.shift[co] : 0.f;
-    v[c] = valid ? acc[c] * sc + sh : 0.f;
+    sc[c] = (ep.scale && co < Cout) ? ep.scale[co] : 1.f;
+    sh[c] = (ep.shift && co < Cout) ? ep.shift[co] : 0.f;
+  }
+  float s1[FL_CO], s2[FL_CO];
+#pragma unroll
+  for (int c = 0; c < FL_CO; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+  const long long total = (long long)N * Ho * Wo;
+  // grid-stride loop: statistics accumulate in registers, one reduction per thread at the end
+  for (long long q = (long long)blockIdx.x * FL_THREADS + threadIdx.x; q < total;
+       q += (long long)gridDim.x * FL_THREADS) {
+    const int n = (int)(q / ((long long)Ho * Wo));
+    const int p = (int)(q % ((long long)Ho * Wo));
+    float acc[FL_CO];
+    first_conv_pixel<TX, FL_CO>(x, ws, n, p / Wo, p % Wo, H, W, Cin, stride, acc);
+    float v[FL_CO];
+#pragma unroll
+    for (int c = 0; c < FL_CO; ++c) {
+      v[c] = acc[c] * sc[c] + sh[c];
+      s1[c] += v[c];
+      s2[c] += v[c] * v[c];
+    }
+    if (y) {
+      const long long o = q * Cout + co0;
+      if (sizeof(T) == 2 && co0 + FL_CO <= Cout && (Cout & 7) == 0 && !ep.preact) {
+        __align__(16) T ob[FL_CO];
+#pragma unroll
+        for (int c = 0; c < FL_CO; ++c) {
+          const float ds = ep.dropscale ? ep.dropscale[(long long)n * Cout + co0 + c] : 1.f;
+          ob[c] = from_f<T>(act_fwd(v[c], ep.act) * ds);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(y + o);
+        dst[0] = reinterpret_cast<uint4*>(ob)[0];
+        dst[1] = reinterpret_cast<uint4*>(ob)[1];
+      } else {
+#pragma unroll
+        for (int c = 0; c < FL_CO; ++c) {
+          const int co = co0 + c;
+          if (co < Cout) {
+            const float ds = ep.dropscale ? ep.dropscale[(long long)n * Cout + co] : 1.f;
+            if (ep.preact) ((T*)ep.preact)[o + c] = from_f<T>(v[c]);
+            y[o + c] = from_f<T>(act_fwd(v[c], ep.act) * ds);
+          }
+        }
+      }
+    }
   }
   if (ep.stats) {
 #pragma unroll
     for (int c = 0; c < FL_CO; ++c) {
-      float s1 = warp_sum(v[c]), s2 = warp_sum(v[c] * v[c]);
-      if ((threadIdx.x & 31) == 0) { atomicAdd(&ssum[c], s1); atomicAdd(&ssq[c], s2); }
+      const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&ssum[c], a); atomicAdd(&ssq[c], b); }
     }
     __syncthreads();
     if (threadIdx.x < FL_CO && co0 + threadIdx.x < Cout) {
@@ -81,47 +116,37 @@ __global__ void __launch_bounds__(FL_THREADS) conv_first_fwd_kernel(
       atomicAdd(&ep.stats[Cout + co0 + threadIdx.x], (double)ssq[threadIdx.x]);
     }
   }
-  if (y && valid) {
-    const long long o = ((long long)n * Ho * Wo + p) * Cout + co0;
-#pragma unroll
-    for (int c = 0; c < FL_CO; ++c) {
-      const int co = co0 + c;
-      if (co < Cout) {
-        const float ds = ep.dropscale ? ep.dropscale[(long long)n * Cout + co] : 1.f;
-        if (ep.preact) ((T*)ep.preact)[o + c] = from_f<T>(v[c]);
-        y[o + c] = from_f<T>(act_fwd(v[c], ep.act) * ds);
-      }
-    }
-  }
 }
+
+constexpr int FLB_CO = 8;  // couts per backward block (keeps 9x8 accumulators + state under 128 registers)
 
 // Backward.  mode 0: accumulate BN sums (sum g, sum g*xhat).  mode 1: weight gradient partials.
 // One block = (co chunk, ci) pair looping over pixels with a grid stride.
 template <typename TX, typename T, int MODE>
-__global__ void __launch_bounds__(FL_THREADS) conv_first_bwd_kernel(
+__global__ void __launch_bounds__(FL_THREADS, 4) conv_first_bwd_kernel(
     const TX* __restrict__ x, const float* __restrict__ w, const T* __restrict__ da,
     int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int stride, BwdEpi be,
     const float* __restrict__ fwd_shift, const float* __restrict__ dy_mean, const float* __restrict__ dyx_mean,
     float* __restrict__ partial, int nchunks) {
-  __shared__ float ws[3 * 9 * FL_CO];
-  __shared__ float red[9 * FL_CO + FL_CO];
+  __shared__ float ws[3 * 9 * FLB_CO];
+  __shared__ float red[9 * FLB_CO + FLB_CO];
   const int chunk = blockIdx.y % nchunks, ci_sel = blockIdx.y / nchunks;
-  const int co0 = chunk * FL_CO;
-  load_first_weights(ws, w, Cin, Cout, co0);
-  for (int i = threadIdx.x; i < 9 * FL_CO + FL_CO; i += blockDim.x) red[i] = 0.f;
+  const int co0 = chunk * FLB_CO;
+  load_first_weights<FLB_CO>(ws, w, Cin, Cout, co0);
+  for (int i = threadIdx.x; i < 9 * FLB_CO + FLB_CO; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 
-  float wacc[MODE == 1 ? 9 : 1][FL_CO];
-  float s1[FL_CO], s2[FL_CO];
+  float wacc[MODE == 1 ? 9 : 1][FLB_CO];
+  float s1[FLB_CO], s2[FLB_CO];
 #pragma unroll
-  for (int c = 0; c < FL_CO; ++c) {
+  for (int c = 0; c < FLB_CO; ++c) {
     s1[c] = 0.f; s2[c] = 0.f;
 #pragma unroll
     for (int t = 0; t < (MODE == 1 ? 9 : 1); ++t) wacc[t][c] = 0.f;
   }
-  float scl[FL_CO], sft[FL_CO], mean[FL_CO], istd[FL_CO], m1[FL_CO], m2[FL_CO], fsh[FL_CO];
+  float scl[FLB_CO], sft[FLB_CO], mean[FLB_CO], istd[FLB_CO], m1[FLB_CO], m2[FLB_CO], fsh[FLB_CO];
 #pragma unroll
-  for (int c = 0; c < FL_CO; ++c) {
+  for (int c = 0; c < FLB_CO; ++c) {
     const int co = co0 + c;
     const bool ok = co < Cout;
     scl[c] = (be.bn_scale && ok) ? be.bn_scale[co] : 1.f;
@@ -138,12 +163,12 @@ __global__ void __launch_bounds__(FL_THREADS) conv_first_bwd_kernel(
     const int n = (int)(q / ((long long)Ho * Wo));
     const int p = (int)(q % ((long long)Ho * Wo));
     const int ho = p / Wo, wo = p % Wo;
-    float acc[FL_CO];
-    first_conv_pixel<TX>(x, ws, n, ho, wo, H, W, Cin, stride, acc);
-    float dzv[FL_CO];
+    float acc[FLB_CO];
+    first_conv_pixel<TX, FLB_CO>(x, ws, n, ho, wo, H, W, Cin, stride, acc);
+    float dzv[FLB_CO];
     const long long o = q * Cout + co0;
 #pragma unroll
-    for (int c = 0; c < FL_CO; ++c) {
+    for (int c = 0; c < FLB_CO; ++c) {
       const int co = co0 + c;
       float g = 0.f, xhat = 0.f;
       if (co < Cout) {
@@ -172,43 +197,43 @@ __global__ void __launch_bounds__(FL_THREADS) conv_first_bwd_kernel(
           float xv = 0.f;
           if (ih >= 0 && ih < H && iw >= 0 && iw < W) xv = to_f<TX>(xp[(long long)ih * W + iw]);
 #pragma unroll
-          for (int c = 0; c < FL_CO; ++c) wacc[r * 3 + s][c] += dzv[c] * xv;
+          for (int c = 0; c < FLB_CO; ++c) wacc[r * 3 + s][c] += dzv[c] * xv;
         }
       }
     }
   }
   // block reduction -> partials
 #pragma unroll
-  for (int c = 0; c < FL_CO; ++c) {
+  for (int c = 0; c < FLB_CO; ++c) {
     float a = warp_sum(s1[c]);
     float b = MODE == 0 ? warp_sum(s2[c]) : 0.f;
     if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&red[9 * FL_CO + c], a);
+      atomicAdd(&red[9 * FLB_CO + c], a);
       if (MODE == 0) atomicAdd(&red[c], b);
     }
     if (MODE == 1) {
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         float v = warp_sum(wacc[t][c]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&red[t * FL_CO + c], v);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&red[t * FLB_CO + c], v);
       }
     }
   }
   __syncthreads();
   if (MODE == 0) {
-    if (threadIdx.x < FL_CO && co0 + threadIdx.x < Cout && ci_sel == 0) {
-      atomicAdd(&be.bn_sums[co0 + threadIdx.x], (double)red[9 * FL_CO + threadIdx.x]);
+    if (threadIdx.x < FLB_CO && co0 + threadIdx.x < Cout && ci_sel == 0) {
+      atomicAdd(&be.bn_sums[co0 + threadIdx.x], (double)red[9 * FLB_CO + threadIdx.x]);
       atomicAdd(&be.bn_sums[Cout + co0 + threadIdx.x], (double)red[threadIdx.x]);
     }
   } else {
     // partial layout per slice (= blockIdx.x): [Cout][Cin][9] then [Cout]
     float* base = partial + (long long)blockIdx.x * ((long long)Cout * Cin * 9 + Cout);
-    for (int i = threadIdx.x; i < 9 * FL_CO; i += blockDim.x) {
-      const int c = i % FL_CO, t = i / FL_CO;
+    for (int i = threadIdx.x; i < 9 * FLB_CO; i += blockDim.x) {
+      const int c = i % FLB_CO, t = i / FLB_CO;
       if (co0 + c < Cout) base[((long long)(co0 + c) * Cin + ci_sel) * 9 + t] = red[i];
     }
-    if (threadIdx.x < FL_CO && co0 + threadIdx.x < Cout && ci_sel == 0)
-      base[(long long)Cout * Cin * 9 + co0 + threadIdx.x] = red[9 * FL_CO + threadIdx.x];
+    if (threadIdx.x < FLB_CO && co0 + threadIdx.x < Cout && ci_sel == 0)
+      base[(long long)Cout * Cin * 9 + co0 + threadIdx.x] = red[9 * FLB_CO + threadIdx.x];
   }
 }
 
@@ -224,7 +249,7 @@ __global__ void wgrad_reduce_kernel2(const float* __restrict__ partial, float* _
   else if (dbias) dbias[i - nw] = s;
 }
 
-constexpr int FL_BWD_BLOCKS = 296;
+constexpr int FL_BWD_BLOCKS = 592;
 
 }  // namespace yg
 
@@ -241,7 +266,9 @@ extern "C" int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, voi
   if (N == 0) return YG_OK;
   FwdEpi ep = make_fwd_epi(epp);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  dim3 grid(cdiv((long long)Ho * Wo, FL_THREADS), cdiv(Cout, FL_CO), N);
+  long long nblk = ((long long)N * Ho * Wo + FL_THREADS - 1) / FL_THREADS;
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  dim3 grid((unsigned)nblk, cdiv(Cout, FL_CO), 1);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(TX, T) conv_first_fwd_kernel<TX, T><<<grid, FL_THREADS, 0, st>>>((const TX*)x, w, (T*)y, N, H, W, Cin, Ho, Wo, Cout, stride, ep)
   if (x_dtype == YG_U8) { if (dtype == YG_BF16) LAUNCH(uint8_t, bf16); else LAUNCH(uint8_t, float); }
@@ -263,7 +290,7 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
   if (N == 0) return YG_OK;
   BwdEpi be = make_bwd_epi(bep);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  const int nchunks = cdiv(Cout, FL_CO);
+  const int nchunks = cdiv(Cout, FLB_CO);
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = dw ? 1 : 0;
   YG_CHECK_ARG(mode == 1 || be.bn_sums, "conv_first_bwd: pass 1 needs bn_sums");

@@ -184,6 +184,166 @@ __global__ void __launch_bounds__(HD_PX) head_bwd_kernel(
   for (int i = threadIdx.x; i < D * Cin + D; i += HD_PX) base[i] = dwacc[i];
 }
 
+
+// Faster backward for the common case (Cin = 32*CPL, D <= 16): one warp per run of 32 pixels.
+//   phase A (lane = pixel): dt[d] from dpred planes (coalesced) and the raw logits -> warp-private smem
+//   phase B (lane = CPL consecutive channels, loop over the 32 pixels): dx = dt.W with the fused backward
+//            epilogue, dw / BN sums accumulate in registers for the whole kernel (one block reduction at
+//            the end), 8-byte (CPL = 4) coalesced loads and stores.
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) head_bwd_warp_kernel(
+    const float* __restrict__ dpred, const float* __restrict__ t_raw, const T* __restrict__ x,
+    const float* __restrict__ w, T* __restrict__ dx, float* __restrict__ partial,
+    long long npix, int Sy, int Sx, int Cin, int D, float anchor_w, float anchor_h, float wmul, float hmul,
+    BwdEpi be) {
+  constexpr int DM = 16;
+  extern __shared__ float smem[];
+  float* wsm = smem;                         // [D][Cin]
+  float* dwacc = wsm + (size_t)D * Cin;      // [D][Cin] + [D]
+  float* dts_all = dwacc + (size_t)D * Cin + DM;  // [8 warps][32][DM]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* dts = dts_all + (size_t)warp * 32 * DM;
+  for (int i = threadIdx.x; i < D * Cin; i += 256) { wsm[i] = w[i]; dwacc[i] = 0.f; }
+  if (threadIdx.x < DM) dwacc[D * Cin + threadIdx.x] = 0.f;
+  __syncthreads();
+  const int SS = Sy * Sx;
+  const int c0 = lane * CPL;
+  float acc[DM][CPL];
+#pragma unroll
+  for (int d = 0; d < DM; ++d)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[d][k] = 0.f;
+  float db[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) db[d] = 0.f;
+  float bsum[CPL], bsx[CPL], k_scale[CPL], k_shift[CPL], k_mean[CPL], k_istd[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    bsum[k] = 0.f; bsx[k] = 0.f;
+    k_scale[k] = be.bn_scale ? be.bn_scale[c0 + k] : 1.f;
+    k_shift[k] = be.bn_scale ? be.bn_shift[c0 + k] : 0.f;
+    k_mean[k] = be.bn_scale ? be.bn_mean[c0 + k] : 0.f;
+    k_istd[k] = be.bn_scale ? be.bn_invstd[c0 + k] : 0.f;
+  }
+  const long long nruns = (npix + 31) / 32;
+  const long long gw = (long long)blockIdx.x * 8 + warp, nw = (long long)gridDim.x * 8;
+  for (long long run = gw; run < nruns; run += nw) {
+    const long long p0 = run * 32;
+    {  // phase A
+      const long long p = p0 + lane;
+      float dt[DM];
+#pragma unroll
+      for (int d = 0; d < DM; ++d) dt[d] = 0.f;
+      if (p < npix) {
+        const int n = (int)(p / SS), cell = (int)(p % SS);
+        const float* g = dpred + (long long)n * D * SS + cell;
+        const float* t = t_raw + p * D;
+        const float t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4];
+        const float s0 = sigmoidf_(t0), s1 = sigmoidf_(t1), s4 = sigmoidf_(t4);
+        dt[0] = g[0] * (1.f / (float)Sx) * s0 * (1.f - s0);
+        dt[1] = g[(long long)SS] * (1.f / (float)Sy) * s1 * (1.f - s1);
+        dt[2] = t2 <= 80.f ? g[2LL * SS] * anchor_w * expf(t2) * wmul : 0.f;
+        dt[3] = t3 <= 80.f ? g[3LL * SS] * anchor_h * expf(t3) * hmul : 0.f;
+        dt[4] = g[4LL * SS] * s4 * (1.f - s4);
+#pragma unroll
+        for (int d = 5; d < DM; ++d)
+          if (d < D) dt[d] = g[(long long)d * SS];
+      }
+#pragma unroll
+      for (int d = 0; d < DM; ++d) { dts[lane * DM + d] = dt[d]; db[d] += dt[d]; }
+    }
+    __syncwarp();
+    const int npx = (int)min((long long)32, npix - p0);
+    for (int pp = 0; pp < npx; ++pp) {
+      const long long q = p0 + pp;
+      const int n = (int)(q / SS);
+      float xv[CPL], g[CPL], sv[CPL];
+      {
+        __align__(16) T tmp[CPL];
+        if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(tmp) = *reinterpret_cast<const uint2*>(x + q * Cin + c0);
+        else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(x + q * Cin + c0);
+        else {
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) tmp[k] = x[q * Cin + c0 + k];
+        }
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { xv[k] = to_f<T>(tmp[k]); g[k] = 0.f; sv[k] = 0.f; }
+        if (be.saved) {
+          const T* sp = (const T*)be.saved + q * Cin + c0;
+          if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(tmp) = *reinterpret_cast<const uint2*>(sp);
+          else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(sp);
+          else {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) tmp[k] = sp[k];
+          }
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) sv[k] = to_f<T>(tmp[k]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < DM; ++d) {
+        if (d < D) {
+          const float dtd = dts[pp * DM + d];
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            g[k] += dtd * wsm[d * Cin + c0 + k];
+            acc[d][k] += dtd * xv[k];
+          }
+        }
+      }
+      if (dx) {
+        __align__(16) T ob[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          float gg = g[k];
+          if (be.dropscale) gg *= be.dropscale[(long long)n * Cin + c0 + k];
+          float xhat = 0.f;
+          if (be.saved) {
+            float pre = sv[k];
+            if (be.bn_scale) { pre = sv[k] * k_scale[k] + k_shift[k]; xhat = (sv[k] - k_mean[k]) * k_istd[k]; }
+            gg *= act_grad(pre, be.act);
+          }
+          if (be.bn_sums) gg = to_f<T>(from_f<T>(gg));
+          bsum[k] += gg; bsx[k] += gg * xhat;
+          ob[k] = from_f<T>(gg);
+        }
+        if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(dx + q * Cin + c0) = *reinterpret_cast<uint2*>(ob);
+        else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(dx + q * Cin + c0) = *reinterpret_cast<uint4*>(ob);
+        else {
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) dx[q * Cin + c0 + k] = ob[k];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // block reduction: lanes own distinct channels, the 8 warps share them
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    if (d < D) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) atomicAdd(&dwacc[d * Cin + c0 + k], acc[d][k]);
+      const float s = warp_sum(db[d]);
+      if (lane == 0) atomicAdd(&dwacc[D * Cin + d], s);
+    }
+  }
+  float* bn_s = dts_all + 8 * 32 * DM;  // [2][Cin], zeroed below before use
+  __syncthreads();
+  if (be.bn_sums) {
+    for (int i = threadIdx.x; i < 2 * Cin; i += 256) bn_s[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      atomicAdd(&bn_s[c0 + k], bsum[k]);
+      atomicAdd(&bn_s[Cin + c0 + k], bsx[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * Cin; i += 256) atomicAdd(&be.bn_sums[i], (double)bn_s[i]);
+  }
+  float* base = partial + (long long)blockIdx.x * ((long long)D * Cin + D);
+  for (int i = threadIdx.x; i < D * Cin + D; i += 256) base[i] = dwacc[i];
+}
+
 __global__ void head_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                    float* __restrict__ dbias, long long nw, int D, int slices, float clip) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,6 +411,28 @@ extern "C" int yg_head_bwd(const float* dpred, const float* t_raw, const void* x
   int blocks = cdiv(npix, HD_PX);
   if (blocks > HD_BWD_BLOCKS) blocks = HD_BWD_BLOCKS;
   if (blocks < 1) blocks = 1;
+  const int cpl = (Cin % 32 == 0) ? Cin / 32 : 0;
+  if (D <= 16 && (cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8) && npix > 0) {
+    blocks = (int)((npix + 255) / 256);
+    if (blocks > HD_BWD_BLOCKS) blocks = HD_BWD_BLOCKS;
+    const size_t smemw = ((size_t)D * Cin * 2 + 16 + 8 * 32 * 16 + 2 * (size_t)Cin) * sizeof(float);
+#define LAUNCHW(T, CPLV)                                                                                          \
+  do {                                                                                                            \
+    YG_CUDA(cudaFuncSetAttribute(head_bwd_warp_kernel<T, CPLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw)); \
+    head_bwd_warp_kernel<T, CPLV><<<blocks, 256, smemw, st>>>(dpred, t_raw, (const T*)x, w, (T*)dx, (float*)workspace,     \
+                                                              npix, Sy, Sx, Cin, D, anchor_w, anchor_h, width_mult,        \
+                                                              height_mult, be);                                            \
+  } while (0)
+#define LAUNCHW_T(CPLV) do { if (dtype == YG_BF16) LAUNCHW(bf16, CPLV); else LAUNCHW(float, CPLV); } while (0)
+    if (cpl == 1) LAUNCHW_T(1); else if (cpl == 2) LAUNCHW_T(2); else if (cpl == 4) LAUNCHW_T(4); else LAUNCHW_T(8);
+#undef LAUNCHW_T
+#undef LAUNCHW
+    YG_LAUNCH_CHECK("head_bwd_warp");
+    const long long nw2 = (long long)D * Cin;
+    head_reduce_kernel<<<cdiv(nw2 + D, 256), 256, 0, st>>>((const float*)workspace, dw, dbias, nw2, D, blocks, clip);
+    YG_LAUNCH_CHECK("head_reduce");
+    return YG_OK;
+  }
   const int DM = D <= 16 ? 16 : 32;
   const size_t smem = ((size_t)D * Cin * 2 + D + (size_t)HD_PX * DM + (size_t)HD_PX * (HD_KC + 1)) * sizeof(float);
   YG_CHECK_ARG(smem <= 200 * 1024, "head_bwd: Cin %d too large", Cin);
