@@ -78,39 +78,47 @@ __global__ void bn_act_apply_kernel(const T* __restrict__ y, T* __restrict__ a, 
   }
 }
 
+// dz = gamma*invstd*(g - m1 - xhat*m2) = g*A[c] + y*B[c] + K[c] with per-channel constants staged in smem
+// (the fp64 divisions happen once per channel per block, not once per element)
 template <typename T>
 __global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, long long total, int C, double M,
                                     const double* __restrict__ sums, const float* __restrict__ gamma,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     int batch_stats) {
-  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (i0 >= total) return;
-  if ((C & 7) == 0) {
-    const int c0 = (int)(i0 % C);
-    __align__(16) T gin[8];
-    __align__(16) T yin[8];
-    constexpr int V = (int)(sizeof(T) * 8 / 16);
+  extern __shared__ float kc[];  // [3][C]: A, B, K
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m1 = batch_stats ? (float)(sums[c] / M) : 0.f, m2 = batch_stats ? (float)(sums[C + c] / M) : 0.f;
+    const float gi = (gamma ? gamma[c] : 1.f) * invstd[c];
+    // xhat = (y - mean)*invstd  ->  dz = gi*g - gi*m2*invstd*y + gi*(m2*invstd*mean - m1)
+    kc[c] = gi;
+    kc[C + c] = -gi * m2 * invstd[c];
+    kc[2 * C + c] = gi * (m2 * invstd[c] * mean[c] - m1);
+  }
+  __syncthreads();
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < total;
+       i0 += (long long)gridDim.x * blockDim.x * 8) {
+    if ((C & 7) == 0) {
+      const int c0 = (int)(i0 % C);
+      __align__(16) T gin[8];
+      __align__(16) T yin[8];
+      constexpr int V = (int)(sizeof(T) * 8 / 16);
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      reinterpret_cast<uint4*>(gin)[v] = reinterpret_cast<const uint4*>(g + i0)[v];
-      reinterpret_cast<uint4*>(yin)[v] = reinterpret_cast<const uint4*>(y + i0)[v];
-    }
+      for (int v = 0; v < V; ++v) {
+        reinterpret_cast<uint4*>(gin)[v] = reinterpret_cast<const uint4*>(g + i0)[v];
+        reinterpret_cast<uint4*>(yin)[v] = reinterpret_cast<const uint4*>(y + i0)[v];
+      }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      const float m1 = batch_stats ? (float)(sums[c] / M) : 0.f, m2 = batch_stats ? (float)(sums[C + c] / M) : 0.f;
-      const float xhat = (to_f<T>(yin[k]) - mean[c]) * invstd[c];
-      gin[k] = from_f<T>((gamma ? gamma[c] : 1.f) * invstd[c] * (to_f<T>(gin[k]) - m1 - xhat * m2));
-    }
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        gin[k] = from_f<T>(to_f<T>(gin[k]) * kc[c] + to_f<T>(yin[k]) * kc[C + c] + kc[2 * C + c]);
+      }
 #pragma unroll
-    for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(g + i0)[v] = reinterpret_cast<uint4*>(gin)[v];
-  } else {
-    for (long long i = i0; i < i0 + 8 && i < total; ++i) {
-      const int c = (int)(i % C);
-      const float m1 = batch_stats ? (float)(sums[c] / M) : 0.f, m2 = batch_stats ? (float)(sums[C + c] / M) : 0.f;
-      const float xhat = (to_f<T>(y[i]) - mean[c]) * invstd[c];
-      const float gi = to_f<T>(g[i]);
-      g[i] = from_f<T>((gamma ? gamma[c] : 1.f) * invstd[c] * (gi - m1 - xhat * m2));
+      for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(g + i0)[v] = reinterpret_cast<uint4*>(gin)[v];
+    } else {
+      for (long long i = i0; i < i0 + 8 && i < total; ++i) {
+        const int c = (int)(i % C);
+        g[i] = from_f<T>(to_f<T>(g[i]) * kc[c] + to_f<T>(y[i]) * kc[C + c] + kc[2 * C + c]);
+      }
     }
   }
 }
@@ -170,12 +178,14 @@ extern "C" int yg_bn_bwd_apply(void* g, const void* y, int dtype, int N, int HW,
   cudaStream_t st = (cudaStream_t)stream;
   if (total && g) {
     YG_CHECK_ARG(y != nullptr, "bn_bwd_apply: y is null");
-    const int blocks = cdiv(cdiv(total, 8), 256);
+    int blocks = cdiv(cdiv(total, 8), 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
     const double M = (double)N * HW;
+    const size_t sm = (size_t)3 * C * sizeof(float);
     if (dtype == YG_BF16)
-      bn_bwd_apply_kernel<bf16><<<blocks, 256, 0, st>>>((bf16*)g, (const bf16*)y, total, C, M, sums, gamma, mean, invstd, batch_stats);
+      bn_bwd_apply_kernel<bf16><<<blocks, 256, sm, st>>>((bf16*)g, (const bf16*)y, total, C, M, sums, gamma, mean, invstd, batch_stats);
     else
-      bn_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>((float*)g, (const float*)y, total, C, M, sums, gamma, mean, invstd, batch_stats);
+      bn_bwd_apply_kernel<float><<<blocks, 256, sm, st>>>((float*)g, (const float*)y, total, C, M, sums, gamma, mean, invstd, batch_stats);
     YG_LAUNCH_CHECK("bn_bwd_apply");
   }
   if (dgamma || dbeta) {
