@@ -185,6 +185,7 @@ def run_ours(args):
     loss_fn = yogo_b200.YOGOLoss().to(dev)
     trainer = DataParallelTrainer(net, loss_fn, total_steps=10000)
     trainer.broadcast_state()
+    use_graph = args.graph and world == 1
 
     nbuf = 2  # distinct host batches, alternated
     host_imgs = [O.synth_images(B, seed=10 * rank + i).pin_memory() for i in range(nbuf)]
@@ -199,6 +200,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value)
+    if use_graph:
+        trainer.step(dev_imgs[0], dev_labs[0])
+        trainer.enable_cuda_graph(dev_imgs[0], dev_labs[0])
     for i in range(args.warmup):
         trainer.step(dev_imgs[i % nbuf], dev_labs[i % nbuf])
     barrier()
@@ -213,6 +217,8 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = L.load().yg_launch_count() - launches0
+    if use_graph:
+        launches = trainer.graph_launches * args.steps
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -251,7 +257,9 @@ def run_ours(args):
     roof = None
     breakdown = None
     if rank == 0:
+        saved_graph, trainer._graph = trainer._graph, None  # the breakdown needs individual launches
         breakdown = kernel_breakdown(trainer, dev_imgs, dev_labs, args, L)
+        trainer._graph = saved_graph
         roof = roofline_from_breakdown(breakdown, args, B)
 
     if rank == 0:
@@ -269,7 +277,7 @@ def run_ours(args):
                             f"772x1032x1 uint8 images, 7 classes, batch {B}/GPU (BASELINE configs[1])",
                 "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                 "l2_policy": "inputs+activations per step (>3 GB) far exceed the 126 MB L2; batches alternate",
-                "conv_impl": L.get_conv_impl(),
+                "conv_impl": L.get_conv_impl(), "cuda_graph": bool(use_graph),
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -362,6 +370,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the whole step from a CUDA graph (single GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

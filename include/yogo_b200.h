@@ -179,6 +179,10 @@ int yg_format_preds_batch(const float* preds, int B, int num_classes, int Sy, in
 int yg_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                   float lr, float beta1, float beta2, float eps, float weight_decay,
                   long long step, float grad_scale, void* stream);
+/* graph-replayable variant: hyper_dev (device, 8 floats) = [lr, beta1, beta2, eps, weight_decay,
+ * 1-beta1^t, sqrt(1-beta2^t), grad_scale] */
+int yg_adamw_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                      const float* hyper_dev, void* stream);
 
 #ifdef __cplusplus
 }

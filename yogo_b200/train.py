@@ -55,6 +55,7 @@ class DataParallelTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.overlap = overlap
         self.step_count = 0
+        self._graph = None
 
         runner = net._get_runner()
         params = [p for p in runner.plan.params if p.requires_grad]
@@ -193,6 +194,60 @@ class DataParallelTrainer:
 
     def step(self, imgs: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """zero_grad is implicit: every gradient view is overwritten by its kernel each step."""
+        if self._graph is not None:
+            return self._graph_step(imgs, labels)
         loss = self.forward_backward(imgs, labels)
         self.optimizer_step()
         return loss
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def _hyper_host(self, step_count: int) -> torch.Tensor:
+        b1, b2 = self.betas
+        return torch.tensor([self.lr_at(step_count - 1), b1, b2, self.eps, self.wd, 1.0 - b1 ** step_count,
+                             math.sqrt(1.0 - b2 ** step_count), 1.0 / self.world], dtype=torch.float32)
+
+    def enable_cuda_graph(self, imgs: torch.Tensor, labels: torch.Tensor, warmup: int = 2) -> None:
+        """Capture forward + loss + backward (+ all-reduce) + AdamW for this input shape into one CUDA graph;
+        afterwards `step` copies the batch into static buffers and replays it (launch-bound inner loop:
+        ~350 kernel launches and their host-side argument marshalling collapse into one graph launch)."""
+        dev = imgs.device
+        self._static_imgs = imgs.clone()
+        self._static_labels = labels.clone()
+        self._hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+
+        def body():
+            loss = self.forward_backward(self._static_imgs, self._static_labels)
+            L.check(L.lib().yg_adamw_flat_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), self.numel, self._hyper.data_ptr(), L.stream()))
+            return loss
+
+        # warm-up on a side stream (allocator pools, library caches), with a learning rate of zero so that the
+        # parameters and optimizer state are not disturbed ... they are: so snapshot and restore instead
+        snap = (self.flat_p.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
+                [b.clone() for b in self.net.buffers()])
+        self._hyper.copy_(self._hyper_host(1))
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = L.load().yg_launch_count()
+        with torch.cuda.graph(graph):
+            self._graph_loss = body()
+        self.graph_launches = int(L.load().yg_launch_count() - n0)  # our kernels inside one replay
+        self.flat_p.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2])
+        for b, v in zip(self.net.buffers(), snap[3]):
+            b.copy_(v)
+        torch.cuda.synchronize()
+        self._graph = graph
+
+    def _graph_step(self, imgs: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        self.step_count += 1
+        self._hyper.copy_(self._hyper_host(self.step_count))  # 32 bytes from pageable memory: staged, race-free
+        self._static_imgs.copy_(imgs, non_blocking=True)
+        self._static_labels.copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._graph_loss
