@@ -391,3 +391,46 @@ def test_variable_batch_and_3d_input():
         o5 = net(torch.rand(5, 1, 64, 96, device=DEV))    # ragged last batch (drop_last=False)
     assert tuple(o1.shape) == (1, 12, 8, 12) and tuple(o5.shape) == (5, 12, 8, 12)
     assert torch.isfinite(o5).all()
+
+
+# ----------------------------------------------------------------------------- trainer
+def _make_trainer(seed=0, dtype=torch.float32):
+    from yogo_b200.train import DataParallelTrainer
+    torch.manual_seed(seed)
+    net = yogo_b200.YOGO((96, 128), O.ANCHOR_W, O.ANCHOR_H, 7).to(DEV)
+    net.compute_dtype = dtype
+    net.train()
+    for m in net.model.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0  # deterministic comparison between eager and graph replay
+    net._runner = None
+    return net, DataParallelTrainer(net, yogo_b200.YOGOLoss().to(DEV), total_steps=50)
+
+
+def test_trainer_step_matches_torch_adamw_and_graph_replay():
+    """fused flat AdamW + cosine schedule == torch.optim.AdamW + CosineAnnealingLR on the same gradients
+    (train.py:213-223); CUDA-graph replay of the whole step == eager execution."""
+    img = O.synth_images(4, 96, 128).to(DEV)
+    lab = O.synth_labels(4, 12, 16, 7, 10).to(DEV)
+    net_a, tr_a = _make_trainer()
+    net_b, tr_b = _make_trainer()
+    ref_params = [p.detach().clone().requires_grad_(True) for p in net_a.parameters()]
+    opt = torch.optim.AdamW(ref_params, lr=3e-4, weight_decay=5e-2)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=50, eta_min=3e-4 / 10)
+    tr_b.enable_cuda_graph(img, lab)
+    for step in range(3):
+        la = tr_a.step(img, lab)
+        lb = tr_b.step(img, lab)
+        assert abs(la.item() - lb.item()) <= 1e-5 * abs(la.item())
+        torch.testing.assert_close(tr_a.flat_p, tr_b.flat_p, rtol=1e-5, atol=1e-7)
+        for rp, p in zip(ref_params, net_a.parameters()):
+            rp.grad = p.grad.detach().clone()
+        opt.step()
+        sched.step()
+        for rp, p in zip(ref_params, net_a.parameters()):
+            torch.testing.assert_close(p.detach(), rp.detach(), rtol=2e-5, atol=2e-7)
+    assert tr_b.graph_launches > 20
+    # BN buffers advanced identically in both modes
+    for (ka, va), (kb, vb) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
+        if "running_" in ka or "num_batches" in ka:
+            torch.testing.assert_close(va.float(), vb.float(), rtol=1e-5, atol=1e-7)

@@ -316,10 +316,31 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int oh = a * p.os + p.oh0, ow = b * p.os + p.ow0;
       const bool valid = a < p.TSH && b < p.TSW && oh < p.OH && ow < p.OW;
       const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
+      // dgrad: the saved-activation operands of this tile are fetched BEFORE waiting for the accumulator,
+      // so their HBM latency hides behind the MMAs instead of serialising the epilogue
+      uint4 sv_pre[8][2];
+      if (MODE == 1) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = half + 2 * jj;
+          if (p.saved && valid && j < BN / 16) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC +
+                                                              nt * BN + j * 16);
+            sv_pre[jj][0] = __ldg(src);
+            sv_pre[jj][1] = __ldg(src + 1);
+          } else {
+            sv_pre[jj][0] = make_uint4(0, 0, 0, 0);
+            sv_pre[jj][1] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      for (int j = half; j < BN / 16; j += 2) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = half + 2 * jj;
+        if (j >= BN / 16) break;
         uint32_t r[16];
         tmem_ld16(taddr0 + (uint32_t)(j * 16), r);
         const int cl = j * 16;          // channel inside the N tile
@@ -339,14 +360,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         __align__(16) bf16 sv[16];
         if (MODE == 1) {
-          if (p.saved && valid) {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
-            reinterpret_cast<uint4*>(sv)[0] = __ldg(src);
-            reinterpret_cast<uint4*>(sv)[1] = __ldg(src + 1);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
-          }
+          reinterpret_cast<uint4*>(sv)[0] = sv_pre[jj][0];
+          reinterpret_cast<uint4*>(sv)[1] = sv_pre[jj][1];
         }
         tmem_ld_wait();
         __align__(16) bf16 ob[16];

@@ -263,17 +263,17 @@ class Runner:
         t_raw = torch.empty((N, h, w, D), dtype=torch.float32, device=dev) if want_grad else None
         hw_ = _f32(plan.head.weight)
         hb_ = _f32(plan.head.bias)
+        hc = own._hc
         cxs = own._Cxs if own._Cxs.is_cuda and tuple(own._Cxs.shape) == (h, w) else None
         cys = own._Cys if own._Cys.is_cuda and tuple(own._Cys.shape) == (h, w) else None
         if cxs is not None:
             cxs, cys = cxs.contiguous(), cys.contiguous()
         L.check(lib.yg_head_fwd(cur.data_ptr(), dcode, hw_.data_ptr(), hb_.data_ptr(), outp.data_ptr(), L.ptr(t_raw),
-                                N, h, w, plan.head.in_channels, nc, float(own.anchor_w), float(own.anchor_h),
-                                float(own.width_multiplier), float(own.height_multiplier),
+                                N, h, w, plan.head.in_channels, nc, hc["anchor_w"], hc["anchor_h"],
+                                hc["width_multiplier"], hc["height_multiplier"],
                                 1 if own.inference else 0, L.ptr(cxs), L.ptr(cys), st))
         saved.update(t_raw=t_raw, head_in=cur, Sy=h, Sx=w, nc=nc,
-                     consts=(float(own.anchor_w), float(own.anchor_h), float(own.width_multiplier),
-                             float(own.height_multiplier)))
+                     consts=(hc["anchor_w"], hc["anchor_h"], hc["width_multiplier"], hc["height_multiplier"]))
         return outp, (saved if want_grad else None)
 
     # ---------------------------------------------------------------- backward

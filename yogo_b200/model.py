@@ -71,10 +71,27 @@ class YOGO(nn.Module):
         self.register_buffer("height_multiplier", torch.tensor(1.0))
         self.register_buffer("width_multiplier", torch.tensor(1.0))
 
+        self._refresh_host_consts()
         if tuning:
             self.model.apply(self.set_bn_eval)  # model.py:69-70
         else:
             self.model.apply(self.init_network_weights)  # model.py:71-73
+
+    def _refresh_host_consts(self) -> None:
+        """Host-side copies of the scalar buffers the kernels take by value.  Reading them from the device
+        buffers on every forward would be a device->host sync per step (and is illegal during CUDA-graph
+        capture); they only change in __init__, load_state_dict and resize_model."""
+        self._hc = {
+            "anchor_w": float(self.anchor_w), "anchor_h": float(self.anchor_h),
+            "width_multiplier": float(self.width_multiplier) if hasattr(self, "width_multiplier") else 1.0,
+            "height_multiplier": float(self.height_multiplier) if hasattr(self, "height_multiplier") else 1.0,
+        }
+        self._clip_value_f = float(self.clip_value)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        self._refresh_host_consts()
+        return out
 
     @staticmethod
     def _grid_offsets(Sx: int, Sy: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -133,7 +150,6 @@ class YOGO(nn.Module):
             model_func=get_model_func(model_version),
         )
         model.load_state_dict(params)
-        model._clip_value_f = float(model.clip_value)
         if inference:
             model.eval()
         return model, {
@@ -212,6 +228,7 @@ class YOGO(nn.Module):
         self.register_buffer("img_size", torch.tensor(crop, device=dev))
         self.register_buffer("_Cxs", _Cxs)
         self.register_buffer("_Cys", _Cys)
+        self._refresh_host_consts()
 
     def _get_runner(self):
         from . import engine
