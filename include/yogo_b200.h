@@ -44,6 +44,9 @@ int yg_device_check(void);
  * shape qualifies, SIMT otherwise).  Used by the parity tests to cross-check both. */
 int yg_set_conv_impl(int impl);
 int yg_get_conv_impl(void);
+/* debug/tuning switch of the tcgen05 engine: bit 0 = weights resident in shared memory when they fit,
+ * bit 1 = cp.async producer for 16/32-channel operands (default 3). */
+int yg_set_tc_options(int options);
 /* number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */
 unsigned long long yg_launch_count(void);
 

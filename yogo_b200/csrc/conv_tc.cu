@@ -25,7 +25,7 @@
 namespace yg {
 
 constexpr int TC_TH = 8, TC_TW = 16;          // output tile (pixels), M = 128
-constexpr int TC_THREADS = 320;           // 2 role warps + 8 epilogue warps
+// conv_tc_kernel: (1 or 2) producer warps + 1 MMA warp + 8 epilogue warps
 constexpr int TC_WG_THREADS = 192;        // wgrad kernel: 2 role warps + 4 epilogue warps
 constexpr int TC_MAX_GROUPS = 9, TC_MAX_TAPS = 3;
 constexpr int TC_SMEM_BUDGET = 227 * 1024 - 14 * 1024;
@@ -42,8 +42,16 @@ struct TcGroup {
   int widx[TC_MAX_TAPS];  // weight slice index
 };
 
+struct TcSrc {            // A-operand source as seen by the cp.async producer (element strides)
+  const bf16* base;
+  int Wd, Hd;
+  long long sw, sh, sn;
+};
+
 struct TcParams {
   int N, TSH, TSW, tiles_h, tiles_w, n_ntiles, total_tiles;
+  int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
+  TcSrc src[4];
   int OH, OW, OC, os, oh0, ow0;   // output tensor (NHWC) and tile-space -> output mapping
   int BN, kchunks, ngroups, nstages;
   int a_stage_bytes, b_tap_bytes, tmem_cols;
@@ -169,9 +177,16 @@ __device__ __forceinline__ float lane_transpose_reduce16(float (&v)[16], int lan
 __device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int KC, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// PROD = 0: A operand by TMA (one producer lane).  PROD = 1: A operand by cp.async from two producer warps
+// writing the swizzled layout by hand - for 16/32-channel tensors, whose 32/64-byte rows make TMA
+// request-rate bound (~4-8 cycles per row measured) - with all weights resident in shared memory.
+template <int KC, int MODE, int PROD>
+__global__ void __launch_bounds__((PROD ? 2 : 1) * 32 + 288, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+  constexpr int PW = PROD ? 2 : 1;             // producer warps; MMA warp = PW; epilogue warps PW+1 .. PW+8
+  constexpr int NTHREADS = PW * 32 + 288;
+  constexpr int CPR = KC / 8;                  // 16-byte chunks per operand row
+  constexpr int LAG = 2;                       // cp.async groups kept in flight per producer thread
   constexpr uint32_t ROW_BYTES = KC * 2;
   constexpr uint32_t SBO = 8 * ROW_BYTES;
   constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
@@ -180,13 +195,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases: align by hand, do not trust the attribute
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = p.a_stage_bytes + TC_MAX_TAPS * p.b_tap_bytes;
-  unsigned char* tail = smem + (size_t)p.nstages * stage_bytes;
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : TC_MAX_TAPS * p.b_tap_bytes);
+  unsigned char* resb = smem + (size_t)p.nstages * stage_bytes;
+  unsigned char* tail = resb + p.resb_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* resb_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resb_bar + 2);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
   float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
 
@@ -196,16 +213,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
     prefetch_tmap(&maps.b);
-    for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], PROD ? 64 : 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    mbar_init(&resb_bar[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (p.b_resident) {
+      // every (tap, K chunk) weight tile is fetched once and stays in shared memory
+      mbar_expect_tx(&resb_bar[0], (uint32_t)(9 * p.kchunks * p.b_tap_bytes));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_3d(resb + (size_t)(tap * p.kchunks + kc) * p.b_tap_bytes, &maps.b, &resb_bar[0], kc * KC, 0, tap);
+    }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == PW) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   // epilogue constants and statistics accumulators (the N tile is fixed per CTA only when n_ntiles == 1,
   // so constants are indexed by absolute channel and reloaded per tile below when needed)
-  for (int i = threadIdx.x; i < 2 * 256; i += TC_THREADS) s_stat[i] = 0.f;
-  for (int i = threadIdx.x; i < p.OC; i += TC_THREADS) {
+  for (int i = threadIdx.x; i < 2 * 256; i += NTHREADS) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < p.OC; i += NTHREADS) {
     if (MODE == 0) {
       s_const[i] = p.scale ? p.scale[i] : 1.f;
       s_const[512 + i] = p.shift ? p.shift[i] : 0.f;
@@ -223,34 +248,93 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   const int items = p.kchunks * p.ngroups;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+  if (warp < PW) {
+    if (PROD == 0) {
+      // ===================================================================== TMA producer
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          int t = tile;
+          const int nt = t % p.n_ntiles; t /= p.n_ntiles;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          const int th = t % p.tiles_h;
+          const int n = t / p.tiles_h;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            for (int gi = 0; gi < p.ngroups; ++gi) {
+              const TcGroup& g = p.g[gi];
+              mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
+              unsigned char* sa = smem + (size_t)stage * stage_bytes;
+              unsigned char* sb = sa + p.a_stage_bytes;
+              const uint32_t bytes =
+                  (uint32_t)(g.rows * TC_TW * (int)ROW_BYTES + (p.b_resident ? 0 : g.ntaps * p.b_tap_bytes));
+              mbar_expect_tx(&full_bar[stage], bytes);
+              tma_load_4d(sa, &maps.a[g.map], &full_bar[stage], kc * KC, tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
+              if (!p.b_resident)
+                for (int tp = 0; tp < g.ntaps; ++tp)
+                  tma_load_3d(sb + (size_t)tp * p.b_tap_bytes, &maps.b, &full_bar[stage], kc * KC, nt * BN, g.widx[tp]);
+              if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    } else {
+      // ===================================================================== cp.async producer (64 threads)
+      const int ptid = threadIdx.x;  // 0..63
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
+      int hist[LAG] = {0, 0};        // stages of the last LAG committed groups (oldest first)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % p.n_ntiles; t /= p.n_ntiles;
+        int t = tile / p.n_ntiles;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h;
         const int n = t / p.tiles_h;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int gi = 0; gi < p.ngroups; ++gi) {
             const TcGroup& g = p.g[gi];
+            const TcSrc& src = p.src[g.map];
             mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
-            unsigned char* sa = smem + (size_t)stage * stage_bytes;
-            unsigned char* sb = sa + p.a_stage_bytes;
-            const uint32_t bytes = (uint32_t)(g.rows * TC_TW * (int)ROW_BYTES + g.ntaps * p.b_tap_bytes);
-            mbar_expect_tx(&full_bar[stage], bytes);
-            tma_load_4d(sa, &maps.a[g.map], &full_bar[stage], kc * KC, tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
-            for (int tp = 0; tp < g.ntaps; ++tp)
-              tma_load_3d(sb + (size_t)tp * p.b_tap_bytes, &maps.b, &full_bar[stage], kc * KC, nt * BN, g.widx[tp]);
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const bf16* nbase = src.base + (long long)n * src.sn + kc * KC;
+            const int nchunk = g.rows * TC_TW * CPR;
+            for (int i = ptid; i < nchunk; i += 64) {
+              const int prow = i / CPR, j = i % CPR;
+              const int h = th * TC_TH + g.dh + prow / TC_TW, w = tw * TC_TW + g.dw + prow % TC_TW;
+              const bool ok = h >= 0 && h < src.Hd && w >= 0 && w < src.Wd;
+              const bf16* gp = ok ? nbase + (long long)h * src.sh + (long long)w * src.sw + j * 8 : src.base;
+              const uint32_t off = (uint32_t)prow * ROW_BYTES;
+              const uint32_t dst = sa + off + ((uint32_t)(j ^ (int)((off >> 7) & (CPR - 1))) << 4);
+              const int nbytes = ok ? 16 : 0;   // src-size 0 = zero fill (the conv padding)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ++issued;
+            if (issued > LAG) {
+              // the group committed LAG items ago has landed: publish it to the async proxy, release the stage
+              asm volatile("cp.async.wait_group 2;" ::: "memory");
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              mbar_arrive(&full_bar[hist[0]]);
+            }
+            hist[0] = hist[1];
+            hist[1] = stage;
             if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
           }
         }
       }
+      // drain
+      if (issued >= 2) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[hist[0]]);
+      }
+      if (issued >= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[hist[1]]);
+      }
     }
-  } else if (warp == 1) {
+  } else if (warp == PW) {
     // ===================================================================== MMA issuer
     // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
@@ -258,6 +342,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.b_resident) mbar_wait(&resb_bar[0], 0, p.error_flag, 5);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, p.error_flag, 2);
       tc_fence_after();
@@ -273,7 +358,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t sb = sa + (uint32_t)p.a_stage_bytes;
             for (int tp = 0; tp < g.ntaps; ++tp) {
               const uint32_t a0 = sa + (uint32_t)(g.ro[tp] * TC_TW) * ROW_BYTES;
-              const uint32_t b0 = sb + (uint32_t)(tp * p.b_tap_bytes);
+              const uint32_t b0 = p.b_resident
+                                      ? smem_u32(resb) + (uint32_t)((g.widx[tp] * p.kchunks + kc) * p.b_tap_bytes)
+                                      : sb + (uint32_t)(tp * p.b_tap_bytes);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
                 const uint64_t ad = umma_desc(a0 + k * 32, SBO, LAYOUT);
@@ -295,7 +382,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // warp w may only touch TMEM lanes [32*(w&3), +32); two warps share a quarter and split the
     // 16-column chunks between them (even / odd chunks).
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - (PW + 1)) >> 2;
     const int m = q * 32 + lane;       // row of the tile = pixel
     const int hl = m / TC_TW, wl = m % TC_TW;
     int acc = 0;
@@ -316,31 +403,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int oh = a * p.os + p.oh0, ow = b * p.os + p.ow0;
       const bool valid = a < p.TSH && b < p.TSW && oh < p.OH && ow < p.OW;
       const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
-      // dgrad: the saved-activation operands of this tile are fetched BEFORE waiting for the accumulator,
-      // so their HBM latency hides behind the MMAs instead of serialising the epilogue
-      uint4 sv_pre[8][2];
-      if (MODE == 1) {
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j = half + 2 * jj;
-          if (p.saved && valid && j < BN / 16) {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC +
-                                                              nt * BN + j * 16);
-            sv_pre[jj][0] = __ldg(src);
-            sv_pre[jj][1] = __ldg(src + 1);
-          } else {
-            sv_pre[jj][0] = make_uint4(0, 0, 0, 0);
-            sv_pre[jj][1] = make_uint4(0, 0, 0, 0);
-          }
-        }
-      }
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int j = half + 2 * jj;
-        if (j >= BN / 16) break;
+      for (int j = half; j < BN / 16; j += 2) {
         uint32_t r[16];
         tmem_ld16(taddr0 + (uint32_t)(j * 16), r);
         const int cl = j * 16;          // channel inside the N tile
@@ -360,8 +426,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         __align__(16) bf16 sv[16];
         if (MODE == 1) {
-          reinterpret_cast<uint4*>(sv)[0] = sv_pre[jj][0];
-          reinterpret_cast<uint4*>(sv)[1] = sv_pre[jj][1];
+          if (p.saved && valid) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
+            reinterpret_cast<uint4*>(sv)[0] = __ldg(src);
+            reinterpret_cast<uint4*>(sv)[1] = __ldg(src + 1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
+          }
         }
         tmem_ld_wait();
         __align__(16) bf16 ob[16];
@@ -466,7 +538,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (p.n_ntiles > 1 && (p.stats || p.bn_sums)) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         double* dst = MODE == 0 ? p.stats : p.bn_sums;
-        for (int i = threadIdx.x - 64; i < BN; i += 256) {
+        for (int i = threadIdx.x - (PW + 1) * 32; i < BN; i += 256) {
           const float a1 = s_stat[i], a2 = s_stat[256 + i];
           if (a1 != 0.f || a2 != 0.f) {
             atomicAdd(dst + nt * BN + i, (double)a1);
@@ -487,13 +559,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (p.n_ntiles == 1) {
     double* dst = MODE == 0 ? p.stats : p.bn_sums;
     if (dst) {
-      for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
+      for (int i = threadIdx.x; i < BN; i += NTHREADS) {
         atomicAdd(dst + i, (double)s_stat[i]);
         atomicAdd(dst + p.OC + i, (double)s_stat[256 + i]);
       }
     }
   }
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == PW) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ weights
@@ -920,13 +992,24 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
 }
 
 // Launch the engine on an already described problem.
+static int g_tc_options = 3;  // bit 0: resident weights, bit 1: cp.async producer (debug switch, yg_set_tc_options)
+
 static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_rows, cudaStream_t st) {
   p.a_stage_bytes = max_rows * TC_TW * KCc * 2;
   p.a_stage_bytes = (p.a_stage_bytes + 1023) & ~1023;
   p.b_tap_bytes = p.BN * KCc * 2;
-  const int stage_bytes = p.a_stage_bytes + TC_MAX_TAPS * p.b_tap_bytes;
-  int nst = TC_SMEM_BUDGET / stage_bytes;
-  if (nst > 6) nst = 6;
+  // resident weights: all 9 x kchunks tiles stay in smem if at least 3 A stages still fit
+  const int resb = (9 * p.kchunks * p.b_tap_bytes + 1023) & ~1023;
+  p.b_resident = 0;
+  p.resb_bytes = 0;
+  if ((g_tc_options & 1) && p.n_ntiles == 1 && (TC_SMEM_BUDGET - resb) / p.a_stage_bytes >= 3) {
+    p.b_resident = 1;
+    p.resb_bytes = resb;
+  }
+  const int prod = (p.b_resident && KCc <= 32 && (g_tc_options & 2)) ? 1 : 0;
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : TC_MAX_TAPS * p.b_tap_bytes);
+  int nst = (TC_SMEM_BUDGET - p.resb_bytes) / stage_bytes;
+  if (nst > 8) nst = 8;
   if (nst < 2) {
     set_error("tcgen05 conv: stage of %d bytes does not fit twice in shared memory", stage_bytes);
     return YG_ERR_INVALID;
@@ -940,25 +1023,32 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
     YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   }
   p.error_flag = g_error_flag;
-  const size_t smem = (size_t)nst * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (2 * 256 + 4 * 512 + 16) * sizeof(float) + 64;
+  const size_t smem = (size_t)nst * stage_bytes + p.resb_bytes + 1024 /*align*/ + 256 /*barriers*/ +
+                      (2 * 256 + 4 * 512 + 16) * sizeof(float) + 64;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
-#define TC_LAUNCH(KCV, MODEV)                                                                                      \
-  do {                                                                                                             \
-    YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_tc_kernel<KCV, MODEV><<<grid, TC_THREADS, smem, st>>>(maps, p);                                          \
+#define TC_LAUNCH(KCV, MODEV, PRODV)                                                                                    \
+  do {                                                                                                                  \
+    YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCV, MODEV, PRODV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tc_kernel<KCV, MODEV, PRODV><<<grid, (PRODV ? 2 : 1) * 32 + 288, smem, st>>>(maps, p);                         \
   } while (0)
   if (mode == 0) {
-    if (KCc == 64) TC_LAUNCH(64, 0); else if (KCc == 32) TC_LAUNCH(32, 0); else TC_LAUNCH(16, 0);
+    if (KCc == 64) TC_LAUNCH(64, 0, 0);
+    else if (KCc == 32) { if (prod) TC_LAUNCH(32, 0, 1); else TC_LAUNCH(32, 0, 0); }
+    else { if (prod) TC_LAUNCH(16, 0, 1); else TC_LAUNCH(16, 0, 0); }
   } else {
-    if (KCc == 64) TC_LAUNCH(64, 1); else if (KCc == 32) TC_LAUNCH(32, 1); else TC_LAUNCH(16, 1);
+    if (KCc == 64) TC_LAUNCH(64, 1, 0);
+    else if (KCc == 32) { if (prod) TC_LAUNCH(32, 1, 1); else TC_LAUNCH(32, 1, 0); }
+    else { if (prod) TC_LAUNCH(16, 1, 1); else TC_LAUNCH(16, 1, 0); }
   }
 #undef TC_LAUNCH
   YG_LAUNCH_CHECK("conv_tc_kernel");
   return YG_OK;
 }
+
+int set_tc_options(int v) { g_tc_options = v; return 0; }
 
 // choose KC so that at least 2 stages fit
 static int fit_kc(int K, int BN, int max_rows) {
@@ -1040,6 +1130,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
     rc = make_map(&maps.a[0], xb, 4, dims, str, box, KCc);
     if (rc) return rc;
     for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+    for (int i = 0; i < 4; ++i) p.src[i] = TcSrc{xb, W, H, (long long)Cin, (long long)W * Cin, (long long)H * W * Cin};
     p.ngroups = 3;
     for (int s = 0; s < 3; ++s) {
       TcGroup& g = p.g[s];
@@ -1057,6 +1148,8 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
         uint32_t box[4] = {(uint32_t)KCc, TC_TW, (uint32_t)(ph ? TC_TH + 1 : TC_TH), 1};
         rc = make_map(&maps.a[ph * 2 + pw], xb + ((long long)ph * W + pw) * Cin, 4, dims, str, box, KCc);
         if (rc) return rc;
+        p.src[ph * 2 + pw] = TcSrc{xb + ((long long)ph * W + pw) * Cin, W2, H2, 2LL * Cin, 2LL * W * Cin,
+                                   (long long)H * W * Cin};
       }
     // input row 2*ho + r - 1: r=0 -> (ph=1, h2=ho-1), r=1 -> (ph=0, h2=ho), r=2 -> (ph=1, h2=ho)
     p.ngroups = 6;
@@ -1146,6 +1239,8 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
       rc = make_map(&maps.a[0], gb, 4, dims, str, box, KCc);
       if (rc) break;
       for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+      for (int i = 0; i < 4; ++i)
+        p.src[i] = TcSrc{gb, Wo, Ho, (long long)Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout};
     }
     p.N = N;
     p.tiles_h = cdiv(p.TSH, TC_TH); p.tiles_w = cdiv(p.TSW, TC_TW);
