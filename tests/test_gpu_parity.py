@@ -424,7 +424,7 @@ def test_trainer_step_matches_torch_adamw_and_graph_replay():
         assert abs(la.item() - lb.item()) <= 1e-5 * abs(la.item())
         # gradients agree up to the fp32 summation order of the BN statistics (atomics); Adam's first steps
         # turn a sign flip of a ~0 gradient into a +-lr difference, so parameters are compared statistically
-        torch.testing.assert_close(tr_a.flat_g, tr_b.flat_g, rtol=2e-3, atol=2e-5)
+        assert float((tr_a.flat_g - tr_b.flat_g).norm() / tr_a.flat_g.norm()) < 1e-4
         bad = ((tr_a.flat_p - tr_b.flat_p).abs() > 1e-6 + 1e-5 * tr_a.flat_p.abs()).float().mean().item()
         assert bad < 2e-3, bad
         for rp, p in zip(ref_params, net_a.parameters()):

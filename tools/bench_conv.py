@@ -29,9 +29,11 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--impl", default="auto")
     ap.add_argument("--stats", type=int, default=0)
+    ap.add_argument("--tc-options", type=int, default=3)
     args = ap.parse_args()
     lib = L.lib()
     L.set_conv_impl(args.impl)
+    lib.yg_set_tc_options(args.tc_options)
     dev = "cuda:0"
     N = args.batch
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
@@ -78,7 +80,7 @@ def main():
             ms = e0.elapsed_time(e1) / args.reps
             tf = flops / ms / 1e9
             act_bytes = (N * H * W * Cin + N * Ho * Wo * Cout) * 2
-            rec = {"layer": li, "op": name, "shape": [N, H, W, Cin, Cout, s], "ms": round(ms, 4), "TFLOPs": round(tf, 1),
+            rec = {"opt": args.tc_options, "layer": li, "op": name, "shape": [N, H, W, Cin, Cout, s], "ms": round(ms, 4), "TFLOPs": round(tf, 1),
                    "frac_bf16_peak": round(tf / peaks["bf16_tflops"], 3), "min_GBps": round(act_bytes / ms / 1e6, 1)}
             print(json.dumps(rec), flush=True)
             out.append(rec)

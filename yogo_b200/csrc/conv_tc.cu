@@ -26,7 +26,6 @@ namespace yg {
 
 constexpr int TC_TH = 8, TC_TW = 16;          // output tile (pixels), M = 128
 // conv_tc_kernel: (1 or 2) producer warps + 1 MMA warp + 8 epilogue warps
-constexpr int TC_WG_THREADS = 192;        // wgrad kernel: 2 role warps + 4 epilogue warps
 constexpr int TC_MAX_GROUPS = 9, TC_MAX_TAPS = 3;
 constexpr int TC_SMEM_BUDGET = 227 * 1024 - 14 * 1024;
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;   // bounded mbarrier spin: trap instead of hanging the GPU
@@ -53,7 +52,7 @@ struct TcParams {
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
   int OH, OW, OC, os, oh0, ow0;   // output tensor (NHWC) and tile-space -> output mapping
-  int BN, kchunks, ngroups, nstages;
+  int BN, kchunks, ngroups, nstages, nacc;
   int a_stage_bytes, b_tap_bytes, tmem_cols;
   TcGroup g[TC_MAX_GROUPS];
   void* out;
@@ -199,10 +198,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   unsigned char* resb = smem + (size_t)p.nstages * stage_bytes;
   unsigned char* tail = resb + p.resb_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + 8;
-  uint64_t* tfull_bar = empty_bar + 8;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* resb_bar = tempty_bar + 2;
+  uint64_t* empty_bar = full_bar + 16;
+  uint64_t* tfull_bar = empty_bar + 16;
+  uint64_t* tempty_bar = tfull_bar + 4;
+  uint64_t* resb_bar = tempty_bar + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resb_bar + 2);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
   float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
@@ -214,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
     prefetch_tmap(&maps.b);
     for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], PROD ? 64 : 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     mbar_init(&resb_bar[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -375,7 +374,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ===================================================================== epilogue (8 warps)
@@ -441,31 +440,62 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (MODE == 0) {
           __align__(16) bf16 pb[16];
           const bool rnd = p.stats || p.preact;
+          {
+            // per-channel constants: 128-bit broadcast loads from smem
+            const float4* sh4 = reinterpret_cast<const float4*>(s_k1 + c0);
+            float shf[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(r[i]) * s_k0[c0 + i] + s_k1[c0 + i];
-            if (rnd) x = round_bf16(x);
-            s1[i] = valid ? x : 0.f;
-            s2[i] = valid ? x * x : 0.f;
-            pb[i] = __float2bfloat16_rn(x);
-            r[i] = __float_as_uint(x);
+            for (int i = 0; i < 4; ++i) { const float4 t4 = sh4[i]; shf[4*i] = t4.x; shf[4*i+1] = t4.y; shf[4*i+2] = t4.z; shf[4*i+3] = t4.w; }
+            if (p.scale) {
+              const float4* sc4 = reinterpret_cast<const float4*>(s_k0 + c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t4 = sc4[i];
+                r[4*i]   = __float_as_uint(__uint_as_float(r[4*i])   * t4.x + shf[4*i]);
+                r[4*i+1] = __float_as_uint(__uint_as_float(r[4*i+1]) * t4.y + shf[4*i+1]);
+                r[4*i+2] = __float_as_uint(__uint_as_float(r[4*i+2]) * t4.z + shf[4*i+2]);
+                r[4*i+3] = __float_as_uint(__uint_as_float(r[4*i+3]) * t4.w + shf[4*i+3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + shf[i]);
+            }
+          }
+          if (rnd) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(r[2*i]), __uint_as_float(r[2*i+1]));
+              reinterpret_cast<__nv_bfloat162*>(pb)[i] = pk;
+              const float2 f2 = __bfloat1622float2(pk);
+              r[2*i] = __float_as_uint(f2.x); r[2*i+1] = __float_as_uint(f2.y);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x = __uint_as_float(r[i]);
+              s1[i] = valid ? x : 0.f;
+              s2[i] = valid ? x * x : 0.f;
+            }
           }
           if (p.act == YG_ACT_LRELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float x = __uint_as_float(r[i]);
-              ob[i] = __float2bfloat16_rn((x > 0.f ? x : 0.01f * x) * ds[i]);
+              r[i] = __float_as_uint(fmaxf(x, 0.01f * x));
             }
           } else if (p.act == YG_ACT_SILU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float x = __uint_as_float(r[i]);
-              ob[i] = __float2bfloat16_rn(x * __frcp_rn(1.f + __expf(-x)) * ds[i]);
+              r[i] = __float_as_uint(x * __frcp_rn(1.f + __expf(-x)));
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(__uint_as_float(r[i]) * ds[i]);
           }
+          if (p.dropscale) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * ds[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<__nv_bfloat162*>(ob)[i] = __floats2bfloat162_rn(__uint_as_float(r[2*i]), __uint_as_float(r[2*i+1]));
           if (valid) {
             if (out) {
               uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
@@ -488,12 +518,39 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         } else {
           float pre[16];
+          // saved activations: packed bf16x2 -> float2
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float sval = __bfloat162float(sv[i]);
-            pre[i] = has_bn ? sval * s_k0[c0 + i] + s_k1[c0 + i] : sval;
-            s2[i] = has_bn ? (sval - s_k2[c0 + i]) * s_k3[c0 + i] : 0.f;  // xhat
-            s1[i] = __uint_as_float(r[i]) * ds[i];
+          for (int i = 0; i < 8; ++i) {
+            const float2 f2 = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sv)[i]);
+            pre[2*i] = f2.x; pre[2*i+1] = f2.y;
+          }
+          if (has_bn) {
+            const float4* k0 = reinterpret_cast<const float4*>(s_k0 + c0);
+            const float4* k1 = reinterpret_cast<const float4*>(s_k1 + c0);
+            const float4* k2 = reinterpret_cast<const float4*>(s_k2 + c0);
+            const float4* k3 = reinterpret_cast<const float4*>(s_k3 + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 a4 = k0[i], b4 = k1[i], m4 = k2[i], i4 = k3[i];
+              const float sc_[4] = {a4.x, a4.y, a4.z, a4.w}, sh_[4] = {b4.x, b4.y, b4.z, b4.w};
+              const float mn_[4] = {m4.x, m4.y, m4.z, m4.w}, is_[4] = {i4.x, i4.y, i4.z, i4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float sval = pre[4*i+k];
+                s2[4*i+k] = (sval - mn_[k]) * is_[k];     // xhat
+                pre[4*i+k] = sval * sc_[k] + sh_[k];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s2[i] = 0.f;
+          }
+          if (p.dropscale) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s1[i] = __uint_as_float(r[i]) * ds[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s1[i] = __uint_as_float(r[i]);
           }
           if (p.saved) {
             if (p.act == YG_ACT_LRELU) {
@@ -508,12 +565,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float g = s1[i];
-            if (p.bn_sums) g = round_bf16(g);
-            ob[i] = __float2bfloat16_rn(g);
-            s1[i] = valid ? g : 0.f;
-            s2[i] = valid ? g * s2[i] : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(s1[2*i], s1[2*i+1]);
+            reinterpret_cast<__nv_bfloat162*>(ob)[i] = pk;
+            if (p.bn_sums) {
+              const float2 f2 = __bfloat1622float2(pk);
+              s1[2*i] = f2.x; s1[2*i+1] = f2.y;
+            }
+          }
+          if (p.bn_sums) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float g = valid ? s1[i] : 0.f;
+              s1[i] = g;
+              s2[i] = g * s2[i];
+            }
           }
           if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
@@ -548,7 +614,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -583,6 +649,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
 }
 
 // ------------------------------------------------------------------------------------------ host
+static int g_tc_options = 1;  // bit 0: resident weights, bit 1: cp.async producer (yg_set_tc_options)
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;
 static int* g_error_flag = nullptr;  // device int, reports which barrier wait timed out
@@ -658,6 +725,8 @@ struct TwParams {
   int kb, nbblocks, a_block_bytes, b_block_bytes, stage_bytes, nstages, tmem_cols;
   int ngroups;                 // groups per filter column
   TwGroup g[3][2];
+  TcSrc asrc;        // dz as seen by the cp.async producer
+  TcSrc bsrc[4];     // x (or its parity sub-grids)
   float* partial;
   int* error_flag;
 };
@@ -672,9 +741,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
   return d;
 }
 
-template <int KB, int KA>
-__global__ void __launch_bounds__(TC_WG_THREADS, 1)
+template <int KB, int KA, int PROD>
+__global__ void __launch_bounds__((PROD ? 2 : 1) * 32 + 160, 1)
 wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwParams p) {
+  constexpr int PW = PROD ? 2 : 1;                        // producer warps; MMA warp = PW; epilogue PW+1..PW+4
+  constexpr int NTHREADS = PW * 32 + 160;
+  constexpr int CPRA = KA / 8, CPRB = KB / 8;             // 16-byte chunks per operand row
   constexpr uint32_t ROWB = KB * 2;                       // bytes per pixel row of a B block
   constexpr uint32_t LAYOUT_B = KB == 64 ? 2u : (KB == 32 ? 4u : 6u);
   constexpr uint32_t ROWA = KA * 2;                       // A blocks are KA couts wide (64: SWIZZLE_128B, 32: 64B)
@@ -697,7 +769,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a);
     for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.b[i]);
-    for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], PROD ? 64 : 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&done_bar[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -706,20 +778,50 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     for (int st = 0; st < p.nstages; ++st) {
       uint4* z = reinterpret_cast<uint4*>(smem + (size_t)st * p.stage_bytes + (size_t)a_blocks * p.a_block_bytes);
       const int n16 = (MBLOCKS - a_blocks) * p.a_block_bytes / 16;
-      for (int i = threadIdx.x; i < n16; i += TC_WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < n16; i += NTHREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == PW) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp < PW) {
+    if (PROD == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
+          int t = tile;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          const int th = t % p.tiles_h;
+          const int n = t / p.tiles_h;
+          for (int gi = 0; gi < p.ngroups; ++gi) {
+            const TwGroup& g = p.g[sg][gi];
+            mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 11);
+            unsigned char* sa = smem + (size_t)stage * p.stage_bytes;
+            unsigned char* sb = sa + MBLOCKS * p.a_block_bytes;
+            const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + p.nbblocks * g.rows * TC_TW * (int)ROWB);
+            mbar_expect_tx(&full_bar[stage], bytes);
+            for (int ab = 0; ab < a_blocks; ++ab)
+              tma_load_4d(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * KA, tw * TC_TW,
+                          th * TC_TH, n);
+            for (int bb = 0; bb < p.nbblocks; ++bb)
+              tma_load_4d(sb + (size_t)bb * p.b_block_bytes, &maps.b[g.map], &full_bar[stage], nt * BNW + bb * KB,
+                          tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else {
+      // cp.async producer (64 threads): both operands written in their swizzled MN-major layouts by hand
+      const int ptid = threadIdx.x;
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
+      int hist[2] = {0, 0};
       for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
         int t = tile;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -727,22 +829,65 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
         const int n = t / p.tiles_h;
         for (int gi = 0; gi < p.ngroups; ++gi) {
           const TwGroup& g = p.g[sg][gi];
+          const TcSrc& src = p.bsrc[g.map];
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 11);
-          unsigned char* sa = smem + (size_t)stage * p.stage_bytes;
-          unsigned char* sb = sa + MBLOCKS * p.a_block_bytes;
-          const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + p.nbblocks * g.rows * TC_TW * (int)ROWB);
-          mbar_expect_tx(&full_bar[stage], bytes);
-          for (int ab = 0; ab < a_blocks; ++ab)
-            tma_load_4d(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * KA, tw * TC_TW,
-                        th * TC_TH, n);
-          for (int bb = 0; bb < p.nbblocks; ++bb)
-            tma_load_4d(sb + (size_t)bb * p.b_block_bytes, &maps.b[g.map], &full_bar[stage], nt * BNW + bb * KB,
-                        tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)MBLOCKS * (uint32_t)p.a_block_bytes;
+          // A = dz tile: a_blocks x (128 pixel rows x KA couts)
+          const int na = a_blocks * 128 * CPRA;
+          for (int i = ptid; i < na; i += 64) {
+            const int j = i % CPRA, prow = (i / CPRA) % 128, ab = i / (CPRA * 128);
+            const int h = th * TC_TH + prow / TC_TW, w = tw * TC_TW + prow % TC_TW;
+            const bool ok = h < p.asrc.Hd && w < p.asrc.Wd;
+            const bf16* gp = ok ? p.asrc.base + (long long)n * p.asrc.sn + (long long)h * p.asrc.sh +
+                                      (long long)w * p.asrc.sw + mt * 128 + ab * KA + j * 8
+                                : p.asrc.base;
+            const uint32_t off = (uint32_t)prow * ROWA;
+            const uint32_t dst = sa + (uint32_t)ab * (uint32_t)p.a_block_bytes + off +
+                                 ((uint32_t)(j ^ (int)((off >> 7) & (CPRA - 1))) << 4);
+            const int nbytes = ok ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
+          }
+          // B = x halo tile: nbblocks x (rows*16 pixel rows x KB cins)
+          const int rowsB = g.rows * TC_TW;
+          const int nb = p.nbblocks * rowsB * CPRB;
+          for (int i = ptid; i < nb; i += 64) {
+            const int j = i % CPRB, prow = (i / CPRB) % rowsB, bb = i / (CPRB * rowsB);
+            const int h = th * TC_TH + g.dh + prow / TC_TW, w = tw * TC_TW + g.dw + prow % TC_TW;
+            const bool ok = h >= 0 && h < src.Hd && w >= 0 && w < src.Wd;
+            const bf16* gp = ok ? src.base + (long long)n * src.sn + (long long)h * src.sh + (long long)w * src.sw +
+                                      nt * BNW + bb * KB + j * 8
+                                : src.base;
+            const uint32_t off = (uint32_t)prow * ROWB;
+            const uint32_t dst = sb + (uint32_t)bb * (uint32_t)p.b_block_bytes + off +
+                                 ((uint32_t)(j ^ (int)((off >> 7) & (CPRB - 1))) << 4);
+            const int nbytes = ok ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          ++issued;
+          if (issued > 2) {
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full_bar[hist[0]]);
+          }
+          hist[0] = hist[1];
+          hist[1] = stage;
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (issued >= 2) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[hist[0]]);
+      }
+      if (issued >= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[hist[1]]);
+      }
     }
-  } else if (warp == 1) {
+  } else if (warp == PW) {
     // D=f32, A=B=bf16, both MN-major (bits 15,16), N = BNW, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(BNW >> 3) << 17) | ((128u >> 4) << 24);
@@ -807,7 +952,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == PW) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
@@ -920,6 +1065,7 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
     uint32_t box[4] = {(uint32_t)ka, TC_TW, TC_TH, 1};
     rc = make_map(&maps.a, dz, 4, dims, str, box, ka);
     if (rc) return rc;
+    p.asrc = TcSrc{(const bf16*)dz, Wo, Ho, (long long)Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout};
   }
   const bf16* xb = (const bf16*)x;
   if (stride == 1) {
@@ -929,6 +1075,7 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
     rc = make_map(&maps.b[0], xb, 4, dims, str, box, kb);
     if (rc) return rc;
     for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+    for (int i = 0; i < 4; ++i) p.bsrc[i] = TcSrc{xb, W, H, (long long)Cin, (long long)W * Cin, (long long)H * W * Cin};
     p.ngroups = 1;
     for (int s = 0; s < 3; ++s) {
       TwGroup& g = p.g[s][0];
@@ -945,6 +1092,8 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
         uint32_t box[4] = {(uint32_t)kb, TC_TW, (uint32_t)(ph ? TC_TH + 1 : TC_TH), 1};
         rc = make_map(&maps.b[ph * 2 + pw], xb + ((long long)ph * W + pw) * Cin, 4, dims, str, box, kb);
         if (rc) return rc;
+        p.bsrc[ph * 2 + pw] = TcSrc{xb + ((long long)ph * W + pw) * Cin, W2, H2, 2LL * Cin, 2LL * W * Cin,
+                                    (long long)H * W * Cin};
       }
     p.ngroups = 2;
     for (int s = 0; s < 3; ++s) {
@@ -965,13 +1114,21 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   }
   p.error_flag = g_error_flag;
   const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 512;
-#define TW_LAUNCH(KBV, KAV)                                                                                          \
-  do {                                                                                                               \
-    YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV, KAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    wgrad_tc_kernel<KBV, KAV><<<grid, TC_WG_THREADS, smem, st>>>(maps, p);                                           \
+const int prodw = (kb <= 32 && nst >= 3 && (g_tc_options & 2)) ? 1 : 0;
+#define TW_LAUNCH(KBV, KAV, PRODV)                                                                                       \
+  do {                                                                                                                   \
+    YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV, KAV, PRODV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    wgrad_tc_kernel<KBV, KAV, PRODV><<<grid, (PRODV ? 2 : 1) * 32 + 160, smem, st>>>(maps, p);                           \
   } while (0)
-  if (ka == 64) { if (kb == 64) TW_LAUNCH(64, 64); else if (kb == 32) TW_LAUNCH(32, 64); else TW_LAUNCH(16, 64); }
-  else { if (kb == 64) TW_LAUNCH(64, 32); else if (kb == 32) TW_LAUNCH(32, 32); else TW_LAUNCH(16, 32); }
+  if (ka == 64) {
+    if (kb == 64) TW_LAUNCH(64, 64, 0);
+    else if (kb == 32) { if (prodw) TW_LAUNCH(32, 64, 1); else TW_LAUNCH(32, 64, 0); }
+    else { if (prodw) TW_LAUNCH(16, 64, 1); else TW_LAUNCH(16, 64, 0); }
+  } else {
+    if (kb == 64) TW_LAUNCH(64, 32, 0);
+    else if (kb == 32) { if (prodw) TW_LAUNCH(32, 32, 1); else TW_LAUNCH(32, 32, 0); }
+    else { if (prodw) TW_LAUNCH(16, 32, 1); else TW_LAUNCH(16, 32, 0); }
+  }
 #undef TW_LAUNCH
   YG_LAUNCH_CHECK("wgrad_tc_kernel");
   const long long nw = (long long)Cout * Cin * 9;
@@ -992,8 +1149,6 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
 }
 
 // Launch the engine on an already described problem.
-static int g_tc_options = 3;  // bit 0: resident weights, bit 1: cp.async producer (debug switch, yg_set_tc_options)
-
 static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_rows, cudaStream_t st) {
   p.a_stage_bytes = max_rows * TC_TW * KCc * 2;
   p.a_stage_bytes = (p.a_stage_bytes + 1023) & ~1023;
@@ -1009,21 +1164,24 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   const int prod = (p.b_resident && KCc <= 32 && (g_tc_options & 2)) ? 1 : 0;
   const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : TC_MAX_TAPS * p.b_tap_bytes);
   int nst = (TC_SMEM_BUDGET - p.resb_bytes) / stage_bytes;
-  if (nst > 8) nst = 8;
+  if (nst > 16) nst = 16;
   if (nst < 2) {
     set_error("tcgen05 conv: stage of %d bytes does not fit twice in shared memory", stage_bytes);
     return YG_ERR_INVALID;
   }
   p.nstages = nst;
+  // as many TMEM accumulators as fit in the 512 columns (up to 4): decouples MMA bursts from the epilogue
+  p.nacc = 512 / p.BN;
+  if (p.nacc > 4) p.nacc = 4;
   int cols = 32;
-  while (cols < 2 * p.BN) cols <<= 1;
+  while (cols < p.nacc * p.BN) cols <<= 1;
   p.tmem_cols = cols;
   if (!g_error_flag) {
     YG_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
     YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   }
   p.error_flag = g_error_flag;
-  const size_t smem = (size_t)nst * stage_bytes + p.resb_bytes + 1024 /*align*/ + 256 /*barriers*/ +
+  const size_t smem = (size_t)nst * stage_bytes + p.resb_bytes + 1024 /*align*/ + 512 /*barriers*/ +
                       (2 * 256 + 4 * 512 + 16) * sizeof(float) + 64;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
