@@ -437,4 +437,4 @@ def test_trainer_step_matches_torch_adamw_and_graph_replay():
     # BN buffers advanced identically in both modes
     for (ka, va), (kb, vb) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
         if "running_" in ka or "num_batches" in ka:
-            torch.testing.assert_close(va.float(), vb.float(), rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(va.float(), vb.float(), rtol=1e-4, atol=1e-6)

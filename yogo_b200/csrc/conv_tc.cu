@@ -53,6 +53,7 @@ struct TcParams {
   TcSrc src[4];
   int OH, OW, OC, os, oh0, ow0;   // output tensor (NHWC) and tile-space -> output mapping
   int BN, kchunks, ngroups, nstages, nacc;
+  int gpi, a_box_bytes;   // groups merged into one pipeline item (small-K layers), bytes reserved per A box
   int a_stage_bytes, b_tap_bytes, tmem_cols;
   TcGroup g[TC_MAX_GROUPS];
   void* out;
@@ -194,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases: align by hand, do not trust the attribute
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : TC_MAX_TAPS * p.b_tap_bytes);
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.gpi * TC_MAX_TAPS * p.b_tap_bytes);
   unsigned char* resb = smem + (size_t)p.nstages * stage_bytes;
   unsigned char* tail = resb + p.resb_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -245,7 +246,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int items = p.kchunks * p.ngroups;
+  const int ipk = p.ngroups / p.gpi;          // items per K chunk
+  const int items = p.kchunks * ipk;
 
   if (warp < PW) {
     if (PROD == 0) {
@@ -260,18 +262,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const int th = t % p.tiles_h;
           const int n = t / p.tiles_h;
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            for (int gi = 0; gi < p.ngroups; ++gi) {
-              const TcGroup& g = p.g[gi];
+            for (int g0 = 0; g0 < p.ngroups; g0 += p.gpi) {
               mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
               unsigned char* sa = smem + (size_t)stage * stage_bytes;
               unsigned char* sb = sa + p.a_stage_bytes;
-              const uint32_t bytes =
-                  (uint32_t)(g.rows * TC_TW * (int)ROW_BYTES + (p.b_resident ? 0 : g.ntaps * p.b_tap_bytes));
+              uint32_t bytes = 0;
+              for (int gi = g0; gi < g0 + p.gpi; ++gi)
+                bytes += (uint32_t)(p.g[gi].rows * TC_TW * (int)ROW_BYTES + (p.b_resident ? 0 : p.g[gi].ntaps * p.b_tap_bytes));
               mbar_expect_tx(&full_bar[stage], bytes);
-              tma_load_4d(sa, &maps.a[g.map], &full_bar[stage], kc * KC, tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
-              if (!p.b_resident)
-                for (int tp = 0; tp < g.ntaps; ++tp)
-                  tma_load_3d(sb + (size_t)tp * p.b_tap_bytes, &maps.b, &full_bar[stage], kc * KC, nt * BN, g.widx[tp]);
+              for (int gi = g0; gi < g0 + p.gpi; ++gi) {
+                const TcGroup& g = p.g[gi];
+                tma_load_4d(sa + (size_t)(gi - g0) * p.a_box_bytes, &maps.a[g.map], &full_bar[stage], kc * KC,
+                            tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
+                if (!p.b_resident)
+                  for (int tp = 0; tp < g.ntaps; ++tp)
+                    tma_load_3d(sb + (size_t)((gi - g0) * TC_MAX_TAPS + tp) * p.b_tap_bytes, &maps.b, &full_bar[stage],
+                                kc * KC, nt * BN, g.widx[tp]);
+              }
               if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -290,22 +297,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int th = t % p.tiles_h;
         const int n = t / p.tiles_h;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int gi = 0; gi < p.ngroups; ++gi) {
-            const TcGroup& g = p.g[gi];
-            const TcSrc& src = p.src[g.map];
+          for (int g0 = 0; g0 < p.ngroups; g0 += p.gpi) {
             mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
-            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-            const bf16* nbase = src.base + (long long)n * src.sn + kc * KC;
-            const int nchunk = g.rows * TC_TW * CPR;
-            for (int i = ptid; i < nchunk; i += 64) {
-              const int prow = i / CPR, j = i % CPR;
-              const int h = th * TC_TH + g.dh + prow / TC_TW, w = tw * TC_TW + g.dw + prow % TC_TW;
-              const bool ok = h >= 0 && h < src.Hd && w >= 0 && w < src.Wd;
-              const bf16* gp = ok ? nbase + (long long)h * src.sh + (long long)w * src.sw + j * 8 : src.base;
-              const uint32_t off = (uint32_t)prow * ROW_BYTES;
-              const uint32_t dst = sa + off + ((uint32_t)(j ^ (int)((off >> 7) & (CPR - 1))) << 4);
-              const int nbytes = ok ? 16 : 0;   // src-size 0 = zero fill (the conv padding)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
+            for (int gi = g0; gi < g0 + p.gpi; ++gi) {
+              const TcGroup& g = p.g[gi];
+              const TcSrc& src = p.src[g.map];
+              const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes) + (uint32_t)((gi - g0) * p.a_box_bytes);
+              const bf16* nbase = src.base + (long long)n * src.sn + kc * KC;
+              const int nchunk = g.rows * TC_TW * CPR;
+              for (int i = ptid; i < nchunk; i += 64) {
+                const int prow = i / CPR, j = i % CPR;
+                const int h = th * TC_TH + g.dh + prow / TC_TW, w = tw * TC_TW + g.dw + prow % TC_TW;
+                const bool ok = h >= 0 && h < src.Hd && w >= 0 && w < src.Wd;
+                const bf16* gp = ok ? nbase + (long long)h * src.sh + (long long)w * src.sw + j * 8 : src.base;
+                const uint32_t off = (uint32_t)prow * ROW_BYTES;
+                const uint32_t dst = sa + off + ((uint32_t)(j ^ (int)((off >> 7) & (CPR - 1))) << 4);
+                const int nbytes = ok ? 16 : 0;   // src-size 0 = zero fill (the conv padding)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
+              }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             ++issued;
@@ -348,23 +357,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       int item = 0;
       for (int kc = 0; kc < p.kchunks; ++kc) {
-        for (int gi = 0; gi < p.ngroups; ++gi, ++item) {
-          const TcGroup& g = p.g[gi];
+        for (int g0 = 0; g0 < p.ngroups; g0 += p.gpi, ++item) {
           mbar_wait(&full_bar[stage], phase, p.error_flag, 3);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t sb = sa + (uint32_t)p.a_stage_bytes;
-            for (int tp = 0; tp < g.ntaps; ++tp) {
-              const uint32_t a0 = sa + (uint32_t)(g.ro[tp] * TC_TW) * ROW_BYTES;
-              const uint32_t b0 = p.b_resident
-                                      ? smem_u32(resb) + (uint32_t)((g.widx[tp] * p.kchunks + kc) * p.b_tap_bytes)
-                                      : sb + (uint32_t)(tp * p.b_tap_bytes);
+            const uint32_t sa0 = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa0 + (uint32_t)p.a_stage_bytes;
+            for (int gi = g0; gi < g0 + p.gpi; ++gi) {
+              const TcGroup& g = p.g[gi];
+              const uint32_t sa = sa0 + (uint32_t)((gi - g0) * p.a_box_bytes);
+              for (int tp = 0; tp < g.ntaps; ++tp) {
+                const uint32_t a0 = sa + (uint32_t)(g.ro[tp] * TC_TW) * ROW_BYTES;
+                const uint32_t b0 = p.b_resident
+                                        ? smem_u32(resb) + (uint32_t)((g.widx[tp] * p.kchunks + kc) * p.b_tap_bytes)
+                                        : sb + (uint32_t)(((gi - g0) * TC_MAX_TAPS + tp) * p.b_tap_bytes);
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                const uint64_t ad = umma_desc(a0 + k * 32, SBO, LAYOUT);
-                const uint64_t bd = umma_desc(b0 + k * 32, SBO, LAYOUT);
-                umma_bf16(d_tmem, ad, bd, idesc, (item > 0 || tp > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint64_t ad = umma_desc(a0 + k * 32, SBO, LAYOUT);
+                  const uint64_t bd = umma_desc(b0 + k * 32, SBO, LAYOUT);
+                  umma_bf16(d_tmem, ad, bd, idesc, (item > 0 || gi > g0 || tp > 0 || k > 0) ? 1u : 0u);
+                }
               }
             }
             umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
@@ -1150,8 +1162,11 @@ const int prodw = (kb <= 32 && nst >= 3 && (g_tc_options & 2)) ? 1 : 0;
 
 // Launch the engine on an already described problem.
 static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_rows, cudaStream_t st) {
-  p.a_stage_bytes = max_rows * TC_TW * KCc * 2;
-  p.a_stage_bytes = (p.a_stage_bytes + 1023) & ~1023;
+  p.a_box_bytes = (max_rows * TC_TW * KCc * 2 + 1023) & ~1023;
+  // small-K layers: merge all tap groups of a K chunk into one pipeline item, so that the fixed per-item
+  // cost (mbarrier round trips, MMA issue, commit) is paid once per tile instead of 3-6 times
+  p.gpi = (p.ngroups * p.a_box_bytes <= 32 * 1024) ? p.ngroups : 1;
+  p.a_stage_bytes = p.gpi * p.a_box_bytes;
   p.b_tap_bytes = p.BN * KCc * 2;
   // resident weights: all 9 x kchunks tiles stay in smem if at least 3 A stages still fit
   const int resb = (9 * p.kchunks * p.b_tap_bytes + 1023) & ~1023;
@@ -1162,7 +1177,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
     p.resb_bytes = resb;
   }
   const int prod = (p.b_resident && KCc <= 32 && (g_tc_options & 2)) ? 1 : 0;
-  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : TC_MAX_TAPS * p.b_tap_bytes);
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.gpi * TC_MAX_TAPS * p.b_tap_bytes);
   int nst = (TC_SMEM_BUDGET - p.resb_bytes) / stage_bytes;
   if (nst > 16) nst = 16;
   if (nst < 2) {
