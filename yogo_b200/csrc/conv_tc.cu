@@ -414,6 +414,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int oh = a * p.os + p.oh0, ow = b * p.os + p.ow0;
       const bool valid = a < p.TSH && b < p.TSW && oh < p.OH && ow < p.OW;
       const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
+      if (MODE == 1 && p.saved && half == 0) {
+        // pull the saved-activation rows of the tile after next into L2 now: by the time its epilogue runs,
+        // the 32-byte operand loads hit L2 instead of paying an HBM round trip per 16-column chunk
+        const int tile2 = tile + 2 * (int)gridDim.x;
+        if (tile2 < p.total_tiles) {
+          int t2 = tile2;
+          const int nt2 = t2 % p.n_ntiles; t2 /= p.n_ntiles;
+          const int tw2 = t2 % p.tiles_w; t2 /= p.tiles_w;
+          const int th2 = t2 % p.tiles_h;
+          const int n2 = t2 / p.tiles_h;
+          const int a2 = th2 * TC_TH + hl, b2 = tw2 * TC_TW + wl;
+          const int oh2 = a2 * p.os + p.oh0, ow2 = b2 * p.os + p.ow0;
+          if (a2 < p.TSH && b2 < p.TSW && oh2 < p.OH && ow2 < p.OW) {
+            const bf16* row = reinterpret_cast<const bf16*>(p.saved) +
+                              (((long long)n2 * p.OH + oh2) * p.OW + ow2) * p.OC + nt2 * BN;
+            for (int c = 0; c < BN; c += 64)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c));
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
