@@ -255,11 +255,12 @@ def run_ours(args):
 
     # ---- per-kernel breakdown with CUDA events (instrumented pass, not part of `value`)
     roof = None
-    breakdown = None
+    # every rank runs the instrumented steps (they contain collectives); rank 0 reports them
+    saved_graph, trainer._graph = trainer._graph, None  # the breakdown needs individual launches
+    breakdown = kernel_breakdown(trainer, dev_imgs, dev_labs, args, L)
+    trainer._graph = saved_graph
+    barrier()
     if rank == 0:
-        saved_graph, trainer._graph = trainer._graph, None  # the breakdown needs individual launches
-        breakdown = kernel_breakdown(trainer, dev_imgs, dev_labs, args, L)
-        trainer._graph = saved_graph
         roof = roofline_from_breakdown(breakdown, args, B)
 
     if rank == 0:

@@ -94,6 +94,18 @@ int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, const void* da
                       float* dw, float* dshift, float clip, void* workspace, size_t workspace_bytes,
                       void* stream);
 size_t yg_conv_first_bwd_workspace(int Cin, int Cout);
+/* Single-channel images (Cin == 1): the 9-tap Gram statistics of the image, gram[54] = S[9] then the upper
+ * triangle of G[9][9] (fp64, overwritten).  With them the BatchNorm batch statistics of the first layer
+ * (yg_conv_first_stats_from_gram: stats[2*Cout] += sum y, sum y^2) and the BN part of its backward
+ * (yg_conv_first_bwd_finalize, from P = sum g*x_t and Sg = sum g as produced by yg_conv_first_bwd with
+ * bn_dy_mean == NULL) follow in closed form instead of extra passes over the 16-channel activations. */
+int yg_conv_first_gram(const void* x, int x_dtype, int N, int H, int W, int stride, double* gram, void* stream);
+int yg_conv_first_stats_from_gram(const double* gram, const float* w, const float* bias, double count, int Cout,
+                                  double* stats, void* stream);
+int yg_conv_first_bwd_finalize(const float* P, const float* Sg, const double* gram, const float* w, const float* bias,
+                               const float* gamma, const float* mean, const float* invstd, double count,
+                               int batch_stats, float clip, int Cout, float* dw, float* dbias, float* dgamma,
+                               float* dbeta, void* stream);
 
 /* ---- generic convolution (3x3 pad 1 or 1x1 pad 0, stride 1 or 2), NHWC -------------
  * replaces nn.Conv2d fprop / dgrad / wgrad (cuDNN) at model_defns.py:34-67 and the

@@ -19,6 +19,8 @@ LAYERS = {2: (386, 516, 16, 32, 1), 3: (386, 516, 32, 64, 2), 4: (193, 258, 64, 
 DOUBLE = {12: (386, 516, 32, 64, 1), 13: (386, 516, 64, 128, 2), 14: (193, 258, 128, 256, 1), 15: (193, 258, 256, 256, 2),
           16: (97, 129, 256, 256, 1)}
 LAYERS.update(DOUBLE)
+# W-folded views of layer 2 (same bytes, 2x / 4x channels): tests the TMA row-rate hypothesis
+LAYERS.update({22: (386, 258, 32, 64, 1), 23: (386, 129, 64, 128, 1), 32: (386, 258, 64, 64, 1)})
 
 
 def main():

@@ -71,6 +71,13 @@ _PROTOS = {
          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p],
     ),
     "yg_conv_first_bwd_workspace": (c_size_t, [c_int, c_int]),
+    "yg_conv_first_gram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "yg_conv_first_stats_from_gram": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p]),
+    "yg_conv_first_bwd_finalize": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_float, c_int,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "yg_conv_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(FwdEpilogue), c_void_p],

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(FL_THREADS, 4) conv_first_bwd_kernel(
       if (MODE == 0) { s1[c] += g; s2[c] += g * xhat; }
       else {
         // BN backward: dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); scl = gamma*invstd
-        dzv[c] = be.bn_scale ? scl[c] * (g - m1[c] - xhat * m2[c]) : g;
+        dzv[c] = (be.bn_scale && dy_mean) ? scl[c] * (g - m1[c] - xhat * m2[c]) : g;
         s1[c] += dzv[c];
       }
     }
@@ -322,4 +322,163 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
 
 extern "C" size_t yg_conv_first_bwd_workspace(int Cin, int Cout) {
   return (size_t)FL_BWD_BLOCKS * ((size_t)Cout * Cin * 9 + Cout) * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-channel images: BatchNorm statistics and the BN part of the backward are obtained
+// algebraically from the 9-tap Gram matrix of the image instead of extra passes over the activations.
+//   y_c(px) = sum_t w[c][t] x_t(px) (+ bias)            x_t = the 9 shifted / strided views of the image
+//   sum y_c   = w_c . S + bias*M,   sum y_c^2 = w_c^T G w_c + 2 bias (w_c . S) + bias^2 M
+//   S_t = sum_px x_t,  G[t][t'] = sum_px x_t x_t'        (channel independent, 9 + 45 numbers)
+// Backward: P[c][t] = sum g x_t and Sg[c] = sum g come from ONE pass over (da, image); sum g*xhat,
+// dgamma, dbeta and dW follow in closed form from P, Sg, S, G (yg_conv_first_bwd_finalize).
+// ------------------------------------------------------------------------------------------------
+namespace yg {
+
+constexpr int GR_THREADS = 256;
+
+template <typename TX>
+__global__ void __launch_bounds__(GR_THREADS) first_gram_kernel(const TX* __restrict__ x, int N, int H, int W,
+                                                                int Ho, int Wo, int stride, double* __restrict__ gram) {
+  float S[9], G[45];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) S[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 45; ++i) G[i] = 0.f;
+  const long long total = (long long)N * Ho * Wo;
+  for (long long q = (long long)blockIdx.x * GR_THREADS + threadIdx.x; q < total; q += (long long)gridDim.x * GR_THREADS) {
+    const int n = (int)(q / ((long long)Ho * Wo));
+    const int p = (int)(q % ((long long)Ho * Wo));
+    const int ho = p / Wo, wo = p % Wo;
+    const TX* xp = x + (long long)n * H * W;
+    float v[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = ho * stride - 1 + r;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = wo * stride - 1 + s;
+        v[r * 3 + s] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? to_f<TX>(xp[(long long)ih * W + iw]) : 0.f;
+      }
+    }
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+      S[a] += v[a];
+#pragma unroll
+      for (int b = a; b < 9; ++b) G[k++] += v[a] * v[b];
+    }
+  }
+  __shared__ double red[54];
+  if (threadIdx.x < 54) red[threadIdx.x] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float s = warp_sum(S[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], (double)s);
+  }
+#pragma unroll
+  for (int i = 0; i < 45; ++i) {
+    const float s = warp_sum(G[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[9 + i], (double)s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 54) atomicAdd(&gram[threadIdx.x], red[threadIdx.x]);
+}
+
+__device__ __forceinline__ double gram_at(const double* gram, int a, int b) {
+  if (a > b) { const int t = a; a = b; b = t; }
+  // upper triangle, row-major: offset(a) = sum_{i<a} (9 - i) = a*9 - a*(a-1)/2
+  return gram[9 + a * 9 - a * (a - 1) / 2 + (b - a)];
+}
+
+__global__ void first_stats_from_gram_kernel(const double* __restrict__ gram, const float* __restrict__ w,
+                                             const float* __restrict__ bias, double count, int Cout,
+                                             double* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cout) return;
+  double ws = 0.0, q = 0.0;
+  for (int a = 0; a < 9; ++a) {
+    const double wa = w[c * 9 + a];
+    ws += wa * gram[a];
+    for (int b = 0; b < 9; ++b) q += wa * (double)w[c * 9 + b] * gram_at(gram, a, b);
+  }
+  const double bi = bias ? (double)bias[c] : 0.0;
+  stats[c] += ws + bi * count;
+  stats[Cout + c] += q + 2.0 * bi * ws + bi * bi * count;
+}
+
+__global__ void first_bwd_finalize_kernel(const float* __restrict__ P, const float* __restrict__ Sg,
+                                          const double* __restrict__ gram, const float* __restrict__ w,
+                                          const float* __restrict__ bias, const float* __restrict__ gamma,
+                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                          double count, int batch_stats, float clip, int Cout,
+                                          float* __restrict__ dw, float* __restrict__ dbias,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cout) return;
+  const double bi = bias ? (double)bias[c] : 0.0;
+  const double mu = mean[c], is = invstd[c], ga = gamma ? (double)gamma[c] : 1.0;
+  const double sg = Sg[c];
+  double wp = 0.0;
+  for (int t = 0; t < 9; ++t) wp += (double)w[c * 9 + t] * (double)P[c * 9 + t];
+  const double sgx = is * (wp + (bi - mu) * sg);  // sum g * xhat
+  if (dgamma) dgamma[c] = clampf((float)sgx, clip);
+  if (dbeta) dbeta[c] = clampf((float)sg, clip);
+  const double m1 = batch_stats ? sg / count : 0.0, m2 = batch_stats ? sgx / count : 0.0;
+  const double scl = ga * is;
+  double sum_x = 0.0;  // sum over pixels of xhat (for d bias)
+  for (int t = 0; t < 9; ++t) {
+    double wg = 0.0;
+    for (int u = 0; u < 9; ++u) wg += (double)w[c * 9 + u] * gram_at(gram, u, t);
+    const double X = is * (wg + (bi - mu) * gram[t]);  // sum xhat * x_t
+    dw[c * 9 + t] = clampf((float)(scl * ((double)P[c * 9 + t] - m1 * gram[t] - m2 * X)), clip);
+  }
+  if (dbias) {
+    double ws = 0.0;
+    for (int t = 0; t < 9; ++t) ws += (double)w[c * 9 + t] * gram[t];
+    sum_x = is * (ws + (bi - mu) * count);
+    dbias[c] = clampf((float)(scl * (sg - m1 * count - m2 * sum_x)), clip);
+  }
+}
+
+}  // namespace yg
+
+extern "C" int yg_conv_first_gram(const void* x, int x_dtype, int N, int H, int W, int stride, double* gram,
+                                  void* stream) {
+  YG_CHECK_ARG(x && gram, "conv_first_gram: null pointer");
+  YG_CHECK_ARG(x_dtype == YG_U8 || x_dtype == YG_F32, "conv_first_gram: x_dtype %d", x_dtype);
+  YG_CHECK_ARG(stride == 1 || stride == 2, "conv_first_gram: stride %d", stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  YG_CUDA(cudaMemsetAsync(gram, 0, 54 * sizeof(double), st));
+  if (N == 0) return YG_OK;
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  long long nblk = ((long long)N * Ho * Wo + GR_THREADS - 1) / GR_THREADS;
+  if (nblk > 148 * 4) nblk = 148 * 4;
+  if (x_dtype == YG_U8)
+    first_gram_kernel<uint8_t><<<(unsigned)nblk, GR_THREADS, 0, st>>>((const uint8_t*)x, N, H, W, Ho, Wo, stride, gram);
+  else
+    first_gram_kernel<float><<<(unsigned)nblk, GR_THREADS, 0, st>>>((const float*)x, N, H, W, Ho, Wo, stride, gram);
+  YG_LAUNCH_CHECK("first_gram");
+  return YG_OK;
+}
+
+extern "C" int yg_conv_first_stats_from_gram(const double* gram, const float* w, const float* bias, double count,
+                                             int Cout, double* stats, void* stream) {
+  YG_CHECK_ARG(gram && w && stats && Cout > 0, "conv_first_stats_from_gram: bad arguments");
+  first_stats_from_gram_kernel<<<cdiv(Cout, 64), 64, 0, (cudaStream_t)stream>>>(gram, w, bias, count, Cout, stats);
+  YG_LAUNCH_CHECK("first_stats_from_gram");
+  return YG_OK;
+}
+
+extern "C" int yg_conv_first_bwd_finalize(const float* P, const float* Sg, const double* gram, const float* w,
+                                          const float* bias, const float* gamma, const float* mean,
+                                          const float* invstd, double count, int batch_stats, float clip, int Cout,
+                                          float* dw, float* dbias, float* dgamma, float* dbeta, void* stream) {
+  YG_CHECK_ARG(P && Sg && gram && w && mean && invstd && dw && Cout > 0, "conv_first_bwd_finalize: bad arguments");
+  first_bwd_finalize_kernel<<<cdiv(Cout, 64), 64, 0, (cudaStream_t)stream>>>(P, Sg, gram, w, bias, gamma, mean, invstd,
+                                                                             count, batch_stats, clip, Cout, dw, dbias,
+                                                                             dgamma, dbeta);
+  YG_LAUNCH_CHECK("first_bwd_finalize");
+  return YG_OK;
 }

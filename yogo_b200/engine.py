@@ -223,10 +223,24 @@ class Runner:
                 else:
                     mean = torch.empty(blk.cout, dtype=torch.float32, device=dev)
                     invstd, scale, shift = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
+                    use_gram = first_direct and blk.cin == 1
+                    if use_gram and want_grad:
+                        # 9-tap Gram statistics of the image: BN statistics now, BN backward later (first_layer.cu)
+                        gram = torch.empty(54, dtype=torch.float64, device=dev)
+                        L.check(lib.yg_conv_first_gram(x.data_ptr(), x_code, N, h, w, blk.stride, gram.data_ptr(), st))
+                        rec["gram"] = gram
                     if bn_train:
                         stats = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
                         y_raw = None if first_direct else torch.empty_like(out)
-                        conv(_fwd_ep(shift=bias, stats=stats), y_raw)  # pass 1: conv (+bias) and statistics
+                        if use_gram:
+                            if "gram" not in rec:
+                                gram = torch.empty(54, dtype=torch.float64, device=dev)
+                                L.check(lib.yg_conv_first_gram(x.data_ptr(), x_code, N, h, w, blk.stride,
+                                                               gram.data_ptr(), st))
+                            L.check(lib.yg_conv_first_stats_from_gram(gram.data_ptr(), wt.data_ptr(), L.ptr(bias),
+                                                                      float(N * ho * wo), blk.cout, stats.data_ptr(), st))
+                        else:
+                            conv(_fwd_ep(shift=bias, stats=stats), y_raw)  # pass 1: conv (+bias) and statistics
                         L.check(lib.yg_bn_finalize(stats.data_ptr(), float(N * ho * wo), g.data_ptr(), b.data_ptr(),
                                                    bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                                    float(bn.momentum), float(bn.eps), mean.data_ptr(),
@@ -352,6 +366,30 @@ class Runner:
                 nb = lib.yg_conv_first_bwd_workspace(blk.cin, blk.cout)
                 ws = L.workspace.get("first_bwd", nb, dev)
                 m1 = m2 = None
+                if blk.bn is not None and "gram" in rec:
+                    # one pass over (da, image): P = sum g*x_t, Sg = sum g; everything else in closed form
+                    P = torch.empty(blk.cout * 9, dtype=torch.float32, device=dev)
+                    Sg = torch.empty(blk.cout, dtype=torch.float32, device=dev)
+                    epp = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), rec["scale"].data_ptr(),
+                                        rec["shift"].data_ptr(), rec["mean"].data_ptr(), rec["invstd"].data_ptr(), None)
+                    L.check(lib.yg_conv_first_bwd(x.data_ptr(), x_code, wt.data_ptr(), g.data_ptr(), dcode, N, h, w,
+                                                  blk.cin, blk.cout, blk.stride, C.byref(epp), L.ptr(rec.get("fwd_shift")),
+                                                  None, None, P.data_ptr(), Sg.data_ptr(), 0.0, ws.data_ptr(), nb, st))
+                    dgam = gbuf(blk.bn.weight)
+                    dbet = gbuf(blk.bn.bias)
+                    L.check(lib.yg_conv_first_bwd_finalize(P.data_ptr(), Sg.data_ptr(), rec["gram"].data_ptr(),
+                                                           wt.data_ptr(), L.ptr(rec.get("fwd_shift")),
+                                                           rec["gamma"].data_ptr(), rec["mean"].data_ptr(),
+                                                           rec["invstd"].data_ptr(), float(N * ho * wo),
+                                                           1 if rec["bn_train"] else 0, clip, blk.cout, dw.data_ptr(),
+                                                           L.ptr(db), dgam.data_ptr(), dbet.data_ptr(), st))
+                    grads[id(blk.bn.weight)] = dgam
+                    grads[id(blk.bn.bias)] = dbet
+                    grads[id(blk.conv.weight)] = dw
+                    if db is not None:
+                        grads[id(blk.conv.bias)] = db
+                    done(blk.conv.weight, blk.conv.bias, blk.bn.weight, blk.bn.bias)
+                    continue
                 if blk.bn is not None:
                     sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
                     ep1 = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), rec["scale"].data_ptr(),
@@ -372,6 +410,9 @@ class Runner:
                         M = float(N * ho * wo)
                         m1 = (sums[: blk.cout] / M).float().contiguous()
                         m2 = (sums[blk.cout :] / M).float().contiguous()
+                    else:
+                        m1 = torch.zeros(blk.cout, dtype=torch.float32, device=dev)
+                        m2 = torch.zeros_like(m1)
                     ep2 = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), rec["scale"].data_ptr(),
                                         rec["shift"].data_ptr(), rec["mean"].data_ptr(), rec["invstd"].data_ptr(), None)
                 else:
