@@ -31,7 +31,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--impl", default="auto")
     ap.add_argument("--stats", type=int, default=0)
-    ap.add_argument("--tc-options", type=int, default=3)
+    ap.add_argument("--tc-options", type=int, default=1)
+    ap.add_argument("--no-saved", type=int, default=0)
     args = ap.parse_args()
     lib = L.lib()
     L.set_conv_impl(args.impl)
@@ -61,7 +62,7 @@ def main():
             L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(ep), st))
 
         def dgrad():
-            ep = L.BwdEpilogue(x.data_ptr(), 1, None, None, None, None, None, None)
+            ep = L.BwdEpilogue(None if args.no_saved else x.data_ptr(), 1, None, None, None, None, None, None)
             L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(ep), st))
 
         def wgrad():
