@@ -54,6 +54,7 @@ struct TcParams {
   int OH, OW, OC, os, oh0, ow0;   // output tensor (NHWC) and tile-space -> output mapping
   int BN, kchunks, ngroups, nstages, nacc;
   int gpi, a_box_bytes;   // groups merged into one pipeline item (small-K layers), bytes reserved per A box
+  int pf_ahead;           // L2 prefetch distance in tiles (0 = off)
   int a_stage_bytes, b_tap_bytes, tmem_cols;
   TcGroup g[TC_MAX_GROUPS];
   void* out;
@@ -181,10 +182,10 @@ __device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(_
 // writing the swizzled layout by hand - for 16/32-channel tensors, whose 32/64-byte rows make TMA
 // request-rate bound (~4-8 cycles per row measured) - with all weights resident in shared memory.
 template <int KC, int MODE, int PROD>
-__global__ void __launch_bounds__((PROD ? 2 : 1) * 32 + 288, 1)
+__global__ void __launch_bounds__((PROD ? 2 : 1) * 32 + 320, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   constexpr int PW = PROD ? 2 : 1;             // producer warps; MMA warp = PW; epilogue warps PW+1 .. PW+8
-  constexpr int NTHREADS = PW * 32 + 288;
+  constexpr int NTHREADS = PW * 32 + 320;      // + 1 MMA warp + 8 epilogue warps + 1 L2-prefetch warp
   constexpr int CPR = KC / 8;                  // 16-byte chunks per operand row
   constexpr int LAG = 2;                       // cp.async groups kept in flight per producer thread
   constexpr uint32_t ROW_BYTES = KC * 2;
@@ -204,6 +205,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   uint64_t* tempty_bar = tfull_bar + 4;
   uint64_t* resb_bar = tempty_bar + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resb_bar + 2);
+  volatile int* prod_iter = reinterpret_cast<volatile int*>(tmem_slot + 1);  // producer's tile-loop counter
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
   float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
 
@@ -216,6 +218,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], PROD ? 64 : 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     mbar_init(&resb_bar[0], 1);
+    *prod_iter = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (p.b_resident) {
@@ -255,7 +258,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
+        int iter = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          *prod_iter = iter++;
           int t = tile;
           const int nt = t % p.n_ntiles; t /= p.n_ntiles;
           const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -387,6 +392,37 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp == PW + 9) {
+    // ===================================================================== L2 prefetch warp
+    // Pulls the A-operand halo boxes of the tile TC_PF_AHEAD iterations ahead from HBM into L2 with plain
+    // prefetch instructions, so that the TMA loads of the (shared-memory-limited, 2-3 stage) pipeline see L2
+    // latency instead of HBM latency.  Costs no shared memory and no TMA issue slots.
+    if (PROD == 0 && p.pf_ahead > 0) {
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+        if (tile % p.n_ntiles != 0) continue;   // the A operand is shared by the N tiles of a pixel tile
+        while (iter > *prod_iter + p.pf_ahead) __nanosleep(256);
+        int t = tile / p.n_ntiles;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        for (int gi = 0; gi < p.ngroups; ++gi) {
+          const TcGroup& g = p.g[gi];
+          const TcSrc& src = p.src[g.map];
+          const int npx = g.rows * TC_TW;
+          // one 128-byte line per (pixel, 64-channel slice); contiguous pixels share lines when C < 64
+          const int lines_per_px = (p.kchunks * KC * 2 + 127) / 128;
+          for (int i = lane; i < npx * lines_per_px; i += 32) {
+            const int px = i / lines_per_px, ln = i % lines_per_px;
+            const int h = th * TC_TH + g.dh + px / TC_TW, w = tw * TC_TW + g.dw + px % TC_TW;
+            if (h >= 0 && h < src.Hd && w >= 0 && w < src.Wd) {
+              const bf16* a = src.base + (long long)n * src.sn + (long long)h * src.sh + (long long)w * src.sw + ln * 64;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+          }
+        }
+      }
     }
   } else {
     // ===================================================================== epilogue (8 warps)
@@ -681,7 +717,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int g_tc_options = 1;  // bit 0: resident weights, bit 1: cp.async producer (yg_set_tc_options)
+static int g_tc_options = 5;  // bit 0: resident weights, bit 1: cp.async producer, bit 2: L2 prefetch warp
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;
 static int* g_error_flag = nullptr;  // device int, reports which barrier wait timed out
@@ -1216,6 +1252,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
     YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   }
   p.error_flag = g_error_flag;
+  p.pf_ahead = (g_tc_options & 4) ? 2 : 0;
   const size_t smem = (size_t)nst * stage_bytes + p.resb_bytes + 1024 /*align*/ + 512 /*barriers*/ +
                       (2 * 256 + 4 * 512 + 16) * sizeof(float) + 64;
   int dev = 0, sms = 148;
@@ -1225,7 +1262,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
 #define TC_LAUNCH(KCV, MODEV, PRODV)                                                                                    \
   do {                                                                                                                  \
     YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCV, MODEV, PRODV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_tc_kernel<KCV, MODEV, PRODV><<<grid, (PRODV ? 2 : 1) * 32 + 288, smem, st>>>(maps, p);                         \
+    conv_tc_kernel<KCV, MODEV, PRODV><<<grid, (PRODV ? 2 : 1) * 32 + 320, smem, st>>>(maps, p);                         \
   } while (0)
   if (mode == 0) {
     if (KCc == 64) TC_LAUNCH(64, 0, 0);
