@@ -35,6 +35,16 @@ CASES = [
     ("wgrad", 2, 19, 35, 16, 64, 1),
     ("wgrad", 1, 16, 32, 256, 256, 1),
     ("wgrad", 64, 97, 129, 128, 128, 1),
+    # W-folded small-channel layers (W divisible by 4 / 2)
+    ("fwd", 2, 19, 36, 16, 32, 1),
+    ("fwd", 2, 19, 36, 32, 64, 1),
+    ("fwd", 2, 13, 40, 8, 16, 1),
+    ("dgrad", 2, 19, 36, 16, 32, 1),
+    ("dgrad", 2, 19, 36, 32, 64, 1),
+    ("dgrad", 2, 13, 40, 8, 16, 1),
+    ("wgrad", 2, 19, 36, 16, 32, 1),
+    ("wgrad", 2, 19, 36, 32, 64, 1),
+    ("wgrad", 3, 13, 40, 8, 16, 1),
 ]
 if os.environ.get("TC_ONLY"):
     CASES = [c for c in CASES if c[0] in os.environ["TC_ONLY"].split(",")]

@@ -21,9 +21,9 @@ int conv_dgrad_simt(const void*, const float*, void*, int, int, int, int, int, i
 int conv_wgrad_simt(const void*, const void*, float*, float*, int, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
 size_t simt_wgrad_workspace(int, int, int, int, int, int, int);
 // conv_tc.cu
-bool tc_fwd_supported(int dtype, int Cin, int Cout, int ks, int stride);
-bool tc_dgrad_supported(int dtype, int Cin, int Cout, int ks, int stride);
-bool tc_wgrad_supported(int dtype, int Cin, int Cout, int ks, int stride);
+bool tc_fwd_supported(int dtype, int W, int Cin, int Cout, int ks, int stride);
+bool tc_dgrad_supported(int dtype, int W, int Cin, int Cout, int ks, int stride);
+bool tc_wgrad_supported(int dtype, int W, int Cin, int Cout, int ks, int stride);
 int conv_fwd_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const FwdEpi&, cudaStream_t);
 int conv_dgrad_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const BwdEpi&, cudaStream_t);
 int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
@@ -72,7 +72,7 @@ extern "C" int yg_conv_fwd(const void* x, const float* w, void* y, int dtype, in
   YG_CHECK_ARG(x && w, "conv_fwd: null pointer");
   if (N == 0) return YG_OK;
   FwdEpi ep = make_fwd_epi(epp);
-  const bool tc_ok = tc_fwd_supported(dtype, Cin, Cout, ks, stride);
+  const bool tc_ok = tc_fwd_supported(dtype, W, Cin, Cout, ks, stride);
   if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
     set_error("conv_fwd: tcgen05 path forced but shape unsupported (dtype %d Cin %d Cout %d k %d s %d)", dtype, Cin, Cout, ks, stride);
     return YG_ERR_INVALID;
@@ -89,7 +89,7 @@ extern "C" int yg_conv_dgrad(const void* dz, const float* w, void* dx, int dtype
   YG_CHECK_ARG(dz && w && dx, "conv_dgrad: null pointer");
   if (N == 0) return YG_OK;
   BwdEpi be = make_bwd_epi(bep);
-  const bool tc_ok = tc_dgrad_supported(dtype, Cin, Cout, ks, stride);
+  const bool tc_ok = tc_dgrad_supported(dtype, W, Cin, Cout, ks, stride);
   if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
     set_error("conv_dgrad: tcgen05 path forced but shape unsupported");
     return YG_ERR_INVALID;
@@ -112,7 +112,7 @@ extern "C" int yg_conv_wgrad(const void* x, const void* dz, float* dw, float* db
   if (rc) return rc;
   YG_CHECK_ARG(x && dz && dw, "conv_wgrad: null pointer");
   YG_CHECK_ARG(N >= 1, "conv_wgrad: empty batch");
-  const bool tc_ok = tc_wgrad_supported(dtype, Cin, Cout, ks, stride);
+  const bool tc_ok = tc_wgrad_supported(dtype, W, Cin, Cout, ks, stride);
   if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
     set_error("conv_wgrad: tcgen05 path forced but shape unsupported");
     return YG_ERR_INVALID;

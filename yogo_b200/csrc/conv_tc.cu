@@ -39,6 +39,7 @@ struct TcGroup {
   int map, dh, dw, rows, ntaps;
   int ro[TC_MAX_TAPS];    // A row offset (in tile rows) of each tap inside the halo box
   int widx[TC_MAX_TAPS];  // weight slice index
+  unsigned kmask[TC_MAX_TAPS];  // bit kk: global 16-wide K step kk of this tap has non-zero weights (W-folded convs)
 };
 
 struct TcSrc {            // A-operand source as seen by the cp.async producer (element strides)
@@ -52,6 +53,7 @@ struct TcParams {
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
   int OH, OW, OC, os, oh0, ow0;   // output tensor (NHWC) and tile-space -> output mapping
+  int OCr;                        // real channel count (OC / W-fold factor): per-channel arrays are indexed modulo OCr
   int BN, kchunks, ngroups, nstages, nacc;
   int gpi, a_box_bytes;   // groups merged into one pipeline item (small-K layers), bytes reserved per A box
   int pf_ahead;           // L2 prefetch distance in tiles (0 = off)
@@ -234,14 +236,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   // so constants are indexed by absolute channel and reloaded per tile below when needed)
   for (int i = threadIdx.x; i < 2 * 256; i += NTHREADS) s_stat[i] = 0.f;
   for (int i = threadIdx.x; i < p.OC; i += NTHREADS) {
+    const int ir = i % p.OCr;
     if (MODE == 0) {
-      s_const[i] = p.scale ? p.scale[i] : 1.f;
-      s_const[512 + i] = p.shift ? p.shift[i] : 0.f;
+      s_const[i] = p.scale ? p.scale[ir] : 1.f;
+      s_const[512 + i] = p.shift ? p.shift[ir] : 0.f;
     } else if (p.bn_scale) {
-      s_const[i] = p.bn_scale[i];
-      s_const[512 + i] = p.bn_shift[i];
-      s_const[1024 + i] = p.bn_mean[i];
-      s_const[1536 + i] = p.bn_invstd[i];
+      s_const[i] = p.bn_scale[ir];
+      s_const[512 + i] = p.bn_shift[ir];
+      s_const[1024 + i] = p.bn_mean[ir];
+      s_const[1536 + i] = p.bn_invstd[ir];
     }
   }
   tc_fence_before();
@@ -361,6 +364,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       int item = 0;
+      uint32_t started = 0;   // 0 until the first MMA of this tile has been issued (overwrite vs accumulate)
       for (int kc = 0; kc < p.kchunks; ++kc) {
         for (int g0 = 0; g0 < p.ngroups; g0 += p.gpi, ++item) {
           mbar_wait(&full_bar[stage], phase, p.error_flag, 3);
@@ -376,11 +380,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 const uint32_t b0 = p.b_resident
                                         ? smem_u32(resb) + (uint32_t)((g.widx[tp] * p.kchunks + kc) * p.b_tap_bytes)
                                         : sb + (uint32_t)(((gi - g0) * TC_MAX_TAPS + tp) * p.b_tap_bytes);
+                const unsigned km = g.kmask[tp] >> (kc * KSTEPS);
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
+                  if (!((km >> k) & 1u)) continue;   // structurally zero weights (W-folded convolution)
                   const uint64_t ad = umma_desc(a0 + k * 32, SBO, LAYOUT);
                   const uint64_t bd = umma_desc(b0 + k * 32, SBO, LAYOUT);
-                  umma_bf16(d_tmem, ad, bd, idesc, (item > 0 || gi > g0 || tp > 0 || k > 0) ? 1u : 0u);
+                  umma_bf16(d_tmem, ad, bd, idesc, started);
+                  started = 1u;
                 }
               }
             }
@@ -481,7 +488,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // global operands of this chunk are fetched while the TMEM load is in flight
         float ds[16];
         if (p.dropscale) {
-          const float4* dp = reinterpret_cast<const float4*>(p.dropscale + (long long)n * p.OC + c0);
+          const float4* dp = reinterpret_cast<const float4*>(p.dropscale + (long long)n * p.OCr + (c0 % p.OCr));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 v4 = __ldg(dp + i);
@@ -675,8 +682,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         for (int i = threadIdx.x - (PW + 1) * 32; i < BN; i += 256) {
           const float a1 = s_stat[i], a2 = s_stat[256 + i];
           if (a1 != 0.f || a2 != 0.f) {
-            atomicAdd(dst + nt * BN + i, (double)a1);
-            atomicAdd(dst + p.OC + nt * BN + i, (double)a2);
+            atomicAdd(dst + (nt * BN + i) % p.OCr, (double)a1);
+            atomicAdd(dst + p.OCr + (nt * BN + i) % p.OCr, (double)a2);
           }
           s_stat[i] = 0.f; s_stat[256 + i] = 0.f;
         }
@@ -694,8 +701,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     double* dst = MODE == 0 ? p.stats : p.bn_sums;
     if (dst) {
       for (int i = threadIdx.x; i < BN; i += NTHREADS) {
-        atomicAdd(dst + i, (double)s_stat[i]);
-        atomicAdd(dst + p.OC + i, (double)s_stat[256 + i]);
+        atomicAdd(dst + i % p.OCr, (double)s_stat[i]);
+        atomicAdd(dst + p.OCr + i % p.OCr, (double)s_stat[256 + i]);
       }
     }
   }
@@ -703,21 +710,60 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 }
 
 // ------------------------------------------------------------------------------------------ weights
-// OIHW fp32 -> bf16 [tap][Cout][Cin] (transpose == 0, fprop) or [tap][Cin][Cout] (transpose == 1, dgrad)
+// OIHW fp32 -> bf16 [tap][Cout][Cin] (transpose == 0, fprop) or [tap][Cin][Cout] (transpose == 1, dgrad).
+// W-fold factor g > 1: the NHWC tensors are viewed as (N, H, W/g, g*C) - g adjacent pixels become one
+// "super pixel" - and the 3x3 convolution becomes a 3x3 convolution over super pixels with structured weights
+//   W'[tap=(r,s')][(q,co)][(pi,ci)] = W[co][ci][r][s],  s = g*(s'-1) + pi - q + 1  (zero if s is not in 0..2).
+// Same bytes, g x fewer and g x longer TMA rows, K and N large enough for efficient UMMA tiles.
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int taps,
-                                    int transpose) {
-  const long long total = (long long)Cout * Cin * taps;
+                                    int transpose, int g) {
+  const int Cof = Cout * g, Cif = Cin * g;
+  const long long total = (long long)Cof * Cif * taps;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int inner, outer, tap;
-  if (!transpose) { inner = (int)(i % Cin); outer = (int)((i / Cin) % Cout); tap = (int)(i / ((long long)Cin * Cout)); }
-  else { inner = (int)(i % Cout); outer = (int)((i / Cout) % Cin); tap = (int)(i / ((long long)Cin * Cout)); }
-  const int co = transpose ? inner : outer, ci = transpose ? outer : inner;
-  out[i] = __float2bfloat16_rn(w[((long long)co * Cin + ci) * taps + tap]);
+  if (!transpose) { inner = (int)(i % Cif); outer = (int)((i / Cif) % Cof); tap = (int)(i / ((long long)Cif * Cof)); }
+  else { inner = (int)(i % Cof); outer = (int)((i / Cof) % Cif); tap = (int)(i / ((long long)Cif * Cof)); }
+  const int cof = transpose ? inner : outer, cif = transpose ? outer : inner;
+  const int q = cof / Cout, co = cof % Cout, pi = cif / Cin, ci = cif % Cin;
+  const int r = tap / 3, sp = tap % 3;
+  const int sreal = g * (sp - 1) + pi - q + 1;
+  float v = 0.f;
+  if (sreal >= 0 && sreal <= 2) v = w[((long long)co * Cin + ci) * taps + r * 3 + sreal];
+  out[i] = __float2bfloat16_rn(v);
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int g_tc_options = 5;  // bit 0: resident weights, bit 1: cp.async producer, bit 2: L2 prefetch warp
+static int g_tc_options = 9;  // bit 0: resident weights, bit 1: cp.async producer, bit 2: L2 prefetch warp, bit 3: W-fold
+// W-fold factor for stride-1 convolutions with few channels (see pack_weights_kernel): fold while the folded
+// input channel count stays <= 64 and everything remains a legal UMMA shape.
+static int fold_factor(int Cin, int Cout, int W, int stride) {
+  if (stride != 1 || !(g_tc_options & 8)) return 1;
+  for (int g = 4; g >= 2; g >>= 1)
+    if (W % g == 0 && g * Cin <= 64 && g * Cout <= 256 && (g * Cin) % 16 == 0 && (g * Cout) % 16 == 0) return g;
+  return 1;
+}
+// bit kk set <=> K step kk (16 folded channels) of folded tap column sp touches a sub-pixel with non-zero weights.
+// kdim_is_input: K runs over (pi, ci) [fprop / wgrad-B], otherwise over (q, co) [dgrad].
+static unsigned fold_kmask(int g, int Cr, int sp, bool kdim_is_input) {
+  if (g == 1) return 0xFFFFFFFFu;
+  unsigned valid = 0;  // valid sub-pixel indices of the K dimension
+  for (int a = 0; a < g; ++a)
+    for (int b = 0; b < g; ++b) {
+      const int pi = kdim_is_input ? a : b, q = kdim_is_input ? b : a;
+      const int sreal = g * (sp - 1) + pi - q + 1;
+      if (sreal >= 0 && sreal <= 2) valid |= 1u << a;
+    }
+  unsigned m = 0;
+  const int ksteps = g * Cr / 16;
+  for (int kk = 0; kk < ksteps && kk < 32; ++kk) {
+    const int lo = (kk * 16) / Cr, hi = (kk * 16 + 15) / Cr;
+    for (int a = lo; a <= hi && a < g; ++a)
+      if ((valid >> a) & 1u) m |= 1u << kk;
+  }
+  return m;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;
 static int* g_error_flag = nullptr;  // device int, reports which barrier wait timed out
@@ -759,11 +805,15 @@ static int pick_bn(int Nc) {
   return 0;
 }
 
-bool tc_fwd_supported(int dtype, int Cin, int Cout, int ks, int stride) {
-  return dtype == YG_BF16 && ks == 3 && pick_kc(Cin) && pick_bn(Cout) && Cout <= 512 && (stride == 1 || stride == 2);
+bool tc_fwd_supported(int dtype, int W, int Cin, int Cout, int ks, int stride) {
+  if (dtype != YG_BF16 || ks != 3 || (stride != 1 && stride != 2)) return false;
+  const int g = fold_factor(Cin, Cout, W, stride);
+  return pick_kc(Cin * g) && pick_bn(Cout * g) && Cout * g <= 512;
 }
-bool tc_dgrad_supported(int dtype, int Cin, int Cout, int ks, int stride) {
-  return dtype == YG_BF16 && ks == 3 && pick_kc(Cout) && pick_bn(Cin) && Cin <= 512 && (stride == 1 || stride == 2);
+bool tc_dgrad_supported(int dtype, int W, int Cin, int Cout, int ks, int stride) {
+  if (dtype != YG_BF16 || ks != 3 || (stride != 1 && stride != 2)) return false;
+  const int g = fold_factor(Cin, Cout, W, stride);
+  return pick_kc(Cout * g) && pick_bn(Cin * g) && Cin * g <= 512;
 }
 
 
@@ -1023,19 +1073,28 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   if (warp == PW) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// Sums the per-CTA partials in a fixed order.  The kernel ran on (possibly W-folded) dimensions Coutf = g*Cout,
+// Cinf = g*Cin; a real weight (co, ci, r, s) collects every folded position (q, pi, s') with
+// s = g*(s'-1) + pi - q + 1 (g = 1: the identity).
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
-                                       int BNW, int n_mtiles, int nunits, int nslices, float clip) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over [co][ci][r][s]
+                                       int g, int BNW, int n_mtiles, int nunits, int nslices, float clip) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over real [co][ci][r][s]
   if (i >= (long long)Cout * Cin * 9) return;
   const int s = (int)(i % 3), r = (int)((i / 3) % 3);
   const int ci = (int)((i / 9) % Cin), co = (int)(i / (9LL * Cin));
-  const int mt = co / 128, nt = ci / BNW;
-  const int unit = s + 3 * (mt + n_mtiles * nt);
   float acc = 0.f;
-  for (int sl = 0; sl < nslices; ++sl) {
-    const size_t cta = (size_t)unit + (size_t)nunits * sl;
-    acc += partial[((cta * 3 + r) * 128 + (co % 128)) * BNW + (ci % BNW)];
-  }
+  for (int sp = 0; sp < 3; ++sp)
+    for (int q = 0; q < g; ++q) {
+      const int pi = s - 1 + q - g * (sp - 1);
+      if (pi < 0 || pi >= g) continue;
+      const int cof = q * Cout + co, cif = pi * Cin + ci;
+      const int mt = cof / 128, nt = cif / BNW;
+      const int unit = sp + 3 * (mt + n_mtiles * nt);
+      for (int sl = 0; sl < nslices; ++sl) {
+        const size_t cta = (size_t)unit + (size_t)nunits * sl;
+        acc += partial[((cta * 3 + r) * 128 + (cof % 128)) * BNW + (cif % BNW)];
+      }
+    }
   dw[i] = clampf(acc, clip);
 }
 
@@ -1068,8 +1127,10 @@ static int wgrad_bnw(int Cin, int kb) {
   return 0;
 }
 
-bool tc_wgrad_supported(int dtype, int Cin, int Cout, int ks, int stride) {
+bool tc_wgrad_supported(int dtype, int W, int Cin, int Cout, int ks, int stride) {
   if (dtype != YG_BF16 || ks != 3 || (stride != 1 && stride != 2)) return false;
+  const int g = fold_factor(Cin, Cout, W, stride);
+  Cin *= g; Cout *= g;
   if (Cout % 32 != 0) return false;
   const int kb = pick_kc(Cin);
   return kb != 0 && wgrad_bnw(Cin, kb) != 0;
@@ -1091,7 +1152,9 @@ static void wgrad_grid(int Cin, int Cout, int* nunits, int* nslices, int* grid, 
 }
 
 size_t tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ks, int stride) {
-  if (!tc_wgrad_supported(YG_BF16, Cin, Cout, ks, stride)) return 0;
+  if (!tc_wgrad_supported(YG_BF16, W, Cin, Cout, ks, stride)) return 0;
+  const int g = fold_factor(Cin, Cout, W, stride);
+  Cin *= g; Cout *= g;
   int nunits, nslices, grid, bnw, nm, nn;
   wgrad_grid(Cin, Cout, &nunits, &nslices, &grid, &bnw, &nm, &nn);
   return (size_t)grid * 3 * 128 * bnw * sizeof(float) + (size_t)COLSUM_BLOCKS * Cout * sizeof(float) + 256;
@@ -1102,6 +1165,10 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
   const size_t need = tc_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
   if (!ws || ws_bytes < need) { set_error("conv_wgrad_tc: workspace %zu < %zu", ws_bytes, need); return YG_ERR_WORKSPACE; }
+  // W-folded view (see pack_weights_kernel): from here on W, Cin, Cout are the folded dimensions
+  const int fg = fold_factor(Cin, Cout, W, stride);
+  const int Cin_r = Cin, Cout_r = Cout, Wo_r = (W + 2 - 3) / stride + 1;
+  W /= fg; Cin *= fg; Cout *= fg;
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   TwMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -1199,18 +1266,18 @@ const int prodw = (kb <= 32 && nst >= 3 && (g_tc_options & 2)) ? 1 : 0;
   }
 #undef TW_LAUNCH
   YG_LAUNCH_CHECK("wgrad_tc_kernel");
-  const long long nw = (long long)Cout * Cin * 9;
-  wgrad_tc_reduce_kernel<<<cdiv(nw, 256), 256, 0, st>>>((const float*)ws, dw, Cout, Cin, p.BNW, p.n_mtiles, p.nunits,
-                                                        p.nslices, clip);
+  const long long nw = (long long)Cout_r * Cin_r * 9;
+  wgrad_tc_reduce_kernel<<<cdiv(nw, 256), 256, 0, st>>>((const float*)ws, dw, Cout_r, Cin_r, fg, p.BNW, p.n_mtiles,
+                                                        p.nunits, p.nslices, clip);
   YG_LAUNCH_CHECK("wgrad_tc_reduce");
   if (dbias) {
     float* part = (float*)((char*)ws + (size_t)grid * 3 * 128 * p.BNW * sizeof(float));
-    const long long npix = (long long)N * Ho * Wo;
+    const long long npix = (long long)N * Ho * Wo_r;   // the bias gradient is taken on the real (unfolded) view
     const int nblk = (int)(npix < COLSUM_BLOCKS ? npix : COLSUM_BLOCKS);
-    dim3 g2(nblk, cdiv(Cout, 128));
-    colsum_partial_kernel<bf16><<<g2, 128, 0, st>>>((const bf16*)dz, part, npix, Cout);
+    dim3 g2(nblk, cdiv(Cout_r, 128));
+    colsum_partial_kernel<bf16><<<g2, 128, 0, st>>>((const bf16*)dz, part, npix, Cout_r);
     YG_LAUNCH_CHECK("colsum_partial");
-    colsum_final_kernel<<<cdiv(Cout, 128), 128, 0, st>>>(part, dbias, Cout, nblk, clip);
+    colsum_final_kernel<<<cdiv(Cout_r, 128), 128, 0, st>>>(part, dbias, Cout_r, nblk, clip);
     YG_LAUNCH_CHECK("colsum_final");
   }
   return YG_OK;
@@ -1306,8 +1373,8 @@ struct PackKey {
 static std::map<PackKey, std::pair<void*, size_t>> g_pack_cache;
 static std::mutex g_pack_mutex;
 
-static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int transpose, cudaStream_t st) {
-  const long long total = (long long)Cout * Cin * 9;
+static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int transpose, int g, cudaStream_t st) {
+  const long long total = (long long)Cout * Cin * 9 * g * g;
   {
     std::lock_guard<std::mutex> lock(g_pack_mutex);
     int dev = 0;
@@ -1324,7 +1391,7 @@ static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int trans
       *out = (bf16*)it->second.first;
     }
   }
-  pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, *out, Cout, Cin, 9, transpose);
+  pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, *out, Cout, Cin, 9, transpose, g);
   YG_LAUNCH_CHECK("pack_weights");
   return YG_OK;
 }
@@ -1332,6 +1399,10 @@ static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int trans
 int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int Cin, int Cout, int ks, int stride,
                 const FwdEpi& ep, cudaStream_t st) {
   if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  // W-folded view for small-channel stride-1 layers: from here on W, Cin, Cout are the folded dimensions
+  const int fg = fold_factor(Cin, Cout, W, stride);
+  const int Cin_r = Cin, Cout_r = Cout;
+  W /= fg; Cin *= fg; Cout *= fg;
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -1342,7 +1413,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   const int KCc = fit_kc(Cin, BN, max_rows);
   if (!KCc) { set_error("conv_fwd_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
   bf16* wp = nullptr;
-  int rc = pack_weights(w, &wp, Cout, Cin, 0, st);
+  int rc = pack_weights(w, &wp, Cout_r, Cin_r, 0, fg, st);
   if (rc) return rc;
   // B map: [tap][Cout][Cin]
   {
@@ -1365,7 +1436,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
     for (int s = 0; s < 3; ++s) {
       TcGroup& g = p.g[s];
       g.map = 0; g.dh = -1; g.dw = s - 1; g.rows = TC_TH + 2; g.ntaps = 3;
-      for (int r = 0; r < 3; ++r) { g.ro[r] = r; g.widx[r] = r * 3 + s; }
+      for (int r = 0; r < 3; ++r) { g.ro[r] = r; g.widx[r] = r * 3 + s; g.kmask[r] = fold_kmask(fg, Cin_r, s, true); }
     }
   } else {
     // parity sub-grids: element (h2, w2) of map (ph, pw) is x[2*h2+ph][2*w2+pw]
@@ -1390,16 +1461,18 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
       g1.map = 2 + pw; g1.dh = -1; g1.dw = dw; g1.rows = TC_TH + 1; g1.ntaps = 2;
       g1.ro[0] = 0; g1.widx[0] = 0 * 3 + s;
       g1.ro[1] = 1; g1.widx[1] = 2 * 3 + s;
+      g1.kmask[0] = g1.kmask[1] = 0xFFFFFFFFu;
       TcGroup& g0 = p.g[gi++];
       g0.map = pw; g0.dh = 0; g0.dw = dw; g0.rows = TC_TH; g0.ntaps = 1;
       g0.ro[0] = 0; g0.widx[0] = 1 * 3 + s;
+      g0.kmask[0] = 0xFFFFFFFFu;
     }
   }
   p.N = N; p.TSH = Ho; p.TSW = Wo;
   p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
   p.n_ntiles = Cout / BN;
   p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
-  p.OH = Ho; p.OW = Wo; p.OC = Cout; p.os = 1; p.oh0 = 0; p.ow0 = 0;
+  p.OH = Ho; p.OW = Wo; p.OC = Cout; p.OCr = Cout_r; p.os = 1; p.oh0 = 0; p.ow0 = 0;
   p.BN = BN; p.kchunks = Cin / KCc;
   p.out = y;
   p.scale = ep.scale; p.shift = ep.shift; p.act = ep.act; p.dropscale = ep.dropscale; p.stats = ep.stats;
@@ -1411,13 +1484,16 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
 int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W, int Cin, int Cout, int ks, int stride,
                   const BwdEpi& be, cudaStream_t st) {
   if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  const int fg = fold_factor(Cin, Cout, W, stride);
+  const int Cin_r = Cin, Cout_r = Cout;
+  W /= fg; Cin *= fg; Cout *= fg;
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const int BN = pick_bn(Cin);
   const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
   const int KCc = fit_kc(Cout, BN, max_rows);
   if (!KCc) { set_error("conv_dgrad_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
   bf16* wp = nullptr;
-  int rc = pack_weights(w, &wp, Cout, Cin, 1, st);
+  int rc = pack_weights(w, &wp, Cout_r, Cin_r, 1, fg, st);
   if (rc) return rc;
   const bf16* gb = (const bf16*)dz;
   const int nclass = stride == 1 ? 1 : 4;
@@ -1442,7 +1518,7 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
       for (int s = 0; s < 3; ++s) {
         TcGroup& g = p.g[s];
         g.map = 0; g.dh = -1; g.dw = 1 - s; g.rows = rows; g.ntaps = 3;
-        for (int r = 0; r < 3; ++r) { g.ro[r] = 2 - r; g.widx[r] = r * 3 + s; }
+        for (int r = 0; r < 3; ++r) { g.ro[r] = 2 - r; g.widx[r] = r * 3 + s; g.kmask[r] = fold_kmask(fg, Cout_r, s, false); }
       }
       p.TSH = H; p.TSW = W; p.os = 1; p.oh0 = 0; p.ow0 = 0;
     } else {
@@ -1459,6 +1535,7 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
         g.map = 0; g.dh = 0; g.dw = dw; g.rows = rows;
         if (qh) { g.ntaps = 2; g.ro[0] = 1; g.widx[0] = 0 * 3 + s; g.ro[1] = 0; g.widx[1] = 2 * 3 + s; }
         else { g.ntaps = 1; g.ro[0] = 0; g.widx[0] = 1 * 3 + s; }
+        g.kmask[0] = g.kmask[1] = 0xFFFFFFFFu;
       }
       p.ngroups = gi;
     }
@@ -1476,7 +1553,7 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
     p.tiles_h = cdiv(p.TSH, TC_TH); p.tiles_w = cdiv(p.TSW, TC_TW);
     p.n_ntiles = Cin / BN;
     p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
-    p.OH = H; p.OW = W; p.OC = Cin;
+    p.OH = H; p.OW = W; p.OC = Cin; p.OCr = Cin_r;
     p.BN = BN; p.kchunks = Cout / KCc;
     p.out = dx;
     p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
