@@ -341,7 +341,9 @@ def kernel_breakdown(trainer, dev_imgs, dev_labs, args, L):
 
 
 def roofline_from_breakdown(breakdown, args, B):
-    """roofline of the dominant kernel (largest share of the step)."""
+    """roofline of the dominant kernel (largest share of the step).  Convolutions are judged against the roof that
+    binds them: arithmetic intensity (FLOP per algorithmic byte) above the machine balance -> tensor, else HBM
+    (base_model layers 2, 3 are HBM-bound, 4-7 tensor-bound)."""
     peaks = load_peaks()
     if not breakdown:
         return None
@@ -352,11 +354,22 @@ def roofline_from_breakdown(breakdown, args, B):
         pad = k // 2
         Ho, Wo = (Hh + 2 * pad - k) // s + 1, (Ww + 2 * pad - k) // s + 1
         flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
-        return {"kernel": top, "bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12,
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
-                "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
-                "ms_per_launch": ms}
+        # algorithmic bytes: every activation tensor the op must touch once (bf16); dgrad also reads the saved
+        # activation of the previous layer for the fused activation backward
+        nbytes = 2.0 * (N * Hh * Ww * Cin + N * Ho * Wo * Cout)
+        if top.startswith("yg_conv_dgrad["):
+            nbytes += 2.0 * N * Hh * Ww * Cin
+        balance = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        if flops / nbytes >= balance:
+            ach = flops / (ms * 1e-3) / 1e12
+            return {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
+                    "ms_per_launch": ms, "algorithmic_flops": flops}
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
+                "ms_per_launch": ms, "algorithmic_bytes": nbytes, "flop_per_byte": flops / nbytes}
     return {"kernel": top, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
             "traffic": None, "ms_per_launch": ms, "peak_source": peaks["source"]}
 

@@ -210,6 +210,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   volatile int* prod_iter = reinterpret_cast<volatile int*>(tmem_slot + 1);  // producer's tile-loop counter
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
   float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
+  float* s_ds = s_const + 4 * 512;                          // [512] Dropout2d scales of the image being processed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
@@ -441,6 +442,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int hl = m / TC_TW, wl = m % TC_TW;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int ds_n = -1;
     bf16* out = reinterpret_cast<bf16*>(p.out);
     const float* s_k0 = s_const;             // fwd: scale      bwd: bn_scale
     const float* s_k1 = s_const + 512;       // fwd: shift      bwd: bn_shift
@@ -457,6 +459,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int oh = a * p.os + p.oh0, ow = b * p.os + p.ow0;
       const bool valid = a < p.TSH && b < p.TSW && oh < p.OH && ow < p.OW;
       const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
+      if (p.dropscale && n != ds_n) {
+        // Dropout2d scales are per (image, channel): stage the row of this image in smem once per image
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = threadIdx.x - (PW + 1) * 32; i < p.OC; i += 256) s_ds[i] = p.dropscale[(long long)n * p.OCr + i % p.OCr];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        ds_n = n;
+      }
       if (MODE == 1 && p.saved && half == 0) {
         // pull the saved-activation rows of the tile after next into L2 now: by the time its epilogue runs,
         // the 32-byte operand loads hit L2 instead of paying an HBM round trip per 16-column chunk
@@ -488,10 +497,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // global operands of this chunk are fetched while the TMEM load is in flight
         float ds[16];
         if (p.dropscale) {
-          const float4* dp = reinterpret_cast<const float4*>(p.dropscale + (long long)n * p.OCr + (c0 % p.OCr));
+          const float4* dp = reinterpret_cast<const float4*>(s_ds + c0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 v4 = __ldg(dp + i);
+            const float4 v4 = dp[i];
             ds[4 * i] = v4.x; ds[4 * i + 1] = v4.y; ds[4 * i + 2] = v4.z; ds[4 * i + 3] = v4.w;
           }
         } else {
@@ -1321,7 +1330,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   p.error_flag = g_error_flag;
   p.pf_ahead = (g_tc_options & 4) ? 2 : 0;
   const size_t smem = (size_t)nst * stage_bytes + p.resb_bytes + 1024 /*align*/ + 512 /*barriers*/ +
-                      (2 * 256 + 4 * 512 + 16) * sizeof(float) + 64;
+                      (2 * 256 + 5 * 512 + 16) * sizeof(float) + 64;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
