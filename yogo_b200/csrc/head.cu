@@ -254,78 +254,64 @@ __global__ void __launch_bounds__(256) head_bwd_warp_kernel(
     }
     __syncwarp();
     const int npx = (int)min((long long)32, npix - p0);
-    constexpr int UNR = 4;  // pixels in flight per lane: the loads of a batch are issued before any of its math
-    for (int pb = 0; pb < npx; pb += UNR) {
-      float xv[UNR][CPL], sv[UNR][CPL];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const long long q = p0 + pb + u;
+    for (int pp = 0; pp < npx; ++pp) {
+      const long long q = p0 + pp;
+      const int n = (int)(q / SS);
+      float xv[CPL], g[CPL], sv[CPL];
+      {
         __align__(16) T tmp[CPL];
-        __align__(16) T tmp2[CPL];
+        if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(tmp) = *reinterpret_cast<const uint2*>(x + q * Cin + c0);
+        else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(x + q * Cin + c0);
+        else {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) { tmp[k] = from_f<T>(0.f); tmp2[k] = from_f<T>(0.f); }
-        if (pb + u < npx) {
-          if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(tmp) = *reinterpret_cast<const uint2*>(x + q * Cin + c0);
-          else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(x + q * Cin + c0);
-          else {
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) tmp[k] = x[q * Cin + c0 + k];
-          }
-          if (be.saved) {
-            const T* sp = (const T*)be.saved + q * Cin + c0;
-            if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(tmp2) = *reinterpret_cast<const uint2*>(sp);
-            else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(tmp2) = *reinterpret_cast<const uint4*>(sp);
-            else {
-#pragma unroll
-              for (int k = 0; k < CPL; ++k) tmp2[k] = sp[k];
-            }
-          }
+          for (int k = 0; k < CPL; ++k) tmp[k] = x[q * Cin + c0 + k];
         }
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) { xv[u][k] = to_f<T>(tmp[k]); sv[u][k] = to_f<T>(tmp2[k]); }
+        for (int k = 0; k < CPL; ++k) { xv[k] = to_f<T>(tmp[k]); g[k] = 0.f; sv[k] = 0.f; }
+        if (be.saved) {
+          const T* sp = (const T*)be.saved + q * Cin + c0;
+          if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(tmp) = *reinterpret_cast<const uint2*>(sp);
+          else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(sp);
+          else {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) tmp[k] = sp[k];
+          }
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) sv[k] = to_f<T>(tmp[k]);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int pp = pb + u;
-        if (pp >= npx) break;
-        const long long q = p0 + pp;
-        const int n = (int)(q / SS);
-        float g[CPL];
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) g[k] = 0.f;
-#pragma unroll
-        for (int d = 0; d < DM; ++d) {
-          if (d < D) {
-            const float dtd = dts[pp * DM + d];
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-              g[k] += dtd * wsm[d * Cin + c0 + k];
-              acc[d][k] += dtd * xv[u][k];
-            }
-          }
-        }
-        if (dx) {
-          __align__(16) T ob[CPL];
+      for (int d = 0; d < DM; ++d) {
+        if (d < D) {
+          const float dtd = dts[pp * DM + d];
 #pragma unroll
           for (int k = 0; k < CPL; ++k) {
-            float gg = g[k];
-            if (be.dropscale) gg *= be.dropscale[(long long)n * Cin + c0 + k];
-            float xhat = 0.f;
-            if (be.saved) {
-              float pre = sv[u][k];
-              if (be.bn_scale) { pre = sv[u][k] * k_scale[k] + k_shift[k]; xhat = (sv[u][k] - k_mean[k]) * k_istd[k]; }
-              gg *= act_grad(pre, be.act);
-            }
-            if (be.bn_sums) gg = to_f<T>(from_f<T>(gg));
-            bsum[k] += gg; bsx[k] += gg * xhat;
-            ob[k] = from_f<T>(gg);
+            g[k] += dtd * wsm[d * Cin + c0 + k];
+            acc[d][k] += dtd * xv[k];
           }
-          if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(dx + q * Cin + c0) = *reinterpret_cast<uint2*>(ob);
-          else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(dx + q * Cin + c0) = *reinterpret_cast<uint4*>(ob);
-          else {
+        }
+      }
+      if (dx) {
+        __align__(16) T ob[CPL];
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) dx[q * Cin + c0 + k] = ob[k];
+        for (int k = 0; k < CPL; ++k) {
+          float gg = g[k];
+          if (be.dropscale) gg *= be.dropscale[(long long)n * Cin + c0 + k];
+          float xhat = 0.f;
+          if (be.saved) {
+            float pre = sv[k];
+            if (be.bn_scale) { pre = sv[k] * k_scale[k] + k_shift[k]; xhat = (sv[k] - k_mean[k]) * k_istd[k]; }
+            gg *= act_grad(pre, be.act);
           }
+          if (be.bn_sums) gg = to_f<T>(from_f<T>(gg));
+          bsum[k] += gg; bsx[k] += gg * xhat;
+          ob[k] = from_f<T>(gg);
+        }
+        if (CPL * sizeof(T) == 8) *reinterpret_cast<uint2*>(dx + q * Cin + c0) = *reinterpret_cast<uint2*>(ob);
+        else if (CPL * sizeof(T) == 16) *reinterpret_cast<uint4*>(dx + q * Cin + c0) = *reinterpret_cast<uint4*>(ob);
+        else {
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) dx[q * Cin + c0 + k] = ob[k];
         }
       }
     }
@@ -369,7 +355,7 @@ __global__ void head_reduce_kernel(const float* __restrict__ partial, float* __r
   else if (dbias) dbias[i - nw] = s;
 }
 
-constexpr int HD_BWD_BLOCKS = 592;
+constexpr int HD_BWD_BLOCKS = 296;
 
 }  // namespace yg
 using namespace yg;
