@@ -489,9 +489,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      const int nchunks = BN / 16;
-      // one 16-column chunk of the accumulator: TMEM -> registers -> fused epilogue -> global
-      auto chunk = [&](const int j, const uint4 svA, const uint4 svB) {
+      for (int j = half; j < BN / 16; j += 2) {
         uint32_t r[16];
         tmem_ld16(taddr0 + (uint32_t)(j * 16), r);
         const int cl = j * 16;          // channel inside the N tile
@@ -511,8 +509,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         __align__(16) bf16 sv[16];
         if (MODE == 1) {
-          reinterpret_cast<uint4*>(sv)[0] = svA;
-          reinterpret_cast<uint4*>(sv)[1] = svB;
+          if (p.saved && valid) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
+            reinterpret_cast<uint4*>(sv)[0] = __ldg(src);
+            reinterpret_cast<uint4*>(sv)[1] = __ldg(src + 1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
+          }
         }
         tmem_ld_wait();
         __align__(16) bf16 ob[16];
@@ -673,34 +677,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               atomicAdd(&s_stat[cl + lane], t1);
               atomicAdd(&s_stat[256 + cl + lane], t2);
             }
-          }
-        }
-      };
-      if (MODE == 0) {
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-        for (int j = half; j < nchunks; j += 2) chunk(j, z4, z4);
-      } else {
-        // dgrad: the saved-activation operands of up to 4 chunks are fetched together, before any of them is
-        // consumed, so the epilogue pays one memory round trip per batch instead of one per chunk
-        constexpr int PFC = 4;
-        for (int jb = half; jb < nchunks; jb += 2 * PFC) {
-          uint4 sva[PFC], svb[PFC];
-#pragma unroll
-          for (int u = 0; u < PFC; ++u) {
-            const int j = jb + 2 * u;
-            sva[u] = make_uint4(0, 0, 0, 0);
-            svb[u] = make_uint4(0, 0, 0, 0);
-            if (j < nchunks && p.saved && valid) {
-              const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC +
-                                                                nt * BN + j * 16);
-              sva[u] = __ldg(src);
-              svb[u] = __ldg(src + 1);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < PFC; ++u) {
-            const int j = jb + 2 * u;
-            if (j < nchunks) chunk(j, sva[u], svb[u]);
           }
         }
       }
