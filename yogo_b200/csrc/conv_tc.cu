@@ -48,14 +48,21 @@ struct TcSrc {            // A-operand source as seen by the cp.async producer (
   long long sw, sh, sn;
 };
 
+struct TcClass {   // one output-parity class of a stride-2 dgrad (or the whole problem when ncls == 1)
+  int g0, ng, gpi;          // its groups: p.g[g0 .. g0+ng), merged gpi at a time into one pipeline item
+  int TSH, TSW, oh0, ow0;   // tile-space extent and output offset
+};
+
 struct TcParams {
-  int N, TSH, TSW, tiles_h, tiles_w, n_ntiles, total_tiles;
+  int N, tiles_h, tiles_w, n_ntiles, total_tiles;
+  int ncls;
+  TcClass cls[4];
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
-  int OH, OW, OC, os, oh0, ow0;   // output tensor (NHWC) and tile-space -> output mapping
+  int OH, OW, OC, os;             // output tensor (NHWC) and tile-space -> output stride
   int OCr;                        // real channel count (OC / W-fold factor): per-channel arrays are indexed modulo OCr
-  int BN, kchunks, ngroups, nstages, nacc;
-  int gpi, a_box_bytes;   // groups merged into one pipeline item (small-K layers), bytes reserved per A box
+  int BN, kchunks, nstages, nacc;
+  int a_box_bytes, b_stage_bytes;   // bytes reserved per A box / per stage for streamed weight tiles
   int pf_ahead;           // L2 prefetch distance in tiles (0 = off)
   int a_stage_bytes, b_tap_bytes, tmem_cols;
   TcGroup g[TC_MAX_GROUPS];
@@ -198,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases: align by hand, do not trust the attribute
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.gpi * TC_MAX_TAPS * p.b_tap_bytes);
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
   unsigned char* resb = smem + (size_t)p.nstages * stage_bytes;
   unsigned char* tail = resb + p.resb_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -253,8 +260,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int ipk = p.ngroups / p.gpi;          // items per K chunk
-  const int items = p.kchunks * ipk;
 
   if (warp < PW) {
     if (PROD == 0) {
@@ -266,20 +271,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
           *prod_iter = iter++;
           int t = tile;
+          const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
           const int nt = t % p.n_ntiles; t /= p.n_ntiles;
           const int tw = t % p.tiles_w; t /= p.tiles_w;
           const int th = t % p.tiles_h;
           const int n = t / p.tiles_h;
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            for (int g0 = 0; g0 < p.ngroups; g0 += p.gpi) {
+            for (int g0 = C.g0; g0 < C.g0 + C.ng; g0 += C.gpi) {
               mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
               unsigned char* sa = smem + (size_t)stage * stage_bytes;
               unsigned char* sb = sa + p.a_stage_bytes;
               uint32_t bytes = 0;
-              for (int gi = g0; gi < g0 + p.gpi; ++gi)
+              for (int gi = g0; gi < g0 + C.gpi; ++gi)
                 bytes += (uint32_t)(p.g[gi].rows * TC_TW * (int)ROW_BYTES + (p.b_resident ? 0 : p.g[gi].ntaps * p.b_tap_bytes));
               mbar_expect_tx(&full_bar[stage], bytes);
-              for (int gi = g0; gi < g0 + p.gpi; ++gi) {
+              for (int gi = g0; gi < g0 + C.gpi; ++gi) {
                 const TcGroup& g = p.g[gi];
                 tma_load_4d(sa + (size_t)(gi - g0) * p.a_box_bytes, &maps.a[g.map], &full_bar[stage], kc * KC,
                             tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
@@ -301,14 +307,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       int issued = 0;
       int hist[LAG] = {0, 0};        // stages of the last LAG committed groups (oldest first)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int t = tile / p.n_ntiles;
+        int t = tile;
+        const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
+        t /= p.n_ntiles;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h;
         const int n = t / p.tiles_h;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int g0 = 0; g0 < p.ngroups; g0 += p.gpi) {
+          for (int g0 = C.g0; g0 < C.g0 + C.ng; g0 += C.gpi) {
             mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
-            for (int gi = g0; gi < g0 + p.gpi; ++gi) {
+            for (int gi = g0; gi < g0 + C.gpi; ++gi) {
               const TcGroup& g = p.g[gi];
               const TcSrc& src = p.src[g.map];
               const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes) + (uint32_t)((gi - g0) * p.a_box_bytes);
@@ -364,16 +372,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, p.error_flag, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const TcClass& C = p.cls[tile % p.ncls];
+      const int items = p.kchunks * (C.ng / C.gpi);
       int item = 0;
       uint32_t started = 0;   // 0 until the first MMA of this tile has been issued (overwrite vs accumulate)
       for (int kc = 0; kc < p.kchunks; ++kc) {
-        for (int g0 = 0; g0 < p.ngroups; g0 += p.gpi, ++item) {
+        for (int g0 = C.g0; g0 < C.g0 + C.ng; g0 += C.gpi, ++item) {
           mbar_wait(&full_bar[stage], phase, p.error_flag, 3);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa0 = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa0 + (uint32_t)p.a_stage_bytes;
-            for (int gi = g0; gi < g0 + p.gpi; ++gi) {
+            for (int gi = g0; gi < g0 + C.gpi; ++gi) {
               const TcGroup& g = p.g[gi];
               const uint32_t sa = sa0 + (uint32_t)((gi - g0) * p.a_box_bytes);
               for (int tp = 0; tp < g.ntaps; ++tp) {
@@ -409,13 +419,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (PROD == 0 && p.pf_ahead > 0) {
       int iter = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
-        if (tile % p.n_ntiles != 0) continue;   // the A operand is shared by the N tiles of a pixel tile
         while (iter > *prod_iter + p.pf_ahead) __nanosleep(256);
-        int t = tile / p.n_ntiles;
+        int t = tile;
+        const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
+        t /= p.n_ntiles;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h;
         const int n = t / p.tiles_h;
-        for (int gi = 0; gi < p.ngroups; ++gi) {
+        for (int gi = C.g0; gi < C.g0 + C.ng; ++gi) {
           const TcGroup& g = p.g[gi];
           const TcSrc& src = p.src[g.map];
           const int npx = g.rows * TC_TW;
@@ -451,13 +462,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool has_bn = p.bn_scale != nullptr;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t = tile;
+      const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
       const int nt = t % p.n_ntiles; t /= p.n_ntiles;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h;
       const int n = t / p.tiles_h;
       const int a = th * TC_TH + hl, b = tw * TC_TW + wl;
-      const int oh = a * p.os + p.oh0, ow = b * p.os + p.ow0;
-      const bool valid = a < p.TSH && b < p.TSW && oh < p.OH && ow < p.OW;
+      const int oh = a * p.os + C.oh0, ow = b * p.os + C.ow0;
+      const bool valid = a < C.TSH && b < C.TSW && oh < p.OH && ow < p.OW;
       const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
       if (p.dropscale && n != ds_n) {
         // Dropout2d scales are per (image, channel): stage the row of this image in smem once per image
@@ -472,13 +484,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int tile2 = tile + 2 * (int)gridDim.x;
         if (tile2 < p.total_tiles) {
           int t2 = tile2;
+          const TcClass& C2 = p.cls[t2 % p.ncls]; t2 /= p.ncls;
           const int nt2 = t2 % p.n_ntiles; t2 /= p.n_ntiles;
           const int tw2 = t2 % p.tiles_w; t2 /= p.tiles_w;
           const int th2 = t2 % p.tiles_h;
           const int n2 = t2 / p.tiles_h;
           const int a2 = th2 * TC_TH + hl, b2 = tw2 * TC_TW + wl;
-          const int oh2 = a2 * p.os + p.oh0, ow2 = b2 * p.os + p.ow0;
-          if (a2 < p.TSH && b2 < p.TSW && oh2 < p.OH && ow2 < p.OW) {
+          const int oh2 = a2 * p.os + C2.oh0, ow2 = b2 * p.os + C2.ow0;
+          if (a2 < C2.TSH && b2 < C2.TSW && oh2 < p.OH && ow2 < p.OW) {
             const bf16* row = reinterpret_cast<const bf16*>(p.saved) +
                               (((long long)n2 * p.OH + oh2) * p.OW + ow2) * p.OC + nt2 * BN;
             for (int c = 0; c < BN; c += 64)
@@ -1297,9 +1310,14 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   p.a_box_bytes = (max_rows * TC_TW * KCc * 2 + 1023) & ~1023;
   // small-K layers: merge all tap groups of a K chunk into one pipeline item, so that the fixed per-item
   // cost (mbarrier round trips, MMA issue, commit) is paid once per tile instead of 3-6 times
-  p.gpi = (p.ngroups * p.a_box_bytes <= 32 * 1024) ? p.ngroups : 1;
-  p.a_stage_bytes = p.gpi * p.a_box_bytes;
+  int max_gpi = 1;
+  for (int c = 0; c < p.ncls; ++c) {
+    p.cls[c].gpi = (p.cls[c].ng * p.a_box_bytes <= 32 * 1024) ? p.cls[c].ng : 1;
+    if (p.cls[c].gpi > max_gpi) max_gpi = p.cls[c].gpi;
+  }
+  p.a_stage_bytes = max_gpi * p.a_box_bytes;
   p.b_tap_bytes = p.BN * KCc * 2;
+  p.b_stage_bytes = max_gpi * TC_MAX_TAPS * p.b_tap_bytes;
   // resident weights: all 9 x kchunks tiles stay in smem if at least 3 A stages still fit
   const int resb = (9 * p.kchunks * p.b_tap_bytes + 1023) & ~1023;
   p.b_resident = 0;
@@ -1309,7 +1327,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
     p.resb_bytes = resb;
   }
   const int prod = (p.b_resident && KCc <= 32 && (g_tc_options & 2)) ? 1 : 0;
-  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.gpi * TC_MAX_TAPS * p.b_tap_bytes);
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
   int nst = (TC_SMEM_BUDGET - p.resb_bytes) / stage_bytes;
   if (nst > 16) nst = 16;
   if (nst < 2) {
@@ -1433,6 +1451,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
     if (rc) return rc;
   }
   const bf16* xb = (const bf16*)x;
+  int ngroups = 0;
   if (stride == 1) {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
@@ -1441,7 +1460,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
     if (rc) return rc;
     for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
     for (int i = 0; i < 4; ++i) p.src[i] = TcSrc{xb, W, H, (long long)Cin, (long long)W * Cin, (long long)H * W * Cin};
-    p.ngroups = 3;
+    ngroups = 3;
     for (int s = 0; s < 3; ++s) {
       TcGroup& g = p.g[s];
       g.map = 0; g.dh = -1; g.dw = s - 1; g.rows = TC_TH + 2; g.ntaps = 3;
@@ -1462,7 +1481,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
                                    (long long)H * W * Cin};
       }
     // input row 2*ho + r - 1: r=0 -> (ph=1, h2=ho-1), r=1 -> (ph=0, h2=ho), r=2 -> (ph=1, h2=ho)
-    p.ngroups = 6;
+    ngroups = 6;
     int gi = 0;
     for (int s = 0; s < 3; ++s) {
       const int pw = (s == 1) ? 0 : 1, dw = (s == 0) ? -1 : 0;
@@ -1477,11 +1496,13 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
       g0.kmask[0] = 0xFFFFFFFFu;
     }
   }
-  p.N = N; p.TSH = Ho; p.TSW = Wo;
+  p.N = N;
+  p.ncls = 1;
+  p.cls[0] = TcClass{0, ngroups, 1, Ho, Wo, 0, 0};
   p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
   p.n_ntiles = Cout / BN;
   p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
-  p.OH = Ho; p.OW = Wo; p.OC = Cout; p.OCr = Cout_r; p.os = 1; p.oh0 = 0; p.ow0 = 0;
+  p.OH = Ho; p.OW = Wo; p.OC = Cout; p.OCr = Cout_r; p.os = 1;
   p.BN = BN; p.kchunks = Cin / KCc;
   p.out = y;
   p.scale = ep.scale; p.shift = ep.shift; p.act = ep.act; p.dropscale = ep.dropscale; p.stats = ep.stats;
@@ -1505,72 +1526,76 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   int rc = pack_weights(w, &wp, Cout_r, Cin_r, 1, fg, st);
   if (rc) return rc;
   const bf16* gb = (const bf16*)dz;
-  const int nclass = stride == 1 ? 1 : 4;
-  for (int cls = 0; cls < nclass; ++cls) {
-    TcMaps maps;
-    memset(&maps, 0, sizeof(maps));
-    TcParams p;
-    memset(&p, 0, sizeof(p));
-    {
-      uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, 9};
-      uint64_t str[2] = {(uint64_t)Cout * 2, (uint64_t)Cin * Cout * 2};
-      uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
-      rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
-      if (rc) break;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, 9};
+    uint64_t str[2] = {(uint64_t)Cout * 2, (uint64_t)Cin * Cout * 2};
+    uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
+    rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
+    if (rc) return rc;
+  }
+  // A maps over dz: map 0 has the tallest box of the problem, map 1 (stride 2 only) the 8-row box
+  for (int mi = 0; mi < 2; ++mi) {
+    const int rows = stride == 1 ? TC_TH + 2 : (mi == 0 ? TC_TH + 1 : TC_TH);
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+    uint32_t box[4] = {(uint32_t)KCc, TC_TW, (uint32_t)rows, 1};
+    rc = make_map(&maps.a[mi], gb, 4, dims, str, box, KCc);
+    if (rc) return rc;
+  }
+  maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  for (int i = 0; i < 4; ++i)
+    p.src[i] = TcSrc{gb, Wo, Ho, (long long)Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout};
+  if (stride == 1) {
+    // dx(h,w) = sum_{r,s} dz(h+1-r, w+1-s) W[r][s]^T
+    for (int s = 0; s < 3; ++s) {
+      TcGroup& g = p.g[s];
+      g.map = 0; g.dh = -1; g.dw = 1 - s; g.rows = TC_TH + 2; g.ntaps = 3;
+      for (int r = 0; r < 3; ++r) { g.ro[r] = 2 - r; g.widx[r] = r * 3 + s; g.kmask[r] = fold_kmask(fg, Cout_r, s, false); }
     }
-    const int qh = cls >> 1, qw = cls & 1;
-    int rows;
-    if (stride == 1) {
-      rows = TC_TH + 2;
-      // dx(h,w) = sum_{r,s} dz(h+1-r, w+1-s) W[r][s]^T
-      p.ngroups = 3;
-      for (int s = 0; s < 3; ++s) {
-        TcGroup& g = p.g[s];
-        g.map = 0; g.dh = -1; g.dw = 1 - s; g.rows = rows; g.ntaps = 3;
-        for (int r = 0; r < 3; ++r) { g.ro[r] = 2 - r; g.widx[r] = r * 3 + s; g.kmask[r] = fold_kmask(fg, Cout_r, s, false); }
-      }
-      p.TSH = H; p.TSW = W; p.os = 1; p.oh0 = 0; p.ow0 = 0;
-    } else {
-      // output parity class (qh, qw): h = 2a+qh.  qh=0: r=1 (dz row a).  qh=1: r=0 (row a+1), r=2 (row a).
-      rows = TC_TH + qh;
-      p.TSH = (H - qh + 1) / 2; p.TSW = (W - qw + 1) / 2; p.os = 2; p.oh0 = qh; p.ow0 = qw;
-      if (p.TSH < 1 || p.TSW < 1) continue;
-      int gi = 0;
+    p.ncls = 1;
+    p.cls[0] = TcClass{0, 3, 1, H, W, 0, 0};
+    p.os = 1;
+    p.tiles_h = cdiv(H, TC_TH); p.tiles_w = cdiv(W, TC_TW);
+  } else {
+    // Four output-parity classes (qh, qw): h = 2a+qh, w = 2b+qw.  qh=0: r=1 (dz row a).  qh=1: r=0 (row a+1), r=2
+    // (row a); same for columns.  All four run in ONE launch with the class as the fastest tile index, so the dz
+    // tile and the saved-activation lines shared by sibling classes are fetched from HBM once and hit L2 after.
+    int gi = 0, nc = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int qh = cls >> 1, qw = cls & 1;
+      const int TSH = (H - qh + 1) / 2, TSW = (W - qw + 1) / 2;
+      TcClass& C = p.cls[nc++];
+      C.g0 = gi; C.TSH = TSH; C.TSW = TSW; C.oh0 = qh; C.ow0 = qw; C.gpi = 1;
       const int ns = qw ? 2 : 1;
       for (int si = 0; si < ns; ++si) {
         const int s = qw ? (si == 0 ? 0 : 2) : 1;
         const int dw = qw ? (si == 0 ? 1 : 0) : 0;
         TcGroup& g = p.g[gi++];
-        g.map = 0; g.dh = 0; g.dw = dw; g.rows = rows;
+        g.map = qh ? 0 : 1; g.dh = 0; g.dw = dw; g.rows = TC_TH + qh;
         if (qh) { g.ntaps = 2; g.ro[0] = 1; g.widx[0] = 0 * 3 + s; g.ro[1] = 0; g.widx[1] = 2 * 3 + s; }
         else { g.ntaps = 1; g.ro[0] = 0; g.widx[0] = 1 * 3 + s; }
         g.kmask[0] = g.kmask[1] = 0xFFFFFFFFu;
       }
-      p.ngroups = gi;
+      C.ng = gi - C.g0;
     }
-    {
-      uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
-      uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
-      uint32_t box[4] = {(uint32_t)KCc, TC_TW, (uint32_t)rows, 1};
-      rc = make_map(&maps.a[0], gb, 4, dims, str, box, KCc);
-      if (rc) break;
-      for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
-      for (int i = 0; i < 4; ++i)
-        p.src[i] = TcSrc{gb, Wo, Ho, (long long)Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout};
-    }
-    p.N = N;
-    p.tiles_h = cdiv(p.TSH, TC_TH); p.tiles_w = cdiv(p.TSW, TC_TW);
-    p.n_ntiles = Cin / BN;
-    p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
-    p.OH = H; p.OW = W; p.OC = Cin; p.OCr = Cin_r;
-    p.BN = BN; p.kchunks = Cout / KCc;
-    p.out = dx;
-    p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
-    p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
-    rc = launch_engine(maps, p, KCc, 1, max_rows, st);
-    if (rc) break;
+    p.ncls = 4;
+    p.os = 2;
+    // tile space of the largest class (qh = qw = 0); smaller classes mask their last row / column
+    p.tiles_h = cdiv((H + 1) / 2, TC_TH); p.tiles_w = cdiv((W + 1) / 2, TC_TW);
   }
-  return rc;
+  p.N = N;
+  p.n_ntiles = Cin / BN;
+  p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles * p.ncls;
+  p.OH = H; p.OW = W; p.OC = Cin; p.OCr = Cin_r;
+  p.BN = BN; p.kchunks = Cout / KCc;
+  p.out = dx;
+  p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
+  p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
+  return launch_engine(maps, p, KCc, 1, max_rows, st);
 }
 
 }  // namespace yg
