@@ -391,14 +391,22 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 const uint32_t b0 = p.b_resident
                                         ? smem_u32(resb) + (uint32_t)((g.widx[tp] * p.kchunks + kc) * p.b_tap_bytes)
                                         : sb + (uint32_t)(((gi - g0) * TC_MAX_TAPS + tp) * p.b_tap_bytes);
-                const unsigned km = g.kmask[tp] >> (kc * KSTEPS);
+                const unsigned km = (g.kmask[tp] >> (kc * KSTEPS)) & ((1u << KSTEPS) - 1u);
+                // descriptors advance by 32 bytes (2 units of 16 B) per K step: one add instead of a rebuild
+                const uint64_t ad0 = umma_desc(a0, SBO, LAYOUT), bd0 = umma_desc(b0, SBO, LAYOUT);
+                if (km == (1u << KSTEPS) - 1u) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                  if (!((km >> k) & 1u)) continue;   // structurally zero weights (W-folded convolution)
-                  const uint64_t ad = umma_desc(a0 + k * 32, SBO, LAYOUT);
-                  const uint64_t bd = umma_desc(b0 + k * 32, SBO, LAYOUT);
-                  umma_bf16(d_tmem, ad, bd, idesc, started);
-                  started = 1u;
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    umma_bf16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, started);
+                    started = 1u;
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    if (!((km >> k) & 1u)) continue;   // structurally zero weights (W-folded convolution)
+                    umma_bf16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, started);
+                    started = 1u;
+                  }
                 }
               }
             }
