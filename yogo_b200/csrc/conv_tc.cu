@@ -63,6 +63,7 @@ struct TcParams {
   int OCr;                        // real channel count (OC / W-fold factor): per-channel arrays are indexed modulo OCr
   int BN, kchunks, nstages, nacc;
   int a_box_bytes, b_stage_bytes;   // bytes reserved per A box / per stage for streamed weight tiles
+  int ntaps_total;                  // weight slices in the packed weight tensor (9 for 3x3, 1 for 1x1)
   int pf_ahead;           // L2 prefetch distance in tiles (0 = off)
   int a_stage_bytes, b_tap_bytes, tmem_cols;
   TcGroup g[TC_MAX_GROUPS];
@@ -233,8 +234,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (p.b_resident) {
       // every (tap, K chunk) weight tile is fetched once and stays in shared memory
-      mbar_expect_tx(&resb_bar[0], (uint32_t)(9 * p.kchunks * p.b_tap_bytes));
-      for (int tap = 0; tap < 9; ++tap)
+      mbar_expect_tx(&resb_bar[0], (uint32_t)(p.ntaps_total * p.kchunks * p.b_tap_bytes));
+      for (int tap = 0; tap < p.ntaps_total; ++tap)
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_3d(resb + (size_t)(tap * p.kchunks + kc) * p.b_tap_bytes, &maps.b, &resb_bar[0], kc * KC, 0, tap);
     }
@@ -872,6 +873,7 @@ struct TwParams {
   int Cin, Cout, BNW, n_ntiles, n_mtiles, nunits, nslices;
   int kb, nbblocks, a_block_bytes, b_block_bytes, stage_bytes, nstages, tmem_cols;
   int ngroups;                 // groups per filter column
+  int ncols;                   // filter columns = work-unit columns (3 for 3x3, 1 for 1x1)
   TwGroup g[3][2];
   TcSrc asrc;        // dz as seen by the cp.async producer
   TcSrc bsrc[4];     // x (or its parity sub-grids)
@@ -910,7 +912,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x % p.nunits, slice = blockIdx.x / p.nunits;
-  const int sg = unit % 3, mt = (unit / 3) % p.n_mtiles, nt = unit / (3 * p.n_mtiles);
+  const int sg = unit % p.ncols, mt = (unit / p.ncols) % p.n_mtiles, nt = unit / (p.ncols * p.n_mtiles);
   const int a_blocks = min(MBLOCKS, (p.Cout - mt * 128) / KA);
   const int BNW = p.BNW;
 
@@ -1166,12 +1168,13 @@ bool tc_wgrad_supported(int dtype, int W, int Cin, int Cout, int ks, int stride)
   return kb != 0 && wgrad_bnw(Cin, kb) != 0;
 }
 
-static void wgrad_grid(int Cin, int Cout, int* nunits, int* nslices, int* grid, int* bnw, int* n_mtiles, int* n_ntiles) {
+static void wgrad_grid(int Cin, int Cout, int* nunits, int* nslices, int* grid, int* bnw, int* n_mtiles, int* n_ntiles,
+                       int ncols = 3) {
   const int kb = pick_kc(Cin);
   *bnw = wgrad_bnw(Cin, kb);
   *n_mtiles = (Cout + 127) / 128;
   *n_ntiles = Cin / *bnw;
-  *nunits = 3 * *n_mtiles * *n_ntiles;
+  *nunits = ncols * *n_mtiles * *n_ntiles;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1208,6 +1211,7 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   wgrad_grid(Cin, Cout, &p.nunits, &p.nslices, &grid, &p.BNW, &p.n_mtiles, &p.n_ntiles);
   const int kb = pick_kc(Cin);
   p.kb = kb; p.nbblocks = p.BNW / kb;
+  p.ncols = 3;
   p.N = N; p.Cin = Cin; p.Cout = Cout;
   p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
   p.total_tiles = N * p.tiles_h * p.tiles_w;
@@ -1327,7 +1331,8 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   p.b_tap_bytes = p.BN * KCc * 2;
   p.b_stage_bytes = max_gpi * TC_MAX_TAPS * p.b_tap_bytes;
   // resident weights: all 9 x kchunks tiles stay in smem if at least 3 A stages still fit
-  const int resb = (9 * p.kchunks * p.b_tap_bytes + 1023) & ~1023;
+  if (p.ntaps_total == 0) p.ntaps_total = 9;
+  const int resb = (p.ntaps_total * p.kchunks * p.b_tap_bytes + 1023) & ~1023;
   p.b_resident = 0;
   p.resb_bytes = 0;
   if ((g_tc_options & 1) && p.n_ntiles == 1 && (TC_SMEM_BUDGET - resb) / p.a_stage_bytes >= 3) {
@@ -1605,5 +1610,177 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
   return launch_engine(maps, p, KCc, 1, max_rows, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 prediction head backward on the tensor cores (called from head.cu):
+//   dt   (N,Sy,Sx,32) bf16: gradient wrt the raw head logits, zero padded from D = 5+C to 32 channels
+//   dx = dt . W    -> the dgrad engine with a single tap, K = 32, N = Cin, MODE 1 epilogue (activation / BN
+//                     backward of the last conv block fused, exactly as for the 3x3 layers)
+//   dW = dt^T . x  -> the wgrad engine with one column / one accumulator slot
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_head_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int D, int Cin, int DP) {
+  // packed [1 tap][N = Cin][K = DP]: out[ci][d] = w[d][ci] (zero for d >= D)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cin * DP) return;
+  const int d = i % DP, ci = i / DP;
+  out[i] = __float2bfloat16_rn(d < D ? w[(long long)d * Cin + ci] : 0.f);
+}
+
+__global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int D, int Cin,
+                                         int BNW, int n_mtiles, int nunits, int nslices, float clip) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [d][ci]
+  if (i >= D * Cin) return;
+  const int ci = i % Cin, d = i / Cin;
+  const int nt = ci / BNW;
+  const int unit = 0 + 1 * (0 + n_mtiles * nt);
+  float acc = 0.f;
+  for (int sl = 0; sl < nslices; ++sl) {
+    const size_t cta = (size_t)unit + (size_t)nunits * sl;
+    acc += partial[((cta * 3 + 0) * 128 + d) * BNW + (ci % BNW)];
+  }
+  dw[i] = clampf(acc, clip);
+}
+
+bool head_bwd_tc_supported(int Cin, int D) {
+  if (D > 32 || Cin % 16 != 0 || Cin > 512) return false;
+  const int kb = pick_kc(Cin);
+  return pick_bn(Cin) != 0 && kb != 0 && wgrad_bnw(Cin, kb) != 0;
+}
+
+size_t head_bwd_tc_workspace(int Cin) {
+  int nunits, nslices, grid, bnw, nm, nn;
+  wgrad_grid(Cin, 32, &nunits, &nslices, &grid, &bnw, &nm, &nn, 1);
+  return (size_t)grid * 3 * 128 * bnw * sizeof(float) + 256;
+}
+
+int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* dw, int N, int Sy, int Sx, int Cin, int D,
+                const BwdEpi& be, float clip, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  constexpr int DP = 32;
+  const bf16* dtb = (const bf16*)dt;
+  int rc;
+  // ---------------- dx = dt . W (+ fused backward epilogue of the last block)
+  {
+    bf16* wp = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_pack_mutex);
+      int dev = 0;
+      cudaGetDevice(&dev);
+      PackKey key{w, 2, dev};
+      auto it = g_pack_cache.find(key);
+      const size_t need = (size_t)Cin * DP * sizeof(bf16);
+      if (it == g_pack_cache.end() || it->second.second < need) {
+        void* buf = nullptr;
+        YG_CUDA(cudaMalloc(&buf, need));
+        if (it != g_pack_cache.end()) { cudaFree(it->second.first); it->second = {buf, need}; }
+        else g_pack_cache[key] = {buf, need};
+        wp = (bf16*)buf;
+      } else wp = (bf16*)it->second.first;
+    }
+    pack_head_weights_kernel<<<cdiv((long long)Cin * DP, 256), 256, 0, st>>>(w, wp, D, Cin, DP);
+    YG_LAUNCH_CHECK("pack_head_weights");
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = pick_bn(Cin), KCc = 32;
+    {
+      uint64_t dims[3] = {(uint64_t)DP, (uint64_t)Cin, 1};
+      uint64_t str[2] = {(uint64_t)DP * 2, (uint64_t)Cin * DP * 2};
+      uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
+      rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[4] = {(uint64_t)DP, (uint64_t)Sx, (uint64_t)Sy, (uint64_t)N};
+      uint64_t str[3] = {(uint64_t)DP * 2, (uint64_t)Sx * DP * 2, (uint64_t)Sy * Sx * DP * 2};
+      uint32_t box[4] = {(uint32_t)KCc, TC_TW, TC_TH, 1};
+      rc = make_map(&maps.a[0], dtb, 4, dims, str, box, KCc);
+      if (rc) return rc;
+      for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+      for (int i = 0; i < 4; ++i) p.src[i] = TcSrc{dtb, Sx, Sy, (long long)DP, (long long)Sx * DP, (long long)Sy * Sx * DP};
+    }
+    TcGroup& g = p.g[0];
+    g.map = 0; g.dh = 0; g.dw = 0; g.rows = TC_TH; g.ntaps = 1; g.ro[0] = 0; g.widx[0] = 0;
+    g.kmask[0] = D <= 16 ? 1u : 3u;   // the second 16-wide K step is all padding when D <= 16
+    p.ncls = 1;
+    p.cls[0] = TcClass{0, 1, 1, Sy, Sx, 0, 0};
+    p.os = 1;
+    p.tiles_h = cdiv(Sy, TC_TH); p.tiles_w = cdiv(Sx, TC_TW);
+    p.N = N; p.n_ntiles = Cin / BN;
+    p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
+    p.OH = Sy; p.OW = Sx; p.OC = Cin; p.OCr = Cin;
+    p.BN = BN; p.kchunks = 1; p.ntaps_total = 1;
+    p.out = dx;
+    p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
+    p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
+    rc = launch_engine(maps, p, KCc, 1, TC_TH, st);
+    if (rc) return rc;
+  }
+  // ---------------- dW = dt^T . x
+  {
+    const size_t need = head_bwd_tc_workspace(Cin);
+    if (!ws || ws_bytes < need) { set_error("head_bwd_tc: workspace %zu < %zu", ws_bytes, need); return YG_ERR_WORKSPACE; }
+    TwMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    TwParams p;
+    memset(&p, 0, sizeof(p));
+    int grid;
+    wgrad_grid(Cin, DP, &p.nunits, &p.nslices, &grid, &p.BNW, &p.n_mtiles, &p.n_ntiles, 1);
+    const int kb = pick_kc(Cin), ka = 32;
+    p.kb = kb; p.nbblocks = p.BNW / kb; p.ncols = 1;
+    p.N = N; p.Cin = Cin; p.Cout = DP;
+    p.tiles_h = cdiv(Sy, TC_TH); p.tiles_w = cdiv(Sx, TC_TW);
+    p.total_tiles = N * p.tiles_h * p.tiles_w;
+    p.a_block_bytes = TC_TH * TC_TW * ka * 2;
+    p.b_block_bytes = (TC_TH * TC_TW * kb * 2 + 1023) & ~1023;
+    p.stage_bytes = (128 / ka) * p.a_block_bytes + p.nbblocks * p.b_block_bytes;
+    int nst = TC_SMEM_BUDGET / p.stage_bytes;
+    if (nst > 6) nst = 6;
+    if (nst < 2) { set_error("head_bwd_tc: stage does not fit"); return YG_ERR_INVALID; }
+    p.nstages = nst;
+    int cols = 32;
+    while (cols < 3 * p.BNW) cols <<= 1;
+    p.tmem_cols = cols;
+    {
+      uint64_t dims[4] = {(uint64_t)DP, (uint64_t)Sx, (uint64_t)Sy, (uint64_t)N};
+      uint64_t str[3] = {(uint64_t)DP * 2, (uint64_t)Sx * DP * 2, (uint64_t)Sy * Sx * DP * 2};
+      uint32_t box[4] = {(uint32_t)ka, TC_TW, TC_TH, 1};
+      rc = make_map(&maps.a, dtb, 4, dims, str, box, ka);
+      if (rc) return rc;
+      p.asrc = TcSrc{dtb, Sx, Sy, (long long)DP, (long long)Sx * DP, (long long)Sy * Sx * DP};
+    }
+    {
+      const bf16* xb = (const bf16*)x;
+      uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Sx, (uint64_t)Sy, (uint64_t)N};
+      uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Sx * Cin * 2, (uint64_t)Sy * Sx * Cin * 2};
+      uint32_t box[4] = {(uint32_t)kb, TC_TW, TC_TH, 1};
+      rc = make_map(&maps.b[0], xb, 4, dims, str, box, kb);
+      if (rc) return rc;
+      for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+      for (int i = 0; i < 4; ++i) p.bsrc[i] = TcSrc{xb, Sx, Sy, (long long)Cin, (long long)Sx * Cin, (long long)Sy * Sx * Cin};
+    }
+    p.ngroups = 1;
+    TwGroup& g = p.g[0][0];
+    g.map = 0; g.dh = 0; g.dw = 0; g.rows = TC_TH; g.ntaps = 1; g.ro[0] = 0; g.slot[0] = 0;
+    p.partial = (float*)ws;
+    p.error_flag = g_error_flag;
+    const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 512;
+#define HW_LAUNCH(KBV)                                                                                                 \
+  do {                                                                                                                 \
+    YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    wgrad_tc_kernel<KBV, 32, 0><<<grid, 192, smem, st>>>(maps, p);                                                     \
+  } while (0)
+    if (kb == 64) HW_LAUNCH(64); else if (kb == 32) HW_LAUNCH(32); else HW_LAUNCH(16);
+#undef HW_LAUNCH
+    YG_LAUNCH_CHECK("wgrad_tc_kernel(head)");
+    head_wgrad_reduce_kernel<<<cdiv((long long)D * Cin, 256), 256, 0, st>>>((const float*)ws, dw, D, Cin, p.BNW,
+                                                                            p.n_mtiles, p.nunits, p.nslices, clip);
+    YG_LAUNCH_CHECK("head_wgrad_reduce");
+  }
+  return YG_OK;
+}
+
+
 
 }  // namespace yg

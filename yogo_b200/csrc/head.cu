@@ -356,6 +356,65 @@ __global__ void head_reduce_kernel(const float* __restrict__ partial, float* __r
 }
 
 constexpr int HD_BWD_BLOCKS = 296;
+constexpr int HD_DP = 32;          // channels of the padded bf16 logit-gradient tensor fed to the tensor cores
+constexpr int HD_DT_BLOCKS = 592;
+
+// conv_tc.cu
+bool head_bwd_tc_supported(int Cin, int D);
+size_t head_bwd_tc_workspace(int Cin);
+int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* dw, int N, int Sy, int Sx, int Cin, int D,
+                const BwdEpi& be, float clip, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// dt[p][0..32) (bf16, zero padded) = d(loss)/d(raw logits) from dpred and the raw logits; per-block bias partials
+__global__ void __launch_bounds__(256) head_dt_kernel(const float* __restrict__ dpred, const float* __restrict__ t_raw,
+                                                      bf16* __restrict__ dt, float* __restrict__ db_partial,
+                                                      long long npix, int Sy, int Sx, int D, float anchor_w,
+                                                      float anchor_h, float wmul, float hmul) {
+  __shared__ float sdb[HD_DP];
+  if (threadIdx.x < HD_DP) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int SS = Sy * Sx;
+  float db[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) db[d] = 0.f;
+  float db_hi[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) db_hi[d] = 0.f;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < npix; p += (long long)gridDim.x * 256) {
+    const int n = (int)(p / SS), cell = (int)(p % SS);
+    const float* g = dpred + (long long)n * D * SS + cell;
+    const float* t = t_raw + p * D;
+    float v[HD_DP];
+#pragma unroll
+    for (int d = 0; d < HD_DP; ++d) v[d] = 0.f;
+    const float t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4];
+    const float s0 = sigmoidf_(t0), s1 = sigmoidf_(t1), s4 = sigmoidf_(t4);
+    v[0] = g[0] * (1.f / (float)Sx) * s0 * (1.f - s0);
+    v[1] = g[(long long)SS] * (1.f / (float)Sy) * s1 * (1.f - s1);
+    v[2] = t2 <= 80.f ? g[2LL * SS] * anchor_w * expf(t2) * wmul : 0.f;
+    v[3] = t3 <= 80.f ? g[3LL * SS] * anchor_h * expf(t3) * hmul : 0.f;
+    v[4] = g[4LL * SS] * s4 * (1.f - s4);
+#pragma unroll
+    for (int d = 5; d < HD_DP; ++d)
+      if (d < D) v[d] = g[(long long)d * SS];
+    __align__(16) bf16 ob[HD_DP];
+#pragma unroll
+    for (int d = 0; d < HD_DP; ++d) ob[d] = __float2bfloat16_rn(v[d]);
+    uint4* dst = reinterpret_cast<uint4*>(dt + p * HD_DP);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<uint4*>(ob)[i];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { db[d] += v[d]; db_hi[d] += v[16 + d]; }
+  }
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    const float a = warp_sum(db[d]);
+    const float b = (D > 16) ? warp_sum(db_hi[d]) : 0.f;
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sdb[d], a); if (D > 16) atomicAdd(&sdb[16 + d], b); }
+  }
+  __syncthreads();
+  if (threadIdx.x < D) db_partial[(long long)blockIdx.x * D + threadIdx.x] = sdb[threadIdx.x];
+}
 
 }  // namespace yg
 using namespace yg;
@@ -387,9 +446,26 @@ extern "C" int yg_head_fwd(const void* x, int dtype, const float* w, const float
   return YG_OK;
 }
 
+static size_t head_tc_offsets(int N, int Sy, int Sx, int Cin, int D, size_t* off_db, size_t* off_wg) {
+  const size_t npix = (size_t)N * Sy * Sx;
+  size_t o = npix * HD_DP * sizeof(bf16);
+  o = (o + 255) & ~(size_t)255;
+  *off_db = o;
+  o += (size_t)HD_DT_BLOCKS * D * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  *off_wg = o;
+  return o + head_bwd_tc_workspace(Cin);
+}
+
 extern "C" size_t yg_head_bwd_workspace(int N, int Sy, int Sx, int Cin, int num_classes) {
   const int D = 5 + num_classes;
-  return (size_t)HD_BWD_BLOCKS * ((size_t)D * Cin + D) * sizeof(float);
+  size_t a = (size_t)HD_BWD_BLOCKS * ((size_t)D * Cin + D) * sizeof(float);
+  if (head_bwd_tc_supported(Cin, D)) {
+    size_t o1, o2;
+    const size_t b = head_tc_offsets(N, Sy, Sx, Cin, D, &o1, &o2);
+    if (b > a) a = b;
+  }
+  return a;
 }
 
 extern "C" int yg_head_bwd(const float* dpred, const float* t_raw, const void* x, const float* w, void* dx, int dtype,
@@ -408,6 +484,23 @@ extern "C" int yg_head_bwd(const float* dpred, const float* t_raw, const void* x
   }
   BwdEpi be = make_bwd_epi(bep);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == YG_BF16 && dx && npix > 0 && yg_get_conv_impl() != YG_IMPL_SIMT && head_bwd_tc_supported(Cin, D)) {
+    // tensor-core path: dt (bf16, padded) -> dgrad engine (1 tap) + wgrad engine (1 column); bias from the dt pass
+    size_t off_db, off_wg;
+    head_tc_offsets(N, Sy, Sx, Cin, D, &off_db, &off_wg);
+    bf16* dt = (bf16*)workspace;
+    float* dbp = (float*)((char*)workspace + off_db);
+    int nb = (int)((npix + 255) / 256);
+    if (nb > HD_DT_BLOCKS) nb = HD_DT_BLOCKS;
+    head_dt_kernel<<<nb, 256, 0, st>>>(dpred, t_raw, dt, dbp, npix, Sy, Sx, D, anchor_w, anchor_h, width_mult, height_mult);
+    YG_LAUNCH_CHECK("head_dt");
+    if (dbias) {
+      head_reduce_kernel<<<1, 256, 0, st>>>(dbp, nullptr, dbias, 0, D, nb, clip);
+      YG_LAUNCH_CHECK("head_bias_reduce");
+    }
+    return head_bwd_tc(dt, x, w, dx, dw, N, Sy, Sx, Cin, D, be, clip, (char*)workspace + off_wg,
+                       workspace_bytes - off_wg, st);
+  }
   int blocks = cdiv(npix, HD_PX);
   if (blocks > HD_BWD_BLOCKS) blocks = HD_BWD_BLOCKS;
   if (blocks < 1) blocks = 1;
