@@ -25,6 +25,9 @@ CASES = [
     ("dgrad", 2, 19, 35, 64, 128, 1),
     ("dgrad", 2, 20, 36, 32, 64, 2),
     ("dgrad", 2, 21, 37, 128, 128, 2),
+    ("dgrad", 2, 21, 36, 32, 64, 2),
+    ("dgrad", 2, 20, 37, 32, 64, 2),
+    ("dgrad", 3, 37, 70, 16, 32, 2),
     ("dgrad", 2, 19, 35, 16, 32, 1),
     ("wgrad", 1, 8, 16, 64, 128, 1),
     ("wgrad", 1, 8, 16, 64, 64, 1),

@@ -59,7 +59,7 @@ struct TcParams {
   TcClass cls[4];
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
-  int OH, OW, OC, os;             // output tensor (NHWC) and tile-space -> output stride
+  int OH, OW, OC, osh, osw;       // output tensor (NHWC) and tile-space -> output strides (rows, columns)
   int OCr;                        // real channel count (OC / W-fold factor): per-channel arrays are indexed modulo OCr
   int BN, kchunks, nstages, nacc;
   int a_box_bytes, b_stage_bytes;   // bytes reserved per A box / per stage for streamed weight tiles
@@ -477,7 +477,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int th = t % p.tiles_h;
       const int n = t / p.tiles_h;
       const int a = th * TC_TH + hl, b = tw * TC_TW + wl;
-      const int oh = a * p.os + C.oh0, ow = b * p.os + C.ow0;
+      const int oh = a * p.osh + C.oh0, ow = b * p.osw + C.ow0;
       const bool valid = a < C.TSH && b < C.TSW && oh < p.OH && ow < p.OW;
       const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
       if (p.dropscale && n != ds_n) {
@@ -499,7 +499,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const int th2 = t2 % p.tiles_h;
           const int n2 = t2 / p.tiles_h;
           const int a2 = th2 * TC_TH + hl, b2 = tw2 * TC_TW + wl;
-          const int oh2 = a2 * p.os + C2.oh0, ow2 = b2 * p.os + C2.ow0;
+          const int oh2 = a2 * p.osh + C2.oh0, ow2 = b2 * p.osw + C2.ow0;
           if (a2 < C2.TSH && b2 < C2.TSW && oh2 < p.OH && ow2 < p.OW) {
             const bf16* row = reinterpret_cast<const bf16*>(p.saved) +
                               (((long long)n2 * p.OH + oh2) * p.OW + ow2) * p.OC + nt2 * BN;
@@ -764,8 +764,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
   out[i] = __float2bfloat16_rn(v);
 }
 
+// Stride-2 dgrad with column pairs folded (see conv_dgrad_tc): [slice = r*2 + dxo][(q,ci)][co], where the
+// output column is x = 2x'+q and the tap reads dz column x'+dxo:  (q=0,dxo=0) -> s=1, (q=1,dxo=0) -> s=2,
+// (q=1,dxo=1) -> s=0, (q=0,dxo=1) -> structurally zero.
+__global__ void pack_weights_s2fold_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+  const long long total = 6LL * 2 * Cin * Cout;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = (int)(i % Cout);
+  const int cif = (int)((i / Cout) % (2 * Cin));
+  const int sl = (int)(i / ((long long)2 * Cin * Cout));
+  const int q = cif / Cin, ci = cif % Cin, r = sl >> 1, dxo = sl & 1;
+  const int s = q == 0 ? (dxo == 0 ? 1 : -1) : (dxo == 0 ? 2 : 0);
+  float v = 0.f;
+  if (s >= 0) v = w[((long long)co * Cin + ci) * 9 + r * 3 + s];
+  out[i] = __float2bfloat16_rn(v);
+}
+
 // ------------------------------------------------------------------------------------------ host
-static int g_tc_options = 9;  // bit 0: resident weights, bit 1: cp.async producer, bit 2: L2 prefetch warp, bit 3: W-fold
+static int g_tc_options = 25;  // bit 0: resident weights, bit 1: cp.async producer, bit 2: L2 prefetch warp, bit 3: W-fold,
+                               // bit 4: column-pair fold for stride-2 dgrad
 // W-fold factor for stride-1 convolutions with few channels (see pack_weights_kernel): fold while the folded
 // input channel count stays <= 64 and everything remains a legal UMMA shape.
 static int fold_factor(int Cin, int Cout, int W, int stride) {
@@ -773,6 +791,10 @@ static int fold_factor(int Cin, int Cout, int W, int stride) {
   for (int g = 4; g >= 2; g >>= 1)
     if (W % g == 0 && g * Cin <= 64 && g * Cout <= 256 && (g * Cin) % 16 == 0 && (g * Cout) % 16 == 0) return g;
   return 1;
+}
+// Stride-2 dgrad with few input channels: fold output column pairs (2 classes x N = 2*Cin instead of 4 x N = Cin).
+static bool s2fold_dgrad(int Cin, int W, int stride) {
+  return stride == 2 && (g_tc_options & 16) && W % 2 == 0 && 2 * Cin <= 64 && (2 * Cin) % 16 == 0;
 }
 // bit kk set <=> K step kk (16 folded channels) of folded tap column sp touches a sub-pixel with non-zero weights.
 // kdim_is_input: K runs over (pi, ci) [fprop / wgrad-B], otherwise over (q, co) [dgrad].
@@ -843,8 +865,8 @@ bool tc_fwd_supported(int dtype, int W, int Cin, int Cout, int ks, int stride) {
 }
 bool tc_dgrad_supported(int dtype, int W, int Cin, int Cout, int ks, int stride) {
   if (dtype != YG_BF16 || ks != 3 || (stride != 1 && stride != 2)) return false;
-  const int g = fold_factor(Cin, Cout, W, stride);
-  return pick_kc(Cout * g) && pick_bn(Cin * g) && Cin * g <= 512;
+  const int g = s2fold_dgrad(Cin, W, stride) ? 2 : fold_factor(Cin, Cout, W, stride);
+  return pick_kc(Cout * (stride == 1 ? g : 1)) && pick_bn(Cin * g) && Cin * g <= 512;
 }
 
 
@@ -1414,7 +1436,8 @@ static std::map<PackKey, std::pair<void*, size_t>> g_pack_cache;
 static std::mutex g_pack_mutex;
 
 static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int transpose, int g, cudaStream_t st) {
-  const long long total = (long long)Cout * Cin * 9 * g * g;
+  // transpose == 2: stride-2 dgrad with folded column pairs (6 slices of [2 Cin][Cout])
+  const long long total = transpose == 2 ? 12LL * Cout * Cin : (long long)Cout * Cin * 9 * g * g;
   {
     std::lock_guard<std::mutex> lock(g_pack_mutex);
     int dev = 0;
@@ -1431,7 +1454,8 @@ static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int trans
       *out = (bf16*)it->second.first;
     }
   }
-  pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, *out, Cout, Cin, 9, transpose, g);
+  if (transpose == 2) pack_weights_s2fold_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, *out, Cout, Cin);
+  else pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, *out, Cout, Cin, 9, transpose, g);
   YG_LAUNCH_CHECK("pack_weights");
   return YG_OK;
 }
@@ -1515,7 +1539,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
   p.n_ntiles = Cout / BN;
   p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
-  p.OH = Ho; p.OW = Wo; p.OC = Cout; p.OCr = Cout_r; p.os = 1;
+  p.OH = Ho; p.OW = Wo; p.OC = Cout; p.OCr = Cout_r; p.osh = p.osw = 1;
   p.BN = BN; p.kchunks = Cin / KCc;
   p.out = y;
   p.scale = ep.scale; p.shift = ep.shift; p.act = ep.act; p.dropscale = ep.dropscale; p.stats = ep.stats;
@@ -1527,16 +1551,19 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
 int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W, int Cin, int Cout, int ks, int stride,
                   const BwdEpi& be, cudaStream_t st) {
   if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  const bool s2f = s2fold_dgrad(Cin, W, stride);
   const int fg = fold_factor(Cin, Cout, W, stride);
   const int Cin_r = Cin, Cout_r = Cout;
-  W /= fg; Cin *= fg; Cout *= fg;
-  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int Ho = (H + 2 - 3) / stride + 1;
+  int Wo;
+  if (s2f) { Wo = (W + 2 - 3) / 2 + 1; W /= 2; Cin *= 2; }   // dx viewed as (N, H, W/2, 2 Cin); dz unchanged
+  else { W /= fg; Cin *= fg; Cout *= fg; Wo = (W + 2 - 3) / stride + 1; }
   const int BN = pick_bn(Cin);
   const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
   const int KCc = fit_kc(Cout, BN, max_rows);
   if (!KCc) { set_error("conv_dgrad_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
   bf16* wp = nullptr;
-  int rc = pack_weights(w, &wp, Cout_r, Cin_r, 1, fg, st);
+  int rc = pack_weights(w, &wp, Cout_r, Cin_r, s2f ? 2 : 1, fg, st);
   if (rc) return rc;
   const bf16* gb = (const bf16*)dz;
   TcMaps maps;
@@ -1544,7 +1571,7 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   TcParams p;
   memset(&p, 0, sizeof(p));
   {
-    uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, 9};
+    uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)(s2f ? 6 : 9)};
     uint64_t str[2] = {(uint64_t)Cout * 2, (uint64_t)Cin * Cout * 2};
     uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
     rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
@@ -1571,8 +1598,29 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
     }
     p.ncls = 1;
     p.cls[0] = TcClass{0, 3, 1, H, W, 0, 0};
-    p.os = 1;
+    p.osh = p.osw = 1;
     p.tiles_h = cdiv(H, TC_TH); p.tiles_w = cdiv(W, TC_TW);
+  } else if (s2f) {
+    // Few input channels: output column pairs (x = 2x'+q) are folded into the channel dimension, which leaves two
+    // row-parity classes with N = 2 Cin and taps over dz columns x', x'+1: half the tiles, twice as wide MMAs,
+    // and every output pixel pair is written as one contiguous run instead of two strided halves.
+    int gi = 0;
+    for (int qh = 0; qh < 2; ++qh) {
+      TcClass& C = p.cls[qh];
+      C.g0 = gi; C.TSH = (H - qh + 1) / 2; C.TSW = W; C.oh0 = qh; C.ow0 = 0; C.gpi = 1;
+      for (int dxo = 0; dxo < 2; ++dxo) {
+        TcGroup& g = p.g[gi++];
+        g.map = qh ? 0 : 1; g.dh = 0; g.dw = dxo; g.rows = TC_TH + qh;
+        if (qh) { g.ntaps = 2; g.ro[0] = 1; g.widx[0] = 0 * 2 + dxo; g.ro[1] = 0; g.widx[1] = 2 * 2 + dxo; }
+        else { g.ntaps = 1; g.ro[0] = 0; g.widx[0] = 1 * 2 + dxo; }
+        g.kmask[0] = g.kmask[1] = 0xFFFFFFFFu;
+      }
+      C.ng = 2;
+    }
+    p.ncls = 2;
+    p.osh = 2; p.osw = 1;
+    p.ntaps_total = 6;
+    p.tiles_h = cdiv((H + 1) / 2, TC_TH); p.tiles_w = cdiv(W, TC_TW);
   } else {
     // Four output-parity classes (qh, qw): h = 2a+qh, w = 2b+qw.  qh=0: r=1 (dz row a).  qh=1: r=0 (row a+1), r=2
     // (row a); same for columns.  All four run in ONE launch with the class as the fastest tile index, so the dz
@@ -1596,7 +1644,7 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
       C.ng = gi - C.g0;
     }
     p.ncls = 4;
-    p.os = 2;
+    p.osh = p.osw = 2;
     // tile space of the largest class (qh = qw = 0); smaller classes mask their last row / column
     p.tiles_h = cdiv((H + 1) / 2, TC_TH); p.tiles_w = cdiv((W + 1) / 2, TC_TW);
   }
@@ -1705,7 +1753,7 @@ int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* 
     g.kmask[0] = D <= 16 ? 1u : 3u;   // the second 16-wide K step is all padding when D <= 16
     p.ncls = 1;
     p.cls[0] = TcClass{0, 1, 1, Sy, Sx, 0, 0};
-    p.os = 1;
+    p.osh = p.osw = 1;
     p.tiles_h = cdiv(Sy, TC_TH); p.tiles_w = cdiv(Sx, TC_TW);
     p.N = N; p.n_ntiles = Cin / BN;
     p.total_tiles = N * p.tiles_h * p.tiles_w * p.n_ntiles;
