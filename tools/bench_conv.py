@@ -85,6 +85,15 @@ def main():
             act_bytes = (N * H * W * Cin + N * Ho * Wo * Cout) * 2
             rec = {"opt": args.tc_options, "layer": li, "op": name, "shape": [N, H, W, Cin, Cout, s], "ms": round(ms, 4), "TFLOPs": round(tf, 1),
                    "frac_bf16_peak": round(tf / peaks["bf16_tflops"], 3), "min_GBps": round(act_bytes / ms / 1e6, 1)}
+            if (args.tc_options >> 11) & 1 and name != "wgrad":
+                import numpy as np
+                buf = np.zeros(148 * 8, dtype=np.uint64)
+                L.check(lib.yg_tc_debug_read(buf.ctypes.data, buf.size))
+                d = buf.reshape(148, 8).astype(np.float64)
+                items = max(d[:, 5].mean(), 1.0)
+                rec["mma_warp_cycles_per_item"] = {k: round(float(d[:, i].mean() / items), 1)
+                                                   for i, k in enumerate(["wait_tempty", "wait_full", "issue", "commit", "rest"])}
+                rec["items_per_cta"] = items
             print(json.dumps(rec), flush=True)
             out.append(rec)
 

@@ -60,6 +60,7 @@ _PROTOS = {
     "yg_set_conv_impl": (c_int, [c_int]),
     "yg_get_conv_impl": (c_int, []),
     "yg_set_tc_options": (c_int, [c_int]),
+    "yg_tc_debug_read": (c_int, [c_void_p, c_int]),
     "yg_launch_count": (C.c_ulonglong, []),
     "yg_conv_first_fwd": (
         c_int,

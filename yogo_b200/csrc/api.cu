@@ -29,6 +29,7 @@ int conv_dgrad_tc(const void*, const float*, void*, int, int, int, int, int, int
 int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace(int, int, int, int, int, int, int);
 int set_tc_options(int);
+int tc_debug_read(unsigned long long*, int);
 
 static int check_conv_args(const char* who, int dtype, int N, int H, int W, int Cin, int Cout, int ks, int stride) {
   YG_CHECK_ARG(dtype == YG_F32 || dtype == YG_BF16, "%s: dtype %d", who, dtype);
@@ -64,6 +65,7 @@ extern "C" int yg_set_conv_impl(int impl) {
 }
 extern "C" int yg_get_conv_impl(void) { return g_conv_impl; }
 extern "C" int yg_set_tc_options(int v) { return set_tc_options(v); }
+extern "C" int yg_tc_debug_read(unsigned long long* out, int n) { return tc_debug_read(out, n); }
 
 extern "C" int yg_conv_fwd(const void* x, const float* w, void* y, int dtype, int N, int H, int W, int Cin, int Cout,
                            int ks, int stride, const yg_fwd_epilogue* epp, void* stream) {

@@ -27,7 +27,7 @@ namespace yg {
 constexpr int TC_TH = 8, TC_TW = 16;          // output tile (pixels), M = 128
 // conv_tc_kernel: (1 or 2) producer warps + 1 MMA warp + 8 epilogue warps
 constexpr int TC_MAX_GROUPS = 9, TC_MAX_TAPS = 3;
-constexpr int TC_SMEM_BUDGET = 227 * 1024 - 14 * 1024;
+constexpr int TC_SMEM_BUDGET = 227 * 1024 - 15 * 1024;
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;   // bounded mbarrier spin: trap instead of hanging the GPU
 
 struct TcMaps {
@@ -55,7 +55,7 @@ struct TcClass {   // one output-parity class of a stride-2 dgrad (or the whole 
 
 struct TcParams {
   int N, tiles_h, tiles_w, n_ntiles, total_tiles;
-  int ncls;
+  int ncls, cls_rot;                // classes and the rotation period max(1, grid / ncls) (see tile_class)
   TcClass cls[4];
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
@@ -74,7 +74,25 @@ struct TcParams {
   const void* saved; const float* bn_scale; const float* bn_shift; const float* bn_mean; const float* bn_invstd;
   double* bn_sums;
   int* error_flag;
+  // MMA issue table (host-built, read through the constant bank = uniform loads): per (group, tap) the operand
+  // offsets inside a stage in 16-byte descriptor units and the K-step mask; ebeg[g] = first entry of group g
+  uint32_t tab_a[TC_MAX_GROUPS * TC_MAX_TAPS], tab_b[TC_MAX_GROUPS * TC_MAX_TAPS], tab_km[TC_MAX_GROUPS * TC_MAX_TAPS];
+  int ebeg[TC_MAX_GROUPS + 1];
+  int debug;   // profiling knobs (tools/bench_conv.py): 1 = no global stores, 2 = no MMA issue, 4 = epilogue skips TMEM loads and math, 8 = no TMA loads, 16 = MMA-warp cycle counters -> g_tc_dbg
 };
+
+// cycle counters of the MMA warp, one row of 8 per CTA (debug bit 16): wait tempty, wait full, issue, commit, rest
+__device__ unsigned long long g_tc_dbg[256 * 8];
+
+// Output-parity class of a tile.  Sibling classes of one spatial tile are neighbours in the tile order (they
+// share dz and saved-activation lines in L2); the class of slot c rotates with the spatial index so that a
+// persistent CTA, whose stride gridDim.x is normally a multiple of ncls, cycles through all classes instead
+// of being stuck with the cheapest (1 tap) or the most expensive (4 taps) one.
+__device__ __forceinline__ int tile_class(const TcParams& p, int tile) {
+  if (p.ncls == 1) return 0;
+  const int sp = tile / p.ncls, c = tile - sp * p.ncls;
+  return (c + sp / p.cls_rot) % p.ncls;
+}
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,6 +157,84 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// same, descriptors given as (low word, shared high word): the issuing thread only ever adds to the low words
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %4};\nmov.b64 db, {%2, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(hi), "r"(accum)
+      : "memory");
+}
+// same with separate high words (the MN-major wgrad operands have different strides / swizzles)
+__device__ __forceinline__ void umma_bf16_lh2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// ---- "one elected lane issues" variants: executed by the whole (converged) warp with the election result as a
+// predicate inside the asm.  With warp-uniform operands ptxas emits the bare uniform-datapath instruction; issuing
+// from an `if (lane == 0)` branch instead costs an ELECT / BRA.U.ANY waterfall loop around every instruction
+// (~90 cycles per tcgen05.mma measured, more than the 64 cycles a 128x128x16 MMA takes to execute).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_lh_p(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                               uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n.reg .b64 da, db;\nsetp.ne.b32 p, %5, 0;\nsetp.ne.b32 q, %6, 0;\n"
+      "mov.b64 da, {%1, %4};\nmov.b64 db, {%2, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(hi), "r"(accum), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lh2_p(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nsetp.ne.b32 q, %7, 0;\n"
+      "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
+      ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t leader) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n"
+               ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_p(uint64_t* bar, uint32_t leader) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n"
+               ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_p(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                              int c3, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                              uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %6, 0;\n"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -220,7 +316,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
   float* s_ds = s_const + 4 * 512;                          // [512] Dropout2d scales of the image being processed
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows that role dispatch and everything derived from kernel
+  // parameters inside a role is warp-uniform (uniform registers feed UTCHMMA / UTMALDG directly)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int BN = p.BN;
 
   if (warp == 0 && lane == 0) {
@@ -265,37 +363,47 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (warp < PW) {
     if (PROD == 0) {
       // ===================================================================== TMA producer
-      if (lane == 0) {
+      // the whole warp runs the loop (uniform control flow), one elected lane issues
+      {
+        const uint32_t leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
+        const int nstages = p.nstages, kchunks = p.kchunks, b_resident = p.b_resident;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-          *prod_iter = iter++;
+          if (lane == 0) *prod_iter = iter;
+          ++iter;
           int t = tile;
-          const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
+          const TcClass& C = p.cls[tile_class(p, t)]; t /= p.ncls;
           const int nt = t % p.n_ntiles; t /= p.n_ntiles;
           const int tw = t % p.tiles_w; t /= p.tiles_w;
           const int th = t % p.tiles_h;
           const int n = t / p.tiles_h;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            for (int g0 = C.g0; g0 < C.g0 + C.ng; g0 += C.gpi) {
+          const int cg0 = C.g0, cg1 = C.g0 + C.ng, gpi = C.gpi;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            for (int g0 = cg0; g0 < cg1; g0 += gpi) {
               mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
               unsigned char* sa = smem + (size_t)stage * stage_bytes;
               unsigned char* sb = sa + p.a_stage_bytes;
-              uint32_t bytes = 0;
-              for (int gi = g0; gi < g0 + C.gpi; ++gi)
-                bytes += (uint32_t)(p.g[gi].rows * TC_TW * (int)ROW_BYTES + (p.b_resident ? 0 : p.g[gi].ntaps * p.b_tap_bytes));
-              mbar_expect_tx(&full_bar[stage], bytes);
-              for (int gi = g0; gi < g0 + C.gpi; ++gi) {
-                const TcGroup& g = p.g[gi];
-                tma_load_4d(sa + (size_t)(gi - g0) * p.a_box_bytes, &maps.a[g.map], &full_bar[stage], kc * KC,
-                            tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
-                if (!p.b_resident)
-                  for (int tp = 0; tp < g.ntaps; ++tp)
-                    tma_load_3d(sb + (size_t)((gi - g0) * TC_MAX_TAPS + tp) * p.b_tap_bytes, &maps.b, &full_bar[stage],
-                                kc * KC, nt * BN, g.widx[tp]);
+              if (p.debug & 8) {
+                mbar_arrive_p(&full_bar[stage], leader);
+                if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                continue;
               }
-              if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+              uint32_t bytes = 0;
+              for (int gi = g0; gi < g0 + gpi; ++gi)
+                bytes += (uint32_t)(p.g[gi].rows * TC_TW * (int)ROW_BYTES + (b_resident ? 0 : p.g[gi].ntaps * p.b_tap_bytes));
+              mbar_expect_tx_p(&full_bar[stage], bytes, leader);
+              for (int gi = g0; gi < g0 + gpi; ++gi) {
+                const TcGroup& g = p.g[gi];
+                tma_load_4d_p(sa + (size_t)(gi - g0) * p.a_box_bytes, &maps.a[g.map], &full_bar[stage], kc * KC,
+                              tw * TC_TW + g.dw, th * TC_TH + g.dh, n, leader);
+                if (!b_resident)
+                  for (int tp = 0; tp < g.ntaps; ++tp)
+                    tma_load_3d_p(sb + (size_t)((gi - g0) * TC_MAX_TAPS + tp) * p.b_tap_bytes, &maps.b, &full_bar[stage],
+                                  kc * KC, nt * BN, g.widx[tp], leader);
+              }
+              if (++stage == nstages) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -309,7 +417,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       int hist[LAG] = {0, 0};        // stages of the last LAG committed groups (oldest first)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int t = tile;
-        const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
+        const TcClass& C = p.cls[tile_class(p, t)]; t /= p.ncls;
         t /= p.n_ntiles;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h;
@@ -369,56 +477,72 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     int acc = 0;
     uint32_t acc_phase = 0;
     if (p.b_resident) mbar_wait(&resb_bar[0], 0, p.error_flag, 5);
+    // descriptors differ only in their 14-bit start-address field (16-byte units): build one and add offsets
+    const uint64_t desc0 = umma_desc(smem_u32(smem), SBO, LAYOUT);
+    const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc0_lo = (uint32_t)desc0;
+    const uint32_t bres0_lo = (uint32_t)umma_desc(smem_u32(resb), SBO, LAYOUT);
+    const uint32_t stage_units = (uint32_t)stage_bytes >> 4, a_units = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t tap_units = (uint32_t)p.b_tap_bytes >> 4;
+    const int b_resident = p.b_resident, kchunks = p.kchunks, nstages = p.nstages, nacc = p.nacc;
+    const bool prof = (p.debug & 16) != 0;
+    const uint32_t leader = elect_one();
+    long long c_tempty = 0, c_full = 0, c_issue = 0, c_commit = 0, c_rest = 0, c_items = 0, tprev = clock64();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long ta = 0;
+      if (prof) ta = clock64();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, p.error_flag, 2);
+      if (prof) { const long long tb = clock64(); c_tempty += tb - ta; c_rest += ta - tprev; tprev = tb; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      const TcClass& C = p.cls[tile % p.ncls];
-      const int items = p.kchunks * (C.ng / C.gpi);
-      int item = 0;
+      const TcClass& C = p.cls[tile_class(p, tile)];
+      const int cg0 = C.g0, cg1 = C.g0 + C.ng, gpi = C.gpi;
       uint32_t started = 0;   // 0 until the first MMA of this tile has been issued (overwrite vs accumulate)
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        for (int g0 = C.g0; g0 < C.g0 + C.ng; g0 += C.gpi, ++item) {
+      for (int kc = 0; kc < kchunks; ++kc) {
+        for (int g0 = cg0; g0 < cg1; g0 += gpi) {
+          long long t0 = 0, t1 = 0, t2 = 0;
+          if (prof) t0 = clock64();
           mbar_wait(&full_bar[stage], phase, p.error_flag, 3);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa0 = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t sb = sa0 + (uint32_t)p.a_stage_bytes;
-            for (int gi = g0; gi < g0 + C.gpi; ++gi) {
-              const TcGroup& g = p.g[gi];
-              const uint32_t sa = sa0 + (uint32_t)((gi - g0) * p.a_box_bytes);
-              for (int tp = 0; tp < g.ntaps; ++tp) {
-                const uint32_t a0 = sa + (uint32_t)(g.ro[tp] * TC_TW) * ROW_BYTES;
-                const uint32_t b0 = p.b_resident
-                                        ? smem_u32(resb) + (uint32_t)((g.widx[tp] * p.kchunks + kc) * p.b_tap_bytes)
-                                        : sb + (uint32_t)(((gi - g0) * TC_MAX_TAPS + tp) * p.b_tap_bytes);
-                const unsigned km = (g.kmask[tp] >> (kc * KSTEPS)) & ((1u << KSTEPS) - 1u);
-                // descriptors advance by 32 bytes (2 units of 16 B) per K step: one add instead of a rebuild
-                const uint64_t ad0 = umma_desc(a0, SBO, LAYOUT), bd0 = umma_desc(b0, SBO, LAYOUT);
-                if (km == (1u << KSTEPS) - 1u) {
+          if (prof) t1 = clock64();
+          // whole warp, uniform control flow; the elected lane issues (predicate inside the asm)
+          const uint32_t ast = desc0_lo + (uint32_t)stage * stage_units;
+          const uint32_t bst = b_resident ? bres0_lo + (uint32_t)kc * tap_units : ast + a_units;
+          const int e1 = p.ebeg[g0 + gpi];
+          for (int e = p.ebeg[g0]; e < e1; ++e) {
+            // descriptors advance by 32 bytes (2 units of 16 B) per K step
+            const uint32_t ad0 = ast + p.tab_a[e], bd0 = bst + p.tab_b[e];
+            const unsigned km = (p.tab_km[e] >> (kc * KSTEPS)) & ((1u << KSTEPS) - 1u);
+            if (p.debug & 2) continue;
+            if (km == (1u << KSTEPS) - 1u) {
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k) {
-                    umma_bf16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, started);
-                    started = 1u;
-                  }
-                } else {
+              for (int k = 0; k < KSTEPS; ++k) {
+                umma_bf16_lh_p(d_tmem, ad0 + 2u * k, bd0 + 2u * k, desc_hi, idesc, started, leader);
+                started = 1u;
+              }
+            } else {
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k) {
-                    if (!((km >> k) & 1u)) continue;   // structurally zero weights (W-folded convolution)
-                    umma_bf16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, started);
-                    started = 1u;
-                  }
-                }
+              for (int k = 0; k < KSTEPS; ++k) {
+                if (!((km >> k) & 1u)) continue;   // structurally zero weights (W-folded convolution)
+                umma_bf16_lh_p(d_tmem, ad0 + 2u * k, bd0 + 2u * k, desc_hi, idesc, started, leader);
+                started = 1u;
               }
             }
-            umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
-            if (item == items - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
           }
-          __syncwarp();
-          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+          if (prof) t2 = clock64();
+          umma_commit_p(&empty_bar[stage], leader);                                  // frees the smem slot when the MMAs retire
+          if (kc == kchunks - 1 && g0 + gpi >= cg1) umma_commit_p(&tfull_bar[acc], leader);  // accumulator complete
+          if (prof) {
+            const long long t3 = clock64();
+            c_rest += t0 - tprev; c_full += t1 - t0; c_issue += t2 - t1; c_commit += t3 - t2; tprev = t3; ++c_items;
+          }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
-      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (prof && lane == 0 && blockIdx.x < 256) {
+      unsigned long long* d = g_tc_dbg + blockIdx.x * 8;
+      d[0] = c_tempty; d[1] = c_full; d[2] = c_issue; d[3] = c_commit; d[4] = c_rest; d[5] = c_items;
     }
   } else if (warp == PW + 9) {
     // ===================================================================== L2 prefetch warp
@@ -430,7 +554,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
         while (iter > *prod_iter + p.pf_ahead) __nanosleep(256);
         int t = tile;
-        const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
+        const TcClass& C = p.cls[tile_class(p, t)]; t /= p.ncls;
         t /= p.n_ntiles;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h;
@@ -471,7 +595,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool has_bn = p.bn_scale != nullptr;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t = tile;
-      const TcClass& C = p.cls[t % p.ncls]; t /= p.ncls;
+      const TcClass& C = p.cls[tile_class(p, t)]; t /= p.ncls;
       const int nt = t % p.n_ntiles; t /= p.n_ntiles;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h;
@@ -493,7 +617,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int tile2 = tile + 2 * (int)gridDim.x;
         if (tile2 < p.total_tiles) {
           int t2 = tile2;
-          const TcClass& C2 = p.cls[t2 % p.ncls]; t2 /= p.ncls;
+          const TcClass& C2 = p.cls[tile_class(p, t2)]; t2 /= p.ncls;
           const int nt2 = t2 % p.n_ntiles; t2 /= p.n_ntiles;
           const int tw2 = t2 % p.tiles_w; t2 /= p.tiles_w;
           const int th2 = t2 % p.tiles_h;
@@ -511,7 +635,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      for (int j = half; j < BN / 16; j += 2) {
+      for (int j = half; j < ((p.debug & 4) ? 0 : BN / 16); j += 2) {
         uint32_t r[16];
         tmem_ld16(taddr0 + (uint32_t)(j * 16), r);
         const int cl = j * 16;          // channel inside the N tile
@@ -602,7 +726,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             reinterpret_cast<__nv_bfloat162*>(ob)[i] = __floats2bfloat162_rn(__uint_as_float(r[2*i]), __uint_as_float(r[2*i+1]));
-          if (valid) {
+          if (valid && !(p.debug & 1)) {
             if (out) {
               uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
               dst[0] = reinterpret_cast<uint4*>(ob)[0];
@@ -687,7 +811,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               s2[i] = g * s2[i];
             }
           }
-          if (valid) {
+          if (valid && !(p.debug & 1)) {
             uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
             dst[0] = reinterpret_cast<uint4*>(ob)[0];
             dst[1] = reinterpret_cast<uint4*>(ob)[1];
@@ -932,7 +1056,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   uint64_t* done_bar = empty_bar + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably uniform
   const int unit = blockIdx.x % p.nunits, slice = blockIdx.x / p.nunits;
   const int sg = unit % p.ncols, mt = (unit / p.ncols) % p.n_mtiles, nt = unit / (p.ncols * p.n_mtiles);
   const int a_blocks = min(MBLOCKS, (p.Cout - mt * 128) / KA);
@@ -962,28 +1086,31 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
 
   if (warp < PW) {
     if (PROD == 0) {
-      if (lane == 0) {
+      {
+        // whole warp, uniform control flow; the elected lane issues (see elect_one)
+        const uint32_t leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
+        const int nstages = p.nstages, ngroups = p.ngroups, nbblocks = p.nbblocks;
         for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
           int t = tile;
           const int tw = t % p.tiles_w; t /= p.tiles_w;
           const int th = t % p.tiles_h;
           const int n = t / p.tiles_h;
-          for (int gi = 0; gi < p.ngroups; ++gi) {
+          for (int gi = 0; gi < ngroups; ++gi) {
             const TwGroup& g = p.g[sg][gi];
             mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 11);
             unsigned char* sa = smem + (size_t)stage * p.stage_bytes;
             unsigned char* sb = sa + MBLOCKS * p.a_block_bytes;
-            const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + p.nbblocks * g.rows * TC_TW * (int)ROWB);
-            mbar_expect_tx(&full_bar[stage], bytes);
+            const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + nbblocks * g.rows * TC_TW * (int)ROWB);
+            mbar_expect_tx_p(&full_bar[stage], bytes, leader);
             for (int ab = 0; ab < a_blocks; ++ab)
-              tma_load_4d(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * KA, tw * TC_TW,
-                          th * TC_TH, n);
-            for (int bb = 0; bb < p.nbblocks; ++bb)
-              tma_load_4d(sb + (size_t)bb * p.b_block_bytes, &maps.b[g.map], &full_bar[stage], nt * BNW + bb * KB,
-                          tw * TC_TW + g.dw, th * TC_TH + g.dh, n);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+              tma_load_4d_p(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * KA, tw * TC_TW,
+                            th * TC_TH, n, leader);
+            for (int bb = 0; bb < nbblocks; ++bb)
+              tma_load_4d_p(sb + (size_t)bb * p.b_block_bytes, &maps.b[g.map], &full_bar[stage], nt * BNW + bb * KB,
+                            tw * TC_TW + g.dw, th * TC_TH + g.dh, n, leader);
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -1066,34 +1193,39 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     int stage = 0;
     uint32_t phase = 0;
     uint32_t started = 0;  // bit r set once accumulator slot r holds data
+    // descriptors of stage 0; everything else is an addition to the low words (16-byte units)
+    const uint64_t ad_base = umma_desc_mn(smem_u32(smem), (uint32_t)p.a_block_bytes, 8 * ROWA, LAYOUT_A);
+    const uint64_t bd_base = umma_desc_mn(smem_u32(smem) + (uint32_t)MBLOCKS * (uint32_t)p.a_block_bytes,
+                                          (uint32_t)p.b_block_bytes, 8 * ROWB, LAYOUT_B);
+    const uint32_t a_lo0 = (uint32_t)ad_base, a_hi = (uint32_t)(ad_base >> 32);
+    const uint32_t b_lo0 = (uint32_t)bd_base, b_hi = (uint32_t)(bd_base >> 32);
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+    const int nstages = p.nstages, ngroups = p.ngroups;
+    const uint32_t leader = elect_one();   // whole warp runs the loop, the elected lane issues
     for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
-      for (int gi = 0; gi < p.ngroups; ++gi) {
+      for (int gi = 0; gi < ngroups; ++gi) {
         const TwGroup& g = p.g[sg][gi];
         mbar_wait(&full_bar[stage], phase, p.error_flag, 13);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + (uint32_t)MBLOCKS * (uint32_t)p.a_block_bytes;
-          for (int tp = 0; tp < g.ntaps; ++tp) {
-            const int slot = g.slot[tp];
-            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BNW);
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units;
+        const uint32_t b_lo_s = b_lo0 + (uint32_t)stage * stage_units;
+        const int ntaps = g.ntaps;
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const int slot = g.slot[tp];
+          const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BNW);
+          const uint32_t b_lo = b_lo_s + (((uint32_t)(g.ro[tp] * TC_TW) * ROWB) >> 4);
+          const uint32_t acc0 = (started >> slot) & 1u;
+          umma_bf16_lh2_p(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc0, leader);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels = one 8x16 tile
-              const uint64_t ad = umma_desc_mn(sa + (uint32_t)k * 16u * ROWA, (uint32_t)p.a_block_bytes, 8 * ROWA, LAYOUT_A);
-              const uint64_t bd = umma_desc_mn(sb + (uint32_t)(g.ro[tp] * TC_TW + k * 16) * ROWB,
-                                               (uint32_t)p.b_block_bytes, 8 * ROWB, LAYOUT_B);
-              umma_bf16(d_tmem, ad, bd, idesc, ((started >> slot) & 1u) | (k > 0 ? 1u : 0u));
-            }
-            started |= 1u << slot;
-          }
-          umma_commit(&empty_bar[stage]);
+          for (int k = 1; k < 8; ++k)  // 8 x 16 pixels = one 8x16 tile; 16 pixel rows = ROW bytes = ROW/16 x 16 units
+            umma_bf16_lh2_p(d_tmem, a_lo + (uint32_t)k * ROWA, a_hi, b_lo + (uint32_t)k * ROWB, b_hi, idesc, 1u, leader);
+          started |= 1u << slot;
         }
-        started = __shfl_sync(0xffffffffu, started, 0);
-        __syncwarp();
-        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        umma_commit_p(&empty_bar[stage], leader);
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
-    if (lane == 0) umma_commit(&done_bar[0]);
+    umma_commit_p(&done_bar[0], leader);
     __syncwarp();
   } else {
     // epilogue: once, after the last MMA retired
@@ -1380,7 +1512,26 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
     YG_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
     YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   }
+  {
+    int e = 0;
+    for (int c = 0; c < p.ncls; ++c) {
+      const TcClass& C = p.cls[c];
+      for (int gi = C.g0; gi < C.g0 + C.ng; ++gi) {
+        const TcGroup& g = p.g[gi];
+        const int pos = (gi - C.g0) % C.gpi;   // position of the group inside its pipeline item
+        p.ebeg[gi] = e;
+        for (int tp = 0; tp < g.ntaps; ++tp, ++e) {
+          const uint32_t a_off = (uint32_t)(pos * p.a_box_bytes) + (uint32_t)(g.ro[tp] * TC_TW * KCc * 2);
+          const uint32_t b_off = p.b_resident ? (uint32_t)(g.widx[tp] * p.kchunks * p.b_tap_bytes)
+                                              : (uint32_t)((pos * TC_MAX_TAPS + tp) * p.b_tap_bytes);
+          p.tab_a[e] = a_off >> 4; p.tab_b[e] = b_off >> 4; p.tab_km[e] = g.kmask[tp];
+        }
+        p.ebeg[gi + 1] = e;
+      }
+    }
+  }
   p.error_flag = g_error_flag;
+  p.debug = (g_tc_options >> 7) & 31;
   p.pf_ahead = (g_tc_options & 4) ? 2 : 0;
   const size_t smem = (size_t)nst * stage_bytes + p.resb_bytes + 1024 /*align*/ + 512 /*barriers*/ +
                       (2 * 256 + 5 * 512 + 16) * sizeof(float) + 64;
@@ -1388,6 +1539,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  p.cls_rot = grid / p.ncls > 0 ? grid / p.ncls : 1;
 #define TC_LAUNCH(KCV, MODEV, PRODV)                                                                                    \
   do {                                                                                                                  \
     YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCV, MODEV, PRODV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -1408,10 +1560,18 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
 }
 
 int set_tc_options(int v) { g_tc_options = v; return 0; }
+int tc_debug_read(unsigned long long* out, int n) {
+  if (n > 256 * 8) n = 256 * 8;
+  YG_CUDA(cudaDeviceSynchronize());
+  YG_CUDA(cudaMemcpyFromSymbol(out, g_tc_dbg, (size_t)n * sizeof(unsigned long long)));
+  return YG_OK;
+}
 
 // choose KC so that at least 2 stages fit
 static int fit_kc(int K, int BN, int max_rows) {
   int kc = pick_kc(K);
+  if ((g_tc_options & 32) && kc > 32) kc = 32;   // experiment knobs: cap the K chunk (swizzle row) at 64 / 32 bytes
+  if ((g_tc_options & 64) && kc > 16) kc = 16;
   while (kc >= 16) {
     const int stage = ((max_rows * TC_TW * kc * 2 + 1023) & ~1023) + TC_MAX_TAPS * BN * kc * 2;
     if (K % kc == 0 && TC_SMEM_BUDGET / stage >= 2) return kc;
