@@ -63,6 +63,9 @@ typedef struct {
   double* stats;           /* [2*Cout] or NULL: += sum(v), sum(v*v) of v = acc*scale+shift
                               (BatchNorm batch statistics, taken before act)             */
   void* preact;            /* NHWC, same dtype as y, or NULL: v before the activation    */
+  void* actmask;           /* [N*Ho*Wo*Cout/8] bytes or NULL: bit e (NHWC element index, bit e%8 of byte
+                              e/8) = (v > 0).  One bit instead of 16 to carry LeakyReLU's slope to
+                              the backward pass; honoured by yg_conv_fwd, needs Cout % 32 == 0 */
 } yg_fwd_epilogue;
 
 typedef struct {
@@ -76,6 +79,9 @@ typedef struct {
   const float* bn_mean;    /* [Cin]                                                      */
   const float* bn_invstd;  /* [Cin]                                                      */
   double* bn_sums;         /* [2*Cin]: += sum(g), sum(g*xhat)                            */
+  const void* actmask;     /* the producer's yg_fwd_epilogue.actmask or NULL.  Used instead of `saved`
+                              by the tcgen05 path when act is LeakyReLU and that layer has no BN
+                              (16x less data to read); other paths read `saved`, so pass both */
 } yg_bwd_epilogue;
 
 /* ---- first layer: direct stencil on the NCHW image (Cin = 1 or 3) -------------------

@@ -233,6 +233,52 @@ def test_conv_kernels_vs_oracle(shape, dtype, impl):
         L.set_conv_impl("auto")
 
 
+@pytest.mark.parametrize("shape", [(2, 20, 36, 32, 64, 3, 2), (2, 19, 36, 32, 64, 3, 1), (2, 12, 20, 64, 128, 3, 1),
+                                   (1, 21, 37, 128, 128, 3, 2)])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_leaky_relu_sign_mask_equals_saved_activation_path(shape, impl):
+    """yg_fwd_epilogue.actmask / yg_bwd_epilogue.actmask: the 1-bit-per-element LeakyReLU record must give the
+    same dgrad result, bit for bit, as reading the saved activation (yogo/model.py's autograd keeps the tensor)."""
+    import ctypes as C
+    N, H, W, Cin, Cout, k, s = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    dt = torch.bfloat16
+    lib = L.lib()
+    L.set_conv_impl(impl)
+    try:
+        # producer: conv (Cin_p -> Cin) + bias + LeakyReLU + Dropout2d writes y and its sign mask
+        Cp = 16
+        xp = torch.randn(N, H, W, Cp, generator=g).to(DEV).to(dt)
+        wp = (torch.randn(Cin, Cp, 3, 3, generator=g) / 12).to(DEV)
+        bp = (torch.randn(Cin, generator=g) * 0.1).to(DEV)
+        keep = ((torch.rand(N, Cin, generator=g) > 0.2).float() / 0.8).to(DEV).contiguous()
+        y = torch.empty(N, H, W, Cin, device=DEV, dtype=dt)
+        pre = torch.empty_like(y)
+        mask = torch.zeros(N * H * W * Cin // 8, dtype=torch.uint8, device=DEV)
+        ep = L.FwdEpilogue(None, bp.data_ptr(), L.ACT_LRELU, keep.data_ptr(), None, pre.data_ptr(), mask.data_ptr())
+        L.check(lib.yg_conv_fwd(xp.data_ptr(), wp.data_ptr(), y.data_ptr(), 1, N, H, W, Cp, Cin, 3, 1, C.byref(ep), L.stream()))
+        bits = torch.from_numpy(np.unpackbits(mask.cpu().numpy(), bitorder="little")).reshape(N, H, W, Cin).bool()
+        kept = (keep > 0)[:, None, None, :].expand(N, H, W, Cin).cpu()
+        # wherever the channel was not dropped the bit is the sign of the activation input
+        assert torch.equal(bits[kept], (pre.float().cpu() > 0)[kept])
+        # consumer: dgrad of the next conv with the activation backward fused, mask vs saved tensor
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).to(dt)
+        w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV)
+        outs = []
+        for use_mask in (False, True):
+            dx = torch.empty(N, H, W, Cin, device=DEV, dtype=dt)
+            sums = torch.zeros(2 * Cin, dtype=torch.float64, device=DEV)
+            be = L.BwdEpilogue(y.data_ptr(), L.ACT_LRELU, keep.data_ptr(), None, None, None, None, sums.data_ptr(),
+                               mask.data_ptr() if use_mask else None)
+            L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, k, s, C.byref(be), L.stream()))
+            outs.append((dx.float().cpu(), sums.cpu()))
+        assert torch.equal(outs[0][0], outs[1][0])
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-3)   # fp32 smem + fp64 global atomics: order varies
+    finally:
+        L.set_conv_impl("auto")
+
+
 # ----------------------------------------------------------------------------- whole model vs golden
 def _build_from_golden(z, name, sdprefix="sd.", dtype=torch.float32, inference=False):
     sd = {k[len(sdprefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(sdprefix)}

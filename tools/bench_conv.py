@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--stats", type=int, default=0)
     ap.add_argument("--tc-options", type=int, default=25)
     ap.add_argument("--no-saved", type=int, default=0)
+    ap.add_argument("--mask", type=int, default=0)
     args = ap.parse_args()
     lib = L.lib()
     L.set_conv_impl(args.impl)
@@ -50,6 +51,8 @@ def main():
         b = torch.zeros(Cout, device=dev)
         y = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
         dx = torch.empty_like(x)
+        ymask = torch.empty(y.numel() // 8, dtype=torch.uint8, device=dev)
+        mask = torch.randint(0, 255, (x.numel() // 8,), dtype=torch.uint8, device=dev)
         dw = torch.empty_like(w)
         stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if args.stats else None
         nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, 3, s)
@@ -58,11 +61,12 @@ def main():
         st = L.stream()
 
         def fwd():
-            ep = L.FwdEpilogue(None, b.data_ptr(), 1, None, L.ptr(stats), None)
+            ep = L.FwdEpilogue(None, b.data_ptr(), 1, None, L.ptr(stats), None, ymask.data_ptr() if args.mask else None)
             L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(ep), st))
 
         def dgrad():
-            ep = L.BwdEpilogue(None if args.no_saved else x.data_ptr(), 1, None, None, None, None, None, None)
+            ep = L.BwdEpilogue(None if args.no_saved else x.data_ptr(), 1, None, None, None, None, None, None,
+                               mask.data_ptr() if args.mask else None)
             L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(ep), st))
 
         def wgrad():

@@ -36,6 +36,7 @@ class FwdEpilogue(C.Structure):
         ("dropscale", c_void_p),
         ("stats", c_void_p),
         ("preact", c_void_p),
+        ("actmask", c_void_p),
     ]
 
 
@@ -49,6 +50,7 @@ class BwdEpilogue(C.Structure):
         ("bn_mean", c_void_p),
         ("bn_invstd", c_void_p),
         ("bn_sums", c_void_p),
+        ("actmask", c_void_p),
     ]
 
 

@@ -67,6 +67,15 @@ extern "C" int yg_get_conv_impl(void) { return g_conv_impl; }
 extern "C" int yg_set_tc_options(int v) { return set_tc_options(v); }
 extern "C" int yg_tc_debug_read(unsigned long long* out, int n) { return tc_debug_read(out, n); }
 
+template <typename T>
+__global__ void actmask_from_output_kernel(const T* __restrict__ y, uint32_t* __restrict__ mask, long long nwords) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  uint32_t bits = 0;
+  for (int i = 0; i < 32; ++i) bits |= (to_f<T>(y[w * 32 + i]) > 0.f ? 1u : 0u) << i;
+  mask[w] = bits;
+}
+
 extern "C" int yg_conv_fwd(const void* x, const float* w, void* y, int dtype, int N, int H, int W, int Cin, int Cout,
                            int ks, int stride, const yg_fwd_epilogue* epp, void* stream) {
   int rc = check_conv_args("conv_fwd", dtype, N, H, W, Cin, Cout, ks, stride);
@@ -79,9 +88,21 @@ extern "C" int yg_conv_fwd(const void* x, const float* w, void* y, int dtype, in
     set_error("conv_fwd: tcgen05 path forced but shape unsupported (dtype %d Cin %d Cout %d k %d s %d)", dtype, Cin, Cout, ks, stride);
     return YG_ERR_INVALID;
   }
+  if (ep.actmask) YG_CHECK_ARG(Cout % 32 == 0 && y, "conv_fwd: actmask needs Cout % 32 == 0 and an output tensor");
   if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
     return conv_fwd_tc(x, w, y, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
-  return conv_fwd_simt(x, w, y, dtype, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
+  rc = conv_fwd_simt(x, w, y, dtype, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
+  if (rc == YG_OK && ep.actmask) {
+    // generic path: derive the sign bits from the stored output (sign(y) == sign(v) wherever dropscale != 0)
+    const int Ho = (H + 2 * (ks / 2) - ks) / stride + 1, Wo = (W + 2 * (ks / 2) - ks) / stride + 1;
+    const long long nwords = (long long)N * Ho * Wo * Cout / 32;
+    if (dtype == YG_BF16)
+      actmask_from_output_kernel<bf16><<<cdiv(nwords, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (uint32_t*)ep.actmask, nwords);
+    else
+      actmask_from_output_kernel<float><<<cdiv(nwords, 256), 256, 0, (cudaStream_t)stream>>>((const float*)y, (uint32_t*)ep.actmask, nwords);
+    YG_LAUNCH_CHECK("actmask_from_output");
+  }
+  return rc;
 }
 
 extern "C" int yg_conv_dgrad(const void* dz, const float* w, void* dx, int dtype, int N, int H, int W, int Cin,

@@ -94,13 +94,14 @@ struct BwdEpi {
   const float* bn_mean;
   const float* bn_invstd;
   double* bn_sums;
+  const void* actmask;
 };
 inline BwdEpi make_bwd_epi(const yg_bwd_epilogue* be) {
   BwdEpi e{};
   if (be) {
     e.saved = be->saved; e.act = be->act; e.dropscale = be->dropscale;
     e.bn_scale = be->bn_scale; e.bn_shift = be->bn_shift; e.bn_mean = be->bn_mean;
-    e.bn_invstd = be->bn_invstd; e.bn_sums = be->bn_sums;
+    e.bn_invstd = be->bn_invstd; e.bn_sums = be->bn_sums; e.actmask = be->actmask;
   }
   return e;
 }
@@ -128,12 +129,13 @@ struct FwdEpi {
   const float* dropscale;
   double* stats;
   void* preact;
+  void* actmask;
 };
 inline FwdEpi make_fwd_epi(const yg_fwd_epilogue* ep) {
   FwdEpi e{};
   if (ep) {
     e.scale = ep->scale; e.shift = ep->shift; e.act = ep->act; e.dropscale = ep->dropscale;
-    e.stats = ep->stats; e.preact = ep->preact;
+    e.stats = ep->stats; e.preact = ep->preact; e.actmask = ep->actmask;
   }
   return e;
 }

@@ -70,6 +70,8 @@ struct TcParams {
   void* out;
   // forward epilogue
   const float* scale; const float* shift; int act; const float* dropscale; double* stats; void* preact;
+  void* actmask_out;        // forward: sign bits of the pre-activation (see yg_fwd_epilogue.actmask)
+  const void* actmask_in;   // backward: the producer's sign bits, replaces `saved` for LeakyReLU without BN
   // backward epilogue
   const void* saved; const float* bn_scale; const float* bn_shift; const float* bn_mean; const float* bn_invstd;
   double* bn_sums;
@@ -593,6 +595,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const float* s_k2 = s_const + 1024;      //                 bwd: bn_mean
     const float* s_k3 = s_const + 1536;      //                 bwd: bn_invstd
     const bool has_bn = p.bn_scale != nullptr;
+    const bool use_mask = MODE == 1 && p.actmask_in && p.act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (p.OC % 32) == 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t = tile;
       const TcClass& C = p.cls[tile_class(p, t)]; t /= p.ncls;
@@ -611,7 +614,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         asm volatile("bar.sync 1, 256;" ::: "memory");
         ds_n = n;
       }
-      if (MODE == 1 && p.saved && half == 0) {
+      if (MODE == 1 && p.saved && half == 0 && !use_mask) {
         // pull the saved-activation rows of the tile after next into L2 now: by the time its epilogue runs,
         // the 32-byte operand loads hit L2 instead of paying an HBM round trip per 16-column chunk
         const int tile2 = tile + 2 * (int)gridDim.x;
@@ -631,6 +634,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c));
           }
         }
+      }
+      // LeakyReLU backward from the producer's sign bits: the BN / 8 bytes of this pixel are requested before the
+      // accumulator wait, so their latency hides behind the MMAs (the 16x larger `saved` row never does)
+      uint32_t mk[8];
+      if (MODE == 1 && use_mask) {
+        const uint32_t* mp = reinterpret_cast<const uint32_t*>(p.actmask_in) + ((pix * p.OC + nt * BN) >> 5);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) mk[w] = (valid && w * 32 < BN) ? __ldg(mp + w) : 0u;
       }
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
@@ -655,7 +666,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         __align__(16) bf16 sv[16];
         if (MODE == 1) {
-          if (p.saved && valid) {
+          if (p.saved && valid && !use_mask) {
             const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
             reinterpret_cast<uint4*>(sv)[0] = __ldg(src);
             reinterpret_cast<uint4*>(sv)[1] = __ldg(src + 1);
@@ -705,6 +716,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               s1[i] = valid ? x : 0.f;
               s2[i] = valid ? x * x : 0.f;
             }
+          }
+          if (p.actmask_out && valid) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bits |= (__uint_as_float(r[i]) > 0.f ? 1u : 0u) << i;
+            reinterpret_cast<unsigned short*>(p.actmask_out)[(pix * p.OC + c0) >> 4] = (unsigned short)bits;
           }
           if (p.act == YG_ACT_LRELU) {
 #pragma unroll
@@ -782,7 +799,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int i = 0; i < 16; ++i) s1[i] = __uint_as_float(r[i]);
           }
-          if (p.saved) {
+          if (use_mask) {
+            const int wi = j >> 1;   // 32-channel word of this chunk; chunks j = half, half+2, .. -> words 0, 1, ..
+            uint32_t word = mk[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) word = (wi == w) ? mk[w] : word;
+            const uint32_t bits = word >> ((j & 1) * 16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s1[i] *= ((bits >> i) & 1u) ? 1.f : 0.01f;
+          } else if (p.saved) {
             if (p.act == YG_ACT_LRELU) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) s1[i] *= pre[i] > 0.f ? 1.f : 0.01f;
@@ -811,6 +836,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               s2[i] = g * s2[i];
             }
           }
+          const bool second_sum = has_bn;   // sum(g * xhat) only exists for BatchNorm layers; sum(g) alone = d(bias)
           if (valid && !(p.debug & 1)) {
             uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
             dst[0] = reinterpret_cast<uint4*>(ob)[0];
@@ -818,10 +844,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
           if (p.bn_sums) {
             const float t1 = lane_transpose_reduce16(s1, lane);
-            const float t2 = lane_transpose_reduce16(s2, lane);
-            if (lane < 16) {
-              atomicAdd(&s_stat[cl + lane], t1);
-              atomicAdd(&s_stat[256 + cl + lane], t2);
+            if (lane < 16) atomicAdd(&s_stat[cl + lane], t1);
+            if (second_sum) {
+              const float t2 = lane_transpose_reduce16(s2, lane);
+              if (lane < 16) atomicAdd(&s_stat[256 + cl + lane], t2);
             }
           }
         }
@@ -1476,22 +1502,26 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   p.a_box_bytes = (max_rows * TC_TW * KCc * 2 + 1023) & ~1023;
   // small-K layers: merge all tap groups of a K chunk into one pipeline item, so that the fixed per-item
   // cost (mbarrier round trips, MMA issue, commit) is paid once per tile instead of 3-6 times
-  int max_gpi = 1;
-  for (int c = 0; c < p.ncls; ++c) {
-    p.cls[c].gpi = (p.cls[c].ng * p.a_box_bytes <= 32 * 1024) ? p.cls[c].ng : 1;
-    if (p.cls[c].gpi > max_gpi) max_gpi = p.cls[c].gpi;
-  }
-  p.a_stage_bytes = max_gpi * p.a_box_bytes;
   p.b_tap_bytes = p.BN * KCc * 2;
-  p.b_stage_bytes = max_gpi * TC_MAX_TAPS * p.b_tap_bytes;
-  // resident weights: all 9 x kchunks tiles stay in smem if at least 3 A stages still fit
   if (p.ntaps_total == 0) p.ntaps_total = 9;
   const int resb = (p.ntaps_total * p.kchunks * p.b_tap_bytes + 1023) & ~1023;
-  p.b_resident = 0;
-  p.resb_bytes = 0;
-  if ((g_tc_options & 1) && p.n_ntiles == 1 && (TC_SMEM_BUDGET - resb) / p.a_stage_bytes >= 3) {
-    p.b_resident = 1;
-    p.resb_bytes = resb;
+  for (int merge = 1; merge >= 0; --merge) {
+    int max_gpi = 1;
+    for (int c = 0; c < p.ncls; ++c) {
+      p.cls[c].gpi = (merge && p.cls[c].ng * p.a_box_bytes <= 32 * 1024) ? p.cls[c].ng : 1;
+      if (p.cls[c].gpi > max_gpi) max_gpi = p.cls[c].gpi;
+    }
+    p.a_stage_bytes = max_gpi * p.a_box_bytes;
+    p.b_stage_bytes = max_gpi * TC_MAX_TAPS * p.b_tap_bytes;
+    // resident weights: all 9 x kchunks tiles stay in smem if at least 3 A stages still fit
+    p.b_resident = 0;
+    p.resb_bytes = 0;
+    if ((g_tc_options & 1) && p.n_ntiles == 1 && (TC_SMEM_BUDGET - resb) / p.a_stage_bytes >= 3) {
+      p.b_resident = 1;
+      p.resb_bytes = resb;
+    }
+    // merged items with streamed weights can outgrow shared memory: fall back to one group per item
+    if (p.b_resident || TC_SMEM_BUDGET / (p.a_stage_bytes + p.b_stage_bytes) >= 3) break;
   }
   const int prod = (p.b_resident && KCc <= 32 && (g_tc_options & 2)) ? 1 : 0;
   const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
@@ -1704,6 +1734,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   p.out = y;
   p.scale = ep.scale; p.shift = ep.shift; p.act = ep.act; p.dropscale = ep.dropscale; p.stats = ep.stats;
   p.preact = ep.preact;
+  p.actmask_out = ep.actmask;
   rc = launch_engine(maps, p, KCc, 0, max_rows, st);
   return rc;
 }
@@ -1816,6 +1847,7 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   p.out = dx;
   p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
   p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
+  p.actmask_in = be.actmask;
   return launch_engine(maps, p, KCc, 1, max_rows, st);
 }
 
@@ -1922,6 +1954,7 @@ int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* 
     p.out = dx;
     p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
     p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
+    p.actmask_in = be.actmask;
     rc = launch_engine(maps, p, KCc, 1, TC_TH, st);
     if (rc) return rc;
   }

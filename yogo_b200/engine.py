@@ -114,8 +114,10 @@ def _out_hw(h: int, w: int, k: int, s: int) -> Tuple[int, int]:
     return (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
 
 
-def _fwd_ep(scale=None, shift=None, act=L.ACT_NONE, dropscale=None, stats=None, preact=None) -> L.FwdEpilogue:
-    return L.FwdEpilogue(L.ptr(scale), L.ptr(shift), act, L.ptr(dropscale), L.ptr(stats), L.ptr(preact))
+def _fwd_ep(scale=None, shift=None, act=L.ACT_NONE, dropscale=None, stats=None, preact=None,
+            actmask=None) -> L.FwdEpilogue:
+    return L.FwdEpilogue(L.ptr(scale), L.ptr(shift), act, L.ptr(dropscale), L.ptr(stats), L.ptr(preact),
+                         L.ptr(actmask))
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -207,8 +209,14 @@ class Runner:
                 pre = None
                 if want_grad and blk.act == L.ACT_SILU:
                     pre = torch.empty_like(out)
-                conv(_fwd_ep(shift=bias, act=blk.act, dropscale=ds, preact=pre), out)
+                mask = None
+                if (want_grad and blk.act == L.ACT_LRELU and not first_direct and blk.cout % 32 == 0
+                        and dt == torch.bfloat16):
+                    # 1 sign bit per element: what the next layer's dgrad epilogue needs of this activation
+                    mask = torch.empty(N * ho * wo * blk.cout // 8, dtype=torch.uint8, device=dev)
+                conv(_fwd_ep(shift=bias, act=blk.act, dropscale=ds, preact=pre, actmask=mask), out)
                 rec["saved"] = pre if pre is not None else out
+                rec["actmask"] = mask
             else:
                 bn = blk.bn
                 g, b = _f32(bn.weight), _f32(bn.bias)
@@ -331,7 +339,8 @@ class Runner:
                 if blk.conv.bias is not None:
                     # the producer of this gradient also accumulates sum(g) per channel = d(bias)
                     sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
-                ep = L.BwdEpilogue(L.ptr(sv), blk.act, L.ptr(rec["dropscale"]), None, None, None, None, L.ptr(sums))
+                ep = L.BwdEpilogue(L.ptr(sv), blk.act, L.ptr(rec["dropscale"]), None, None, None, None, L.ptr(sums),
+                                   L.ptr(rec.get("actmask")))
             return ep, sums
 
         # ---- head
