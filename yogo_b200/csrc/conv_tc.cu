@@ -70,6 +70,9 @@ struct TcParams {
   void* out;
   // forward epilogue
   const float* scale; const float* shift; int act; const float* dropscale; double* stats; void* preact;
+  // prediction head (1x1 conv + YOGO output transform fused into the forward epilogue, see head_fwd_tc)
+  float* head_out; float* head_traw; const float* head_cxs; const float* head_cys;
+  float head_aw, head_ah, head_wm, head_hm; int head_D, head_inf;
   void* actmask_out;        // forward: sign bits of the pre-activation (see yg_fwd_epilogue.actmask)
   const void* actmask_in;   // backward: the producer's sign bits, replaces `saved` for LeakyReLU without BN
   // backward epilogue
@@ -348,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int ir = i % p.OCr;
     if (MODE == 0) {
       s_const[i] = p.scale ? p.scale[ir] : 1.f;
-      s_const[512 + i] = p.shift ? p.shift[ir] : 0.f;
+      s_const[512 + i] = (p.shift && (p.head_D == 0 || i < p.head_D)) ? p.shift[ir] : 0.f;
     } else if (p.bn_scale) {
       s_const[i] = p.bn_scale[ir];
       s_const[512 + i] = p.bn_shift[ir];
@@ -678,7 +681,51 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         tmem_ld_wait();
         __align__(16) bf16 ob[16];
         float s1[16], s2[16];
-        if (MODE == 0) {
+        if (MODE == 0 && p.head_out) {
+          // prediction head: the 16 accumulators of this pixel are the raw logits (5 + classes, zero padded);
+          // /root/reference/yogo/model.py:295-313 applied in registers, written straight to the NCHW fp32 tensor
+          if (valid) {
+            const int D = p.head_D;
+            float t[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(r[i]) + s_k1[i];
+            if (p.head_traw) {
+              float* tr = p.head_traw + pix * D;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < D) tr[i] = t[i];
+            }
+            const int SS = p.OH * p.OW, cell = oh * p.OW + ow;
+            float* o = p.head_out + (long long)n * D * SS + cell;
+            const float cx = p.head_cxs ? p.head_cxs[cell]
+                                        : (p.OW > 1 ? (float)ow * ((1.f - 1.f / (float)p.OW) / (float)(p.OW - 1)) : 0.f);
+            const float cy = p.head_cys ? p.head_cys[cell]
+                                        : (p.OH > 1 ? (float)oh * ((1.f - 1.f / (float)p.OH) / (float)(p.OH - 1)) : 0.f);
+            o[0] = (1.f / (float)p.OW) * sigmoidf_(t[0]) + cx;
+            o[(long long)SS] = (1.f / (float)p.OH) * sigmoidf_(t[1]) + cy;
+            o[2LL * SS] = p.head_aw * expf(fminf(t[2], 80.f)) * p.head_wm;
+            o[3LL * SS] = p.head_ah * expf(fminf(t[3], 80.f)) * p.head_hm;
+            o[4LL * SS] = sigmoidf_(t[4]);
+            if (p.head_inf) {
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 5; i < 16; ++i)
+                if (i < D) mx = fmaxf(mx, t[i]);
+              float se = 0.f;
+#pragma unroll
+              for (int i = 5; i < 16; ++i)
+                if (i < D) { t[i] = expf(t[i] - mx); se += t[i]; }
+              const float inv = 1.f / se;
+#pragma unroll
+              for (int i = 5; i < 16; ++i)
+                if (i < D) o[(long long)i * SS] = t[i] * inv;
+            } else {
+#pragma unroll
+              for (int i = 5; i < 16; ++i)
+                if (i < D) o[(long long)i * SS] = t[i];
+            }
+          }
+        } else if (MODE == 0) {
           __align__(16) bf16 pb[16];
           const bool rnd = p.stats || p.preact;
           {
@@ -1891,6 +1938,80 @@ size_t head_bwd_tc_workspace(int Cin) {
   int nunits, nslices, grid, bnw, nm, nn;
   wgrad_grid(Cin, 32, &nunits, &nslices, &grid, &bnw, &nm, &nn, 1);
   return (size_t)grid * 3 * 128 * bnw * sizeof(float) + 256;
+}
+
+__global__ void pack_head_weights_fwd_kernel(const float* __restrict__ w, bf16* __restrict__ out, int D, int Cin) {
+  // packed [1 tap][N = 16][K = Cin]: rows d >= D are zero
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16 * Cin) return;
+  const int ci = i % Cin, d = i / Cin;
+  out[i] = __float2bfloat16_rn(d < D ? w[(long long)d * Cin + ci] : 0.f);
+}
+
+bool head_fwd_tc_supported(int Cin, int D) { return D <= 16 && Cin % 16 == 0 && Cin >= 16 && Cin <= 512 && pick_kc(Cin) != 0; }
+
+// 1x1 prediction head forward on the tensor cores: one tap, N = 16 (5 + classes zero padded), K = Cin; the YOGO
+// output transform runs in the epilogue (replaces head_fwd_kernel, which is shared-memory-bandwidth bound).
+int head_fwd_tc(const void* x, const float* w, const float* bias, float* out, float* t_raw, int N, int Sy, int Sx, int Cin,
+                int D, float aw, float ah, float wm, float hm, int inference, const float* cxs, const float* cys,
+                cudaStream_t st) {
+  if (!get_encode()) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return YG_ERR_CUDA; }
+  bf16* wp = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pack_mutex);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PackKey key{w, 4, dev};
+    auto it = g_pack_cache.find(key);
+    const size_t need = (size_t)Cin * 16 * sizeof(bf16);
+    if (it == g_pack_cache.end() || it->second.second < need) {
+      void* buf = nullptr;
+      YG_CUDA(cudaMalloc(&buf, need));
+      if (it != g_pack_cache.end()) { cudaFree(it->second.first); it->second = {buf, need}; }
+      else g_pack_cache[key] = {buf, need};
+      wp = (bf16*)buf;
+    } else wp = (bf16*)it->second.first;
+  }
+  pack_head_weights_fwd_kernel<<<cdiv(16LL * Cin, 256), 256, 0, st>>>(w, wp, D, Cin);
+  YG_LAUNCH_CHECK("pack_head_weights_fwd");
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int BN = 16, KCc = pick_kc(Cin);
+  const bf16* xb = (const bf16*)x;
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, 16, 1};
+    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 16 * 2};
+    uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
+    rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Sx, (uint64_t)Sy, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Sx * Cin * 2, (uint64_t)Sy * Sx * Cin * 2};
+    uint32_t box[4] = {(uint32_t)KCc, TC_TW, TC_TH, 1};
+    rc = make_map(&maps.a[0], xb, 4, dims, str, box, KCc);
+    if (rc) return rc;
+    for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+    for (int i = 0; i < 4; ++i) p.src[i] = TcSrc{xb, Sx, Sy, (long long)Cin, (long long)Sx * Cin, (long long)Sy * Sx * Cin};
+  }
+  TcGroup& g = p.g[0];
+  g.map = 0; g.dh = 0; g.dw = 0; g.rows = TC_TH; g.ntaps = 1; g.ro[0] = 0; g.widx[0] = 0; g.kmask[0] = 0xFFFFFFFFu;
+  p.ncls = 1;
+  p.cls[0] = TcClass{0, 1, 1, Sy, Sx, 0, 0};
+  p.osh = p.osw = 1;
+  p.N = N;
+  p.tiles_h = cdiv(Sy, TC_TH); p.tiles_w = cdiv(Sx, TC_TW);
+  p.n_ntiles = 1;
+  p.total_tiles = N * p.tiles_h * p.tiles_w;
+  p.OH = Sy; p.OW = Sx; p.OC = 16; p.OCr = 16;
+  p.BN = BN; p.kchunks = Cin / KCc; p.ntaps_total = 1;
+  p.shift = bias;
+  p.head_out = out; p.head_traw = t_raw; p.head_cxs = cxs; p.head_cys = cys;
+  p.head_aw = aw; p.head_ah = ah; p.head_wm = wm; p.head_hm = hm; p.head_D = D; p.head_inf = inference;
+  return launch_engine(maps, p, KCc, 0, TC_TH, st);
 }
 
 int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* dw, int N, int Sy, int Sx, int Cin, int D,

@@ -361,6 +361,10 @@ constexpr int HD_DT_BLOCKS = 592;
 
 // conv_tc.cu
 bool head_bwd_tc_supported(int Cin, int D);
+bool head_fwd_tc_supported(int Cin, int D);
+int head_fwd_tc(const void* x, const float* w, const float* bias, float* out, float* t_raw, int N, int Sy, int Sx, int Cin,
+                int D, float aw, float ah, float wm, float hm, int inference, const float* cxs, const float* cys,
+                cudaStream_t st);
 size_t head_bwd_tc_workspace(int Cin);
 int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* dw, int N, int Sy, int Sx, int Cin, int D,
                 const BwdEpi& be, float clip, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -429,6 +433,9 @@ extern "C" int yg_head_fwd(const void* x, int dtype, const float* w, const float
   YG_CHECK_ARG(dtype == YG_F32 || dtype == YG_BF16, "head_fwd: dtype %d", dtype);
   const long long npix = (long long)N * Sy * Sx;
   if (npix == 0) return YG_OK;
+  if (dtype == YG_BF16 && yg_get_conv_impl() != YG_IMPL_SIMT && head_fwd_tc_supported(Cin, D))
+    return head_fwd_tc(x, w, bias, out, t_raw, N, Sy, Sx, Cin, D, anchor_w, anchor_h, width_mult, height_mult, inference,
+                       cxs, cys, (cudaStream_t)stream);
   const size_t smem = ((size_t)D * Cin + (size_t)HD_KC * (HD_PX + 1)) * sizeof(float);
   YG_CHECK_ARG(smem <= 200 * 1024, "head_fwd: Cin %d too large", Cin);
   const int blocks = cdiv(npix, HD_PX);
