@@ -249,6 +249,278 @@ __global__ void wgrad_reduce_kernel2(const float* __restrict__ partial, float* _
   else if (dbias) dbias[i - nw] = s;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path for the configuration every YOGO model uses: one input channel, 16 output channels, bf16
+// activations.  Same arithmetic as the generic kernels above, restructured so that the instruction stream
+// is dominated by the 9x16 FMAs instead of index arithmetic (the generic kernels spend ~950 instructions
+// per pixel and 8-channel chunk, mostly 64-bit div/mod, bounds checks and reloading the 9 taps):
+//   * work = (image, contiguous pixel chunk) tasks, (ho, wo) advanced incrementally - no per-pixel division
+//   * one thread owns all 16 channels of a pixel; the 9 taps are loaded once and shared by the stencil
+//     recomputation and the weight-gradient accumulation
+//   * weights / per-channel constants are read as 128-bit shared-memory broadcasts
+// ------------------------------------------------------------------------------------------------
+constexpr int FF_CO = 16;
+
+struct PixCursor {
+  int p, ho, wo;
+  __device__ __forceinline__ void init(int p0, int Wo) { p = p0; ho = p0 / Wo; wo = p0 - ho * Wo; }
+  __device__ __forceinline__ void advance(int step, int Wo) {
+    p += step; wo += step;
+    while (wo >= Wo) { wo -= Wo; ++ho; }
+  }
+};
+
+template <typename TX>
+__device__ __forceinline__ void load_taps1(const TX* __restrict__ xim, int H, int W, int stride, int ho, int wo,
+                                           float (&v)[9]) {
+  const int ih0 = ho * stride - 1, iw0 = wo * stride - 1;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ih = ih0 + r;
+    const bool rok = (unsigned)ih < (unsigned)H;
+    const TX* row = xim + ih * W;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int iw = iw0 + s;
+      v[r * 3 + s] = (rok && (unsigned)iw < (unsigned)W) ? to_f<TX>(__ldg(row + iw)) : 0.f;
+    }
+  }
+}
+
+// acc[c] = sum_t v[t] * ws[t][c], ws in shared memory as [9][16]
+__device__ __forceinline__ void stencil16(const float* ws, const float (&v)[9], float (&acc)[FF_CO]) {
+#pragma unroll
+  for (int c = 0; c < FF_CO; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4* w4 = reinterpret_cast<const float4*>(ws + t * FF_CO);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 q = w4[i];
+      acc[4 * i] += v[t] * q.x; acc[4 * i + 1] += v[t] * q.y; acc[4 * i + 2] += v[t] * q.z; acc[4 * i + 3] += v[t] * q.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void lds16(const float* s, float (&o)[FF_CO]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 q = reinterpret_cast<const float4*>(s)[i];
+    o[4 * i] = q.x; o[4 * i + 1] = q.y; o[4 * i + 2] = q.z; o[4 * i + 3] = q.w;
+  }
+}
+
+template <typename TX, bool STATS>
+__global__ void __launch_bounds__(FL_THREADS, 3) first_fwd16_kernel(
+    const TX* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int H, int W, int Ho, int Wo,
+    int stride, FwdEpi ep, int chunk, int cpi, int ntasks) {
+  __shared__ __align__(16) float ws[9 * FF_CO];
+  __shared__ __align__(16) float s_ds[FF_CO];
+  __shared__ float ssum[2 * FF_CO];
+  for (int i = threadIdx.x; i < 9 * FF_CO; i += FL_THREADS) ws[i] = w[(i % FF_CO) * 9 + i / FF_CO];
+  if (threadIdx.x < 2 * FF_CO) ssum[threadIdx.x] = 0.f;
+  if (threadIdx.x < FF_CO) s_ds[threadIdx.x] = 1.f;
+  float sc[FF_CO], sh[FF_CO];
+#pragma unroll
+  for (int c = 0; c < FF_CO; ++c) { sc[c] = ep.scale ? ep.scale[c] : 1.f; sh[c] = ep.shift ? ep.shift[c] : 0.f; }
+  float s1[STATS ? FF_CO : 1], s2[STATS ? FF_CO : 1];
+#pragma unroll
+  for (int c = 0; c < (STATS ? FF_CO : 1); ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+  __syncthreads();
+  const int npix = Ho * Wo, act = ep.act;
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
+    const int p1 = min(p0 + chunk, npix);
+    if (ep.dropscale) {
+      __syncthreads();
+      if (threadIdx.x < FF_CO) s_ds[threadIdx.x] = ep.dropscale[(long long)n * FF_CO + threadIdx.x];
+      __syncthreads();
+    }
+    const TX* xim = x + (long long)n * H * W;
+    bf16* yim = y ? y + (long long)n * npix * FF_CO : nullptr;
+    PixCursor cur;
+    cur.init(p0 + (int)threadIdx.x, Wo);
+    for (; cur.p < p1; cur.advance(FL_THREADS, Wo)) {
+      float v[9], acc[FF_CO];
+      load_taps1<TX>(xim, H, W, stride, cur.ho, cur.wo, v);
+      stencil16(ws, v, acc);
+#pragma unroll
+      for (int c = 0; c < FF_CO; ++c) {
+        acc[c] = acc[c] * sc[c] + sh[c];
+        if (STATS) { s1[c] += acc[c]; s2[c] += acc[c] * acc[c]; }
+      }
+      if (yim) {
+        if (act == YG_ACT_LRELU) {
+#pragma unroll
+          for (int c = 0; c < FF_CO; ++c) acc[c] = fmaxf(acc[c], 0.01f * acc[c]);
+        } else if (act == YG_ACT_SILU) {
+#pragma unroll
+          for (int c = 0; c < FF_CO; ++c) acc[c] = acc[c] * sigmoidf_(acc[c]);
+        }
+        if (ep.dropscale) {
+          float ds[FF_CO];
+          lds16(s_ds, ds);
+#pragma unroll
+          for (int c = 0; c < FF_CO; ++c) acc[c] *= ds[c];
+        }
+        __align__(16) __nv_bfloat162 ob[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ob[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+        uint4* dst = reinterpret_cast<uint4*>(yim + (long long)cur.p * FF_CO);
+        dst[0] = reinterpret_cast<uint4*>(ob)[0];
+        dst[1] = reinterpret_cast<uint4*>(ob)[1];
+      }
+    }
+  }
+  if (STATS) {
+#pragma unroll
+    for (int c = 0; c < (STATS ? FF_CO : 1); ++c) {
+      const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&ssum[c], a); atomicAdd(&ssum[FF_CO + c], b); }
+    }
+    __syncthreads();
+    if (threadIdx.x < FF_CO) {
+      atomicAdd(&ep.stats[threadIdx.x], (double)ssum[threadIdx.x]);
+      atomicAdd(&ep.stats[FF_CO + threadIdx.x], (double)ssum[FF_CO + threadIdx.x]);
+    }
+  }
+}
+
+// weight-gradient pass (mode 1 of conv_first_bwd_kernel): CO of the 16 channels per thread, blockIdx.y selects the
+// channel group (CO = 8: 72 + 72 FMAs per pixel at ~128 registers, four blocks per SM)
+template <int CO>
+__device__ __forceinline__ void ldsN(const float* s, float (&o)[CO]) {
+#pragma unroll
+  for (int i = 0; i < CO / 4; ++i) {
+    const float4 q = reinterpret_cast<const float4*>(s)[i];
+    o[4 * i] = q.x; o[4 * i + 1] = q.y; o[4 * i + 2] = q.z; o[4 * i + 3] = q.w;
+  }
+}
+
+template <typename TX, int CO>
+__global__ void __launch_bounds__(FL_THREADS, CO == 8 ? 3 : 2) first_bwd16_kernel(
+    const TX* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ da, int H, int W, int Ho, int Wo,
+    int stride, BwdEpi be, const float* __restrict__ fwd_shift, const float* __restrict__ dy_mean,
+    const float* __restrict__ dyx_mean, float* __restrict__ partial, int chunk, int cpi, int ntasks) {
+  __shared__ __align__(16) float ws[9 * CO];
+  __shared__ __align__(16) float cst[8 * CO];   // scl, sft, mean, istd, m1, m2, fsh, ds
+  __shared__ float red[10 * CO];
+  const int co0 = blockIdx.y * CO;
+  for (int i = threadIdx.x; i < 9 * CO; i += FL_THREADS) ws[i] = w[(co0 + i % CO) * 9 + i / CO];
+  for (int i = threadIdx.x; i < 10 * CO; i += FL_THREADS) red[i] = 0.f;
+  if (threadIdx.x < CO) {
+    const int c = threadIdx.x, co = co0 + c;
+    cst[c] = be.bn_scale ? be.bn_scale[co] : 1.f;
+    cst[CO + c] = be.bn_shift ? be.bn_shift[co] : 0.f;
+    cst[2 * CO + c] = be.bn_mean ? be.bn_mean[co] : 0.f;
+    cst[3 * CO + c] = be.bn_invstd ? be.bn_invstd[co] : 1.f;
+    cst[4 * CO + c] = dy_mean ? dy_mean[co] : 0.f;
+    cst[5 * CO + c] = dyx_mean ? dyx_mean[co] : 0.f;
+    cst[6 * CO + c] = fwd_shift ? fwd_shift[co] : 0.f;
+    cst[7 * CO + c] = 1.f;
+  }
+  float wacc[9][CO], s1[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    s1[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wacc[t][c] = 0.f;
+  }
+  __syncthreads();
+  const int npix = Ho * Wo, act = be.act;
+  const bool bn = be.bn_scale != nullptr, bn_full = bn && dy_mean != nullptr;
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
+    const int p1 = min(p0 + chunk, npix);
+    if (be.dropscale) {
+      __syncthreads();
+      if (threadIdx.x < CO) cst[7 * CO + threadIdx.x] = be.dropscale[(long long)n * FF_CO + co0 + threadIdx.x];
+      __syncthreads();
+    }
+    const TX* xim = x + (long long)n * H * W;
+    const bf16* dim = da + (long long)n * npix * FF_CO + co0;
+    PixCursor cur;
+    cur.init(p0 + (int)threadIdx.x, Wo);
+    for (; cur.p < p1; cur.advance(FL_THREADS, Wo)) {
+      float v[9], acc[CO], g[CO];
+      const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)cur.p * FF_CO);
+      uint4 gv[CO / 8];
+#pragma unroll
+      for (int i = 0; i < CO / 8; ++i) gv[i] = __ldg(gp + i);
+      load_taps1<TX>(xim, H, W, stride, cur.ho, cur.wo, v);
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float wr[CO];
+        ldsN<CO>(ws + t * CO, wr);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] += v[t] * wr[c];
+      }
+#pragma unroll
+      for (int i = 0; i < CO / 8; ++i) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&gv[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __bfloat1622float2(h[j]);
+          g[8 * i + 2 * j] = a.x; g[8 * i + 2 * j + 1] = a.y;
+        }
+      }
+      float k0[CO], k1[CO];
+      ldsN<CO>(cst + 6 * CO, k0);   // forward shift (conv bias when there is no BN)
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc[c] += k0[c];          // yv
+      if (be.dropscale) {
+        ldsN<CO>(cst + 7 * CO, k0);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) g[c] *= k0[c];
+      }
+      if (bn) {
+        ldsN<CO>(cst, k0); ldsN<CO>(cst + CO, k1);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) g[c] *= act_grad(acc[c] * k0[c] + k1[c], act);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CO; ++c) g[c] *= act_grad(acc[c], act);
+      }
+      if (bn_full) {
+        // BN backward: dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
+        ldsN<CO>(cst + 2 * CO, k0); ldsN<CO>(cst + 3 * CO, k1);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] = (acc[c] - k0[c]) * k1[c];   // xhat
+        ldsN<CO>(cst + 4 * CO, k0); ldsN<CO>(cst + 5 * CO, k1);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) g[c] = g[c] - k0[c] - acc[c] * k1[c];
+        ldsN<CO>(cst, k0);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) g[c] *= k0[c];
+      }
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        s1[c] += g[c];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wacc[t][c] += g[c] * v[t];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    const float a = warp_sum(s1[c]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[9 * CO + c], a);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float b = warp_sum(wacc[t][c]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&red[c * 9 + t], b);
+    }
+  }
+  __syncthreads();
+  // partial layout per slice (= blockIdx.x): [16][1][9] then [16] (what wgrad_reduce_kernel2 sums)
+  float* base = partial + (long long)blockIdx.x * (10 * FF_CO);
+  for (int i = threadIdx.x; i < 9 * CO; i += FL_THREADS) base[co0 * 9 + i] = red[i];
+  if (threadIdx.x < CO) base[9 * FF_CO + co0 + threadIdx.x] = red[9 * CO + threadIdx.x];
+}
+
 constexpr int FL_BWD_BLOCKS = 592;
 
 }  // namespace yg
@@ -266,10 +538,21 @@ extern "C" int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, voi
   if (N == 0) return YG_OK;
   FwdEpi ep = make_fwd_epi(epp);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 1 && Cout == FF_CO && dtype == YG_BF16 && !ep.preact && (long long)Ho * Wo < (1LL << 30) &&
+      (long long)H * W < (1LL << 31)) {
+    const int chunk = 16 * FL_THREADS, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
+    const int grid1 = ntasks < 148 * 3 ? ntasks : 148 * 3;
+#define LAUNCHF(TX, ST) first_fwd16_kernel<TX, ST><<<grid1, FL_THREADS, 0, st>>>((const TX*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunk, cpi, ntasks)
+    if (x_dtype == YG_U8) { if (ep.stats) LAUNCHF(uint8_t, true); else LAUNCHF(uint8_t, false); }
+    else { if (ep.stats) LAUNCHF(float, true); else LAUNCHF(float, false); }
+#undef LAUNCHF
+    YG_LAUNCH_CHECK("conv_first_fwd16");
+    return YG_OK;
+  }
   long long nblk = ((long long)N * Ho * Wo + FL_THREADS - 1) / FL_THREADS;
   if (nblk > 148 * 16) nblk = 148 * 16;
   dim3 grid((unsigned)nblk, cdiv(Cout, FL_CO), 1);
-  cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(TX, T) conv_first_fwd_kernel<TX, T><<<grid, FL_THREADS, 0, st>>>((const TX*)x, w, (T*)y, N, H, W, Cin, Ho, Wo, Cout, stride, ep)
   if (x_dtype == YG_U8) { if (dtype == YG_BF16) LAUNCH(uint8_t, bf16); else LAUNCH(uint8_t, float); }
   else { if (dtype == YG_BF16) LAUNCH(float, bf16); else LAUNCH(float, float); }
@@ -305,6 +588,22 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
       return YG_ERR_WORKSPACE;
     }
   }
+  if (mode == 1 && Cin == 1 && Cout == FF_CO && dtype == YG_BF16 && (long long)Ho * Wo < (1LL << 30) &&
+      (long long)H * W < (1LL << 31)) {
+    const int chunk = 32 * FL_THREADS, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
+    const int grid1 = ntasks < 222 ? ntasks : 222;   // x 2 channel groups = one wave of 3 blocks per SM; <= FL_BWD_BLOCKS slices
+    const dim3 gridf(grid1, 2, 1);
+    if (x_dtype == YG_U8)
+      first_bwd16_kernel<uint8_t, 8><<<gridf, FL_THREADS, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be,
+                                                                   fwd_shift, bn_dy_mean, bn_dyx_mean, (float*)workspace, chunk, cpi, ntasks);
+    else
+      first_bwd16_kernel<float, 8><<<gridf, FL_THREADS, 0, st>>>((const float*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be,
+                                                                 fwd_shift, bn_dy_mean, bn_dyx_mean, (float*)workspace, chunk, cpi, ntasks);
+    YG_LAUNCH_CHECK("conv_first_bwd16");
+    wgrad_reduce_kernel2<<<cdiv(nw + Cout, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, grid1, clip);
+    YG_LAUNCH_CHECK("conv_first_bwd reduce");
+    return YG_OK;
+  }
   dim3 grid(blocks, nchunks * (mode == 1 ? Cin : 1), 1);
 #define LAUNCH(TX, T, M) conv_first_bwd_kernel<TX, T, M><<<grid, FL_THREADS, 0, st>>>((const TX*)x, w, (const T*)da, N, H, W, Cin, Ho, Wo, Cout, stride, be, fwd_shift, bn_dy_mean, bn_dyx_mean, (float*)workspace, nchunks)
 #define LAUNCH_M(TX, T) do { if (mode == 1) LAUNCH(TX, T, 1); else LAUNCH(TX, T, 0); } while (0)
@@ -339,34 +638,31 @@ constexpr int GR_THREADS = 256;
 
 template <typename TX>
 __global__ void __launch_bounds__(GR_THREADS) first_gram_kernel(const TX* __restrict__ x, int N, int H, int W,
-                                                                int Ho, int Wo, int stride, double* __restrict__ gram) {
+                                                                int Ho, int Wo, int stride, double* __restrict__ gram,
+                                                                int chunk, int cpi, int ntasks) {
   float S[9], G[45];
 #pragma unroll
   for (int i = 0; i < 9; ++i) S[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < 45; ++i) G[i] = 0.f;
-  const long long total = (long long)N * Ho * Wo;
-  for (long long q = (long long)blockIdx.x * GR_THREADS + threadIdx.x; q < total; q += (long long)gridDim.x * GR_THREADS) {
-    const int n = (int)(q / ((long long)Ho * Wo));
-    const int p = (int)(q % ((long long)Ho * Wo));
-    const int ho = p / Wo, wo = p % Wo;
-    const TX* xp = x + (long long)n * H * W;
-    float v[9];
+  const int npix = Ho * Wo;
+  // (image, pixel chunk) tasks with an incrementally advanced (ho, wo): no per-pixel division
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
+    const int p1 = min(p0 + chunk, npix);
+    const TX* xim = x + (long long)n * H * W;
+    PixCursor cur;
+    cur.init(p0 + (int)threadIdx.x, Wo);
+    for (; cur.p < p1; cur.advance(GR_THREADS, Wo)) {
+      float v[9];
+      load_taps1<TX>(xim, H, W, stride, cur.ho, cur.wo, v);
+      int k = 0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int ih = ho * stride - 1 + r;
+      for (int a = 0; a < 9; ++a) {
+        S[a] += v[a];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int iw = wo * stride - 1 + s;
-        v[r * 3 + s] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? to_f<TX>(xp[(long long)ih * W + iw]) : 0.f;
+        for (int b = a; b < 9; ++b) G[k++] += v[a] * v[b];
       }
-    }
-    int k = 0;
-#pragma unroll
-    for (int a = 0; a < 9; ++a) {
-      S[a] += v[a];
-#pragma unroll
-      for (int b = a; b < 9; ++b) G[k++] += v[a] * v[b];
     }
   }
   __shared__ double red[54];
@@ -453,12 +749,13 @@ extern "C" int yg_conv_first_gram(const void* x, int x_dtype, int N, int H, int 
   YG_CUDA(cudaMemsetAsync(gram, 0, 54 * sizeof(double), st));
   if (N == 0) return YG_OK;
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  long long nblk = ((long long)N * Ho * Wo + GR_THREADS - 1) / GR_THREADS;
-  if (nblk > 148 * 4) nblk = 148 * 4;
+  YG_CHECK_ARG((long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31), "conv_first_gram: image too large");
+  const int chunk = 32 * GR_THREADS, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
+  const int nblk = ntasks < 148 * 4 ? ntasks : 148 * 4;
   if (x_dtype == YG_U8)
-    first_gram_kernel<uint8_t><<<(unsigned)nblk, GR_THREADS, 0, st>>>((const uint8_t*)x, N, H, W, Ho, Wo, stride, gram);
+    first_gram_kernel<uint8_t><<<nblk, GR_THREADS, 0, st>>>((const uint8_t*)x, N, H, W, Ho, Wo, stride, gram, chunk, cpi, ntasks);
   else
-    first_gram_kernel<float><<<(unsigned)nblk, GR_THREADS, 0, st>>>((const float*)x, N, H, W, Ho, Wo, stride, gram);
+    first_gram_kernel<float><<<nblk, GR_THREADS, 0, st>>>((const float*)x, N, H, W, Ho, Wo, stride, gram, chunk, cpi, ntasks);
   YG_LAUNCH_CHECK("first_gram");
   return YG_OK;
 }
