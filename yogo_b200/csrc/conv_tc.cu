@@ -1097,6 +1097,8 @@ struct TwParams {
   TcSrc asrc;        // dz as seen by the cp.async producer
   TcSrc bsrc[4];     // x (or its parity sub-grids)
   float* partial;
+  int do_bias;          // also accumulate d(bias)[co] = sum over pixels of dz: one extra N = 16 MMA per K step against
+  float* bias_partial;  // a block of ones (units with s == 0, nt == 0); partials [slice][mtile][128]
   int* error_flag;
 };
 
@@ -1128,6 +1130,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* done_bar = empty_bar + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 2);
+  unsigned char* ones = tail + 1024;   // 16 pixel rows x ROWB bytes of bf16 1.0 (B operand of the bias column)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably uniform
   const int unit = blockIdx.x % p.nunits, slice = blockIdx.x / p.nunits;
@@ -1150,12 +1153,17 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
       for (int i = threadIdx.x; i < n16; i += NTHREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
   }
+  if (p.do_bias)
+    for (int i = threadIdx.x; i < 512; i += NTHREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == PW) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the bias column of a pixel tile is taken by one of the units that share this M tile, round robin over the tiles
+  const bool do_bias = p.do_bias != 0;
+  const int bias_period = p.ncols * p.n_ntiles, bias_phase = sg + p.ncols * nt;
 
   if (warp < PW) {
     if (PROD == 0) {
@@ -1274,8 +1282,14 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     const uint32_t b_lo0 = (uint32_t)bd_base, b_hi = (uint32_t)(bd_base >> 32);
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     const int nstages = p.nstages, ngroups = p.ngroups;
+    const uint32_t ones_lo = (uint32_t)umma_desc_mn(smem_u32(ones), (uint32_t)p.b_block_bytes, 8 * ROWB, LAYOUT_B);
+    const uint32_t idesc_bias = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t bias_started = 0;
     const uint32_t leader = elect_one();   // whole warp runs the loop, the elected lane issues
+    int bias_it = 0;
     for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
+      const bool bias_tile = do_bias && bias_it == bias_phase;
+      if (++bias_it == bias_period) bias_it = 0;
       for (int gi = 0; gi < ngroups; ++gi) {
         const TwGroup& g = p.g[sg][gi];
         mbar_wait(&full_bar[stage], phase, p.error_flag, 13);
@@ -1283,6 +1297,14 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
         const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units;
         const uint32_t b_lo_s = b_lo0 + (uint32_t)stage * stage_units;
         const int ntaps = g.ntaps;
+        if (bias_tile && gi == 0) {
+          // d(bias) column: dz^T . ones, once per pixel tile
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_lh2_p(tmem_base + (uint32_t)(3 * BNW), a_lo + (uint32_t)k * ROWA, a_hi, ones_lo, b_hi, idesc_bias,
+                            (k > 0 ? 1u : bias_started), leader);
+          bias_started = 1u;
+        }
         for (int tp = 0; tp < ntaps; ++tp) {
           const int slot = g.slot[tp];
           const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BNW);
@@ -1308,6 +1330,17 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     tc_fence_after();
     const bool any_tile = slice < p.total_tiles;
     float* dst = p.partial + ((size_t)blockIdx.x * 3) * 128 * BNW;
+    if (do_bias) {
+      uint32_t v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0u;
+      // this unit took tiles slice + (bias_phase + k * bias_period) * nslices: at least one exists iff the first does
+      if (slice + (long long)bias_phase * p.nslices < p.total_tiles) {
+        tmem_ld16(tmem_base + (uint32_t)(3 * BNW) + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+      }
+      p.bias_partial[(size_t)blockIdx.x * 128 + row] = __uint_as_float(v[0]);
+    }
     for (int r = 0; r < 3; ++r) {
       for (int j = 0; j < BNW / 16; ++j) {
         uint32_t v[16];
@@ -1330,6 +1363,23 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   __syncthreads();
   tc_fence_after();
   if (warp == PW) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// d(bias)[co] = sum over the CTAs that share the M tile and over the W-fold sub-pixels q of the bias-column
+// partials [cta][128]  (cta = unit + nunits * slice, unit = s + ncols * (mtile + n_mtiles * ntile))
+__global__ void wgrad_bias_reduce_kernel(const float* __restrict__ part, float* __restrict__ dbias, int Cout, int g,
+                                         int ncols, int n_mtiles, int nunits, int grid, float clip) {
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= Cout) return;
+  float acc = 0.f;
+  for (int b = 0; b < grid; ++b) {
+    const int mt = ((b % nunits) / ncols) % n_mtiles;
+    for (int q = 0; q < g; ++q) {
+      const int cof = q * Cout + co;
+      if (cof / 128 == mt) acc += part[(size_t)b * 128 + cof % 128];
+    }
+  }
+  dbias[co] = clampf(acc, clip);
 }
 
 // Sums the per-CTA partials in a fixed order.  The kernel ran on (possibly W-folded) dimensions Coutf = g*Cout,
@@ -1451,9 +1501,13 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   if (nst > 6) nst = 6;
   if (nst < 2) { set_error("conv_wgrad_tc: stage of %d bytes does not fit twice", p.stage_bytes); return YG_ERR_INVALID; }
   p.nstages = nst;
+  // the bias column needs 16 more TMEM columns; without room for them the column sums come from a separate pass
+  const bool bias_col = dbias != nullptr && 3 * p.BNW + 16 <= 512;
   int cols = 32;
-  while (cols < 3 * p.BNW) cols <<= 1;
+  while (cols < 3 * p.BNW + (bias_col ? 16 : 0)) cols <<= 1;
   p.tmem_cols = cols;
+  p.do_bias = bias_col ? 1 : 0;
+  p.bias_partial = (float*)((char*)ws + (size_t)grid * 3 * 128 * p.BNW * sizeof(float));
   int rc;
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
@@ -1509,7 +1563,7 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
     YG_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   }
   p.error_flag = g_error_flag;
-  const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 512;
+  const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 1024 + 2048;   // align slack, barriers, ones block
 const int prodw = (kb <= 32 && nst >= 3 && (g_tc_options & 2)) ? 1 : 0;
 #define TW_LAUNCH(KBV, KAV, PRODV)                                                                                       \
   do {                                                                                                                   \
@@ -1531,7 +1585,10 @@ const int prodw = (kb <= 32 && nst >= 3 && (g_tc_options & 2)) ? 1 : 0;
   wgrad_tc_reduce_kernel<<<cdiv(nw, 256), 256, 0, st>>>((const float*)ws, dw, Cout_r, Cin_r, fg, p.BNW, p.n_mtiles,
                                                         p.nunits, p.nslices, clip);
   YG_LAUNCH_CHECK("wgrad_tc_reduce");
-  if (dbias) {
+  if (bias_col) {
+    wgrad_bias_reduce_kernel<<<cdiv(Cout_r, 128), 128, 0, st>>>(p.bias_partial, dbias, Cout_r, fg, p.ncols, p.n_mtiles, p.nunits, grid, clip);
+    YG_LAUNCH_CHECK("wgrad_bias_reduce");
+  } else if (dbias) {
     float* part = (float*)((char*)ws + (size_t)grid * 3 * 128 * p.BNW * sizeof(float));
     const long long npix = (long long)N * Ho * Wo_r;   // the bias gradient is taken on the real (unfolded) view
     const int nblk = (int)(npix < COLSUM_BLOCKS ? npix : COLSUM_BLOCKS);
@@ -2127,7 +2184,7 @@ int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* 
     g.map = 0; g.dh = 0; g.dw = 0; g.rows = TC_TH; g.ntaps = 1; g.ro[0] = 0; g.slot[0] = 0;
     p.partial = (float*)ws;
     p.error_flag = g_error_flag;
-    const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 512;
+    const size_t smem = (size_t)nst * p.stage_bytes + 1024 + 1024 + 2048;
 #define HW_LAUNCH(KBV)                                                                                                 \
   do {                                                                                                                 \
     YG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KBV, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -336,9 +336,7 @@ class Runner:
                                    rec["invstd"].data_ptr(), sums.data_ptr())
             else:
                 sv = rec["saved"] if blk.act != L.ACT_NONE else None
-                if blk.conv.bias is not None:
-                    # the producer of this gradient also accumulates sum(g) per channel = d(bias)
-                    sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                # d(bias) of this block comes from its own wgrad call (a ones column in the tcgen05 kernel)
                 ep = L.BwdEpilogue(L.ptr(sv), blk.act, L.ptr(rec["dropscale"]), None, None, None, None, L.ptr(sums),
                                    L.ptr(rec.get("actmask")))
             return ep, sums
@@ -446,11 +444,6 @@ class Runner:
                 grads[id(blk.bn.bias)] = dbet
             # g is now d(loss)/d(conv output of block i)
             db_from_wgrad = db
-            if blk.bn is None and db is not None:
-                # d(bias) = per-channel sum of g, already accumulated by the kernel that produced g
-                L.check(lib.yg_bn_bwd_apply(None, None, dcode, N, ho * wo, blk.cout, sums.data_ptr(), None, None, None,
-                                            None, db.data_ptr(), clip, 0, st))
-                db_from_wgrad = None
             nb = lib.yg_conv_wgrad_workspace(N, h, w, blk.cin, blk.cout, blk.ksize, blk.stride)
             ws = L.workspace.get("wgrad", nb, dev)
             L.check(lib.yg_conv_wgrad(rec["in"].data_ptr(), g.data_ptr(), dw.data_ptr(), L.ptr(db_from_wgrad), dcode, N, h, w,
