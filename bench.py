@@ -257,11 +257,11 @@ def run_ours(args):
     roof = None
     # every rank runs the instrumented steps (they contain collectives); rank 0 reports them
     saved_graph, trainer._graph = trainer._graph, None  # the breakdown needs individual launches
-    breakdown = kernel_breakdown(trainer, dev_imgs, dev_labs, args, L)
+    breakdown, calls_per_step = kernel_breakdown(trainer, dev_imgs, dev_labs, args, L)
     trainer._graph = saved_graph
     barrier()
     if rank == 0:
-        roof = roofline_from_breakdown(breakdown, args, B)
+        roof = roofline_from_breakdown(breakdown, calls_per_step, args, B)
 
     if rank == 0:
         cpu = None
@@ -337,10 +337,23 @@ def kernel_breakdown(trainer, dev_imgs, dev_labs, args, L):
         d = agg.setdefault(key, [0.0, 0])
         d[0] += e0.elapsed_time(e1) / steps
         d[1] += 1
-    return {k: round(v[0], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    ordered = sorted(agg.items(), key=lambda kv: -kv[1][0])
+    return ({k: round(v[0], 4) for k, v in ordered}, {k: v[1] / steps for k, v in ordered})
 
 
-def roofline_from_breakdown(breakdown, args, B):
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum), or None when that kernel has not been captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            ent = json.load(f).get(kernel)
+        return float(ent["dram_bytes_per_launch"]) if ent else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def roofline_from_breakdown(breakdown, calls_per_step, args, B):
     """roofline of the dominant kernel (largest share of the step).  Convolutions are judged against the roof that
     binds them: arithmetic intensity (FLOP per algorithmic byte) above the machine balance -> tensor, else HBM
     (base_model layers 2, 3 are HBM-bound, 4-7 tensor-bound)."""
@@ -348,6 +361,8 @@ def roofline_from_breakdown(breakdown, args, B):
     if not breakdown:
         return None
     top, ms = next(iter(breakdown.items()))
+    ms = ms / max(calls_per_step.get(top, 1.0), 1.0)   # the breakdown sums same-shaped layers: per launch here
+    traffic = measured_traffic(top)
     if top.startswith(("yg_conv_fwd[", "yg_conv_dgrad[", "yg_conv_wgrad[")):
         dims = [int(v) for v in top[top.index("[") + 1:-1].split("x")]
         N, Hh, Ww, Cin, Cout, k, s = dims
@@ -363,15 +378,15 @@ def roofline_from_breakdown(breakdown, args, B):
         if flops / nbytes >= balance:
             ach = flops / (ms * 1e-3) / 1e12
             return {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
                     "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
                     "ms_per_launch": ms, "algorithmic_flops": flops}
         ach = nbytes / (ms * 1e-3) / 1e9
         return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"] + " (copy bandwidth)",
                 "ms_per_launch": ms, "algorithmic_bytes": nbytes, "flop_per_byte": flops / nbytes}
     return {"kernel": top, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
-            "traffic": None, "ms_per_launch": ms, "peak_source": peaks["source"]}
+            "traffic": traffic, "ms_per_launch": ms, "peak_source": peaks["source"]}
 
 
 def main():

@@ -91,13 +91,16 @@ def main():
                    "frac_bf16_peak": round(tf / peaks["bf16_tflops"], 3), "min_GBps": round(act_bytes / ms / 1e6, 1)}
             if (args.tc_options >> 11) & 1 and name != "wgrad":
                 import numpy as np
-                buf = np.zeros(148 * 8, dtype=np.uint64)
+                buf = np.zeros(148 * 16, dtype=np.uint64)
                 L.check(lib.yg_tc_debug_read(buf.ctypes.data, buf.size))
-                d = buf.reshape(148, 8).astype(np.float64)
+                d = buf.reshape(148, 16).astype(np.float64)
                 items = max(d[:, 5].mean(), 1.0)
                 rec["mma_warp_cycles_per_item"] = {k: round(float(d[:, i].mean() / items), 1)
                                                    for i, k in enumerate(["wait_tempty", "wait_full", "issue", "commit", "rest"])}
                 rec["items_per_cta"] = items
+                tiles = max(d[:, 14].mean(), 1.0)
+                rec["epi_warp_cycles_per_tile"] = {k: round(float(d[:, 8 + i].mean() / tiles), 1)
+                                                   for i, k in enumerate(["wait_tfull", "ld_wait", "pre", "math", "store", "rest"])}
             print(json.dumps(rec), flush=True)
             out.append(rec)
 

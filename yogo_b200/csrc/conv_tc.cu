@@ -92,7 +92,7 @@ struct TcParams {
 };
 
 // cycle counters of the MMA warp, one row of 8 per CTA (debug bit 16): wait tempty, wait full, issue, commit, rest
-__device__ unsigned long long g_tc_dbg[256 * 8];
+__device__ unsigned long long g_tc_dbg[256 * 16];   // per CTA: 0-5 MMA warp, 8-13 first epilogue warp
 
 // Output-parity class of a tile.  Sibling classes of one spatial tile are neighbours in the tile order (they
 // share dz and saved-activation lines in L2); the class of slot c rotates with the spatial index so that a
@@ -258,6 +258,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// wait for the TMEM loads AND tie the destination registers to the wait, so that no use of them can be scheduled
+// above it (the loads complete asynchronously; plain register reads have no other dependency on the wait)
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -551,7 +559,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
     if (prof && lane == 0 && blockIdx.x < 256) {
-      unsigned long long* d = g_tc_dbg + blockIdx.x * 8;
+      unsigned long long* d = g_tc_dbg + blockIdx.x * 16;
       d[0] = c_tempty; d[1] = c_full; d[2] = c_issue; d[3] = c_commit; d[4] = c_rest; d[5] = c_items;
     }
   } else if (warp == PW + 9) {
@@ -603,41 +611,56 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const float* s_k2 = s_const + 1024;      //                 bwd: bn_mean
     const float* s_k3 = s_const + 1536;      //                 bwd: bn_invstd
     const bool has_bn = p.bn_scale != nullptr;
-    const bool use_mask = MODE == 1 && p.actmask_in && p.act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (p.OC % 32) == 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    // parameters used per chunk live in registers: the parameter block is larger than the fastest constant cache
+    // level and every LDC in the chunk loop is a potential miss on the critical path of the accumulator hand-back
+    const float* const e_dropscale = p.dropscale;
+    const void* const e_saved = p.saved;
+    double* const e_stats = p.stats;
+    double* const e_bn_sums = p.bn_sums;
+    void* const e_preact = p.preact;
+    void* const e_mask_out = p.actmask_out;
+    float* const e_head_out = p.head_out;
+    const bool e_has_scale = p.scale != nullptr;
+    const int e_act = p.act, e_OC = p.OC, e_OH = p.OH, e_OW = p.OW, e_dbg = p.debug, e_nnt = p.n_ntiles, e_OCr = p.OCr;
+    const int e_TH = p.TH, e_TW = p.TW, e_osh = p.osh, e_osw = p.osw, e_total = p.total_tiles, e_nacc = p.nacc;
+    const int e_tiles_w = p.tiles_w, e_tiles_h = p.tiles_h, e_ncls = p.ncls;
+    const bool eprof = (p.debug & 16) != 0 && warp == PW + 1;
+    long long ec_tfull = 0, ec_ld = 0, ec_pre = 0, ec_math = 0, ec_store = 0, ec_rest = 0, ec_tiles = 0, eprev = clock64();
+    const bool use_mask = MODE == 1 && p.actmask_in && e_act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (e_OC % 32) == 0;
+    for (int tile = blockIdx.x; tile < e_total; tile += gridDim.x) {
       int t = tile;
-      const TcClass& C = p.cls[tile_class(p, t)]; t /= p.ncls;
-      const int nt = t % p.n_ntiles; t /= p.n_ntiles;
-      const int tw = t % p.tiles_w; t /= p.tiles_w;
-      const int th = t % p.tiles_h;
-      const int n = t / p.tiles_h;
-      const int a = th * p.TH + hl, b = tw * p.TW + wl;
-      const int oh = a * p.osh + C.oh0, ow = b * p.osw + C.ow0;
-      const bool valid = a < C.TSH && b < C.TSW && oh < p.OH && ow < p.OW;
-      const long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
-      if (p.dropscale && n != ds_n) {
+      const TcClass& C = p.cls[tile_class(p, t)]; t /= e_ncls;
+      const int nt = t % e_nnt; t /= e_nnt;
+      const int tw = t % e_tiles_w; t /= e_tiles_w;
+      const int th = t % e_tiles_h;
+      const int n = t / e_tiles_h;
+      const int a = th * e_TH + hl, b = tw * e_TW + wl;
+      const int oh = a * e_osh + C.oh0, ow = b * e_osw + C.ow0;
+      const bool valid = a < C.TSH && b < C.TSW && oh < e_OH && ow < e_OW;
+      const long long pix = ((long long)n * e_OH + oh) * e_OW + ow;
+      if (e_dropscale && n != ds_n) {
         // Dropout2d scales are per (image, channel): stage the row of this image in smem once per image
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = threadIdx.x - (PW + 1) * 32; i < p.OC; i += 256) s_ds[i] = p.dropscale[(long long)n * p.OCr + i % p.OCr];
+        for (int i = threadIdx.x - (PW + 1) * 32; i < e_OC; i += 256) s_ds[i] = e_dropscale[(long long)n * e_OCr + i % e_OCr];
         asm volatile("bar.sync 1, 256;" ::: "memory");
         ds_n = n;
       }
-      if (MODE == 1 && p.saved && half == 0 && !use_mask) {
+      if (MODE == 1 && e_saved && half == 0 && !use_mask) {
         // pull the saved-activation rows of the tile after next into L2 now: by the time its epilogue runs,
         // the 32-byte operand loads hit L2 instead of paying an HBM round trip per 16-column chunk
         const int tile2 = tile + 2 * (int)gridDim.x;
-        if (tile2 < p.total_tiles) {
+        if (tile2 < e_total) {
           int t2 = tile2;
-          const TcClass& C2 = p.cls[tile_class(p, t2)]; t2 /= p.ncls;
-          const int nt2 = t2 % p.n_ntiles; t2 /= p.n_ntiles;
-          const int tw2 = t2 % p.tiles_w; t2 /= p.tiles_w;
-          const int th2 = t2 % p.tiles_h;
-          const int n2 = t2 / p.tiles_h;
-          const int a2 = th2 * p.TH + hl, b2 = tw2 * p.TW + wl;
-          const int oh2 = a2 * p.osh + C2.oh0, ow2 = b2 * p.osw + C2.ow0;
-          if (a2 < C2.TSH && b2 < C2.TSW && oh2 < p.OH && ow2 < p.OW) {
-            const bf16* row = reinterpret_cast<const bf16*>(p.saved) +
-                              (((long long)n2 * p.OH + oh2) * p.OW + ow2) * p.OC + nt2 * BN;
+          const TcClass& C2 = p.cls[tile_class(p, t2)]; t2 /= e_ncls;
+          const int nt2 = t2 % e_nnt; t2 /= e_nnt;
+          const int tw2 = t2 % e_tiles_w; t2 /= e_tiles_w;
+          const int th2 = t2 % e_tiles_h;
+          const int n2 = t2 / e_tiles_h;
+          const int a2 = th2 * e_TH + hl, b2 = tw2 * e_TW + wl;
+          const int oh2 = a2 * e_osh + C2.oh0, ow2 = b2 * e_osw + C2.ow0;
+          if (a2 < C2.TSH && b2 < C2.TSW && oh2 < e_OH && ow2 < e_OW) {
+            const bf16* row = reinterpret_cast<const bf16*>(e_saved) +
+                              (((long long)n2 * e_OH + oh2) * e_OW + ow2) * e_OC + nt2 * BN;
             for (int c = 0; c < BN; c += 64)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c));
           }
@@ -647,25 +670,30 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // accumulator wait, so their latency hides behind the MMAs (the 16x larger `saved` row never does)
       uint32_t mk[8];
       if (MODE == 1 && use_mask) {
-        const uint32_t* mp = reinterpret_cast<const uint32_t*>(p.actmask_in) + ((pix * p.OC + nt * BN) >> 5);
+        const uint32_t* mp = reinterpret_cast<const uint32_t*>(p.actmask_in) + ((pix * e_OC + nt * BN) >> 5);
 #pragma unroll
         for (int w = 0; w < 8; ++w) mk[w] = (valid && w * 32 < BN) ? __ldg(mp + w) : 0u;
       }
+      long long et0 = 0, et1 = 0;
+      if (eprof) et0 = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase, p.error_flag, 4);
       tc_fence_after();
+      if (eprof) { et1 = clock64(); ec_tfull += et1 - et0; ec_rest += et0 - eprev; eprev = et1; }
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
       // the two warps of a TMEM lane quarter split the 16-column chunks into a lower and an upper contiguous half
-      const int nchunks = (p.debug & 4) ? 0 : BN / 16, nper = (nchunks + 1) >> 1;
+      const int nchunks = (e_dbg & 4) ? 0 : BN / 16, nper = (nchunks + 1) >> 1;
       const int j_end = min(nchunks, (half + 1) * nper);
       unsigned long long mbits_lo = 0ull, mbits_hi = 0ull;   // forward: sign bits of this thread's chunks
+      // software pipeline over the chunks: the TMEM load of chunk j+1 is in flight while chunk j is processed
+      uint32_t rn[16];
+      if (half * nper < j_end) tmem_ld16(taddr0 + (uint32_t)(half * nper * 16), rn);
       for (int j = half * nper; j < j_end; ++j) {
         uint32_t r[16];
-        tmem_ld16(taddr0 + (uint32_t)(j * 16), r);
         const int cl = j * 16;          // channel inside the N tile
         const int c0 = nt * BN + cl;    // absolute output channel
         // global operands of this chunk are fetched while the TMEM load is in flight
         float ds[16];
-        if (p.dropscale) {
+        if (e_dropscale) {
           const float4* dp = reinterpret_cast<const float4*>(s_ds + c0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -678,8 +706,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         __align__(16) bf16 sv[16];
         if (MODE == 1) {
-          if (p.saved && valid && !use_mask) {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.saved) + pix * p.OC + c0);
+          if (e_saved && valid && !use_mask) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e_saved) + pix * e_OC + c0);
             reinterpret_cast<uint4*>(sv)[0] = __ldg(src);
             reinterpret_cast<uint4*>(sv)[1] = __ldg(src + 1);
           } else {
@@ -687,10 +715,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
           }
         }
-        tmem_ld_wait();
+        long long ec0 = 0;
+        if (eprof) ec0 = clock64();
+        tmem_ld_wait16(rn);
+        if (eprof) { const long long t = clock64(); ec_ld += t - ec0; ec_pre += ec0 - eprev; eprev = t; }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = rn[i];
+        if (j + 1 < j_end) tmem_ld16(taddr0 + (uint32_t)((j + 1) * 16), rn);
         __align__(16) bf16 ob[16];
         float s1[16], s2[16];
-        if (MODE == 0 && p.head_out) {
+        if (MODE == 0 && e_head_out) {
           // prediction head: the 16 accumulators of this pixel are the raw logits (5 + classes, zero padded);
           // /root/reference/yogo/model.py:295-313 applied in registers, written straight to the NCHW fp32 tensor
           if (valid) {
@@ -704,14 +738,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               for (int i = 0; i < 16; ++i)
                 if (i < D) tr[i] = t[i];
             }
-            const int SS = p.OH * p.OW, cell = oh * p.OW + ow;
-            float* o = p.head_out + (long long)n * D * SS + cell;
+            const int SS = e_OH * e_OW, cell = oh * e_OW + ow;
+            float* o = e_head_out + (long long)n * D * SS + cell;
             const float cx = p.head_cxs ? p.head_cxs[cell]
-                                        : (p.OW > 1 ? (float)ow * ((1.f - 1.f / (float)p.OW) / (float)(p.OW - 1)) : 0.f);
+                                        : (e_OW > 1 ? (float)ow * ((1.f - 1.f / (float)e_OW) / (float)(e_OW - 1)) : 0.f);
             const float cy = p.head_cys ? p.head_cys[cell]
-                                        : (p.OH > 1 ? (float)oh * ((1.f - 1.f / (float)p.OH) / (float)(p.OH - 1)) : 0.f);
-            o[0] = (1.f / (float)p.OW) * sigmoidf_(t[0]) + cx;
-            o[(long long)SS] = (1.f / (float)p.OH) * sigmoidf_(t[1]) + cy;
+                                        : (e_OH > 1 ? (float)oh * ((1.f - 1.f / (float)e_OH) / (float)(e_OH - 1)) : 0.f);
+            o[0] = (1.f / (float)e_OW) * sigmoidf_(t[0]) + cx;
+            o[(long long)SS] = (1.f / (float)e_OH) * sigmoidf_(t[1]) + cy;
             o[2LL * SS] = p.head_aw * expf(fminf(t[2], 80.f)) * p.head_wm;
             o[3LL * SS] = p.head_ah * expf(fminf(t[3], 80.f)) * p.head_hm;
             o[4LL * SS] = sigmoidf_(t[4]);
@@ -736,14 +770,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         } else if (MODE == 0) {
           __align__(16) bf16 pb[16];
-          const bool rnd = p.stats || p.preact;
+          const bool rnd = e_stats || e_preact;
           {
             // per-channel constants: 128-bit broadcast loads from smem
             const float4* sh4 = reinterpret_cast<const float4*>(s_k1 + c0);
             float shf[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { const float4 t4 = sh4[i]; shf[4*i] = t4.x; shf[4*i+1] = t4.y; shf[4*i+2] = t4.z; shf[4*i+3] = t4.w; }
-            if (p.scale) {
+            if (e_has_scale) {
               const float4* sc4 = reinterpret_cast<const float4*>(s_k0 + c0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -773,7 +807,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               s2[i] = valid ? x * x : 0.f;
             }
           }
-          if (p.actmask_out && valid) {
+          if (e_mask_out && valid) {
             uint32_t bits = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) bits |= (__uint_as_float(r[i]) > 0.f ? 1u : 0u) << i;
@@ -781,39 +815,41 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (jj < 4) mbits_lo |= (unsigned long long)bits << (16 * jj);
             else mbits_hi |= (unsigned long long)bits << (16 * (jj - 4));
           }
-          if (p.act == YG_ACT_LRELU) {
+          if (e_act == YG_ACT_LRELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float x = __uint_as_float(r[i]);
               r[i] = __float_as_uint(fmaxf(x, 0.01f * x));
             }
-          } else if (p.act == YG_ACT_SILU) {
+          } else if (e_act == YG_ACT_SILU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float x = __uint_as_float(r[i]);
               r[i] = __float_as_uint(x * __frcp_rn(1.f + __expf(-x)));
             }
           }
-          if (p.dropscale) {
+          if (e_dropscale) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * ds[i]);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             reinterpret_cast<__nv_bfloat162*>(ob)[i] = __floats2bfloat162_rn(__uint_as_float(r[2*i]), __uint_as_float(r[2*i+1]));
-          if (valid && !(p.debug & 1)) {
+          if (eprof) { const long long t = clock64(); ec_math += t - eprev; eprev = t; }
+          if (valid && !(e_dbg & 1)) {
             if (out) {
-              uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
+              uint4* dst = reinterpret_cast<uint4*>(out + pix * e_OC + c0);
               dst[0] = reinterpret_cast<uint4*>(ob)[0];
               dst[1] = reinterpret_cast<uint4*>(ob)[1];
             }
-            if (p.preact) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.preact) + pix * p.OC + c0);
+            if (e_preact) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e_preact) + pix * e_OC + c0);
               dst[0] = reinterpret_cast<uint4*>(pb)[0];
               dst[1] = reinterpret_cast<uint4*>(pb)[1];
             }
           }
-          if (p.stats) {
+          if (eprof) { const long long t = clock64(); ec_store += t - eprev; eprev = t; }
+          if (e_stats) {
             const float t1 = lane_transpose_reduce16(s1, lane);
             const float t2 = lane_transpose_reduce16(s2, lane);
             if (lane < 16) {
@@ -850,7 +886,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int i = 0; i < 16; ++i) s2[i] = 0.f;
           }
-          if (p.dropscale) {
+          if (e_dropscale) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) s1[i] = __uint_as_float(r[i]) * ds[i];
           } else {
@@ -865,11 +901,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t bits = word >> ((j & 1) * 16);
 #pragma unroll
             for (int i = 0; i < 16; ++i) s1[i] *= ((bits >> i) & 1u) ? 1.f : 0.01f;
-          } else if (p.saved) {
-            if (p.act == YG_ACT_LRELU) {
+          } else if (e_saved) {
+            if (e_act == YG_ACT_LRELU) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) s1[i] *= pre[i] > 0.f ? 1.f : 0.01f;
-            } else if (p.act == YG_ACT_SILU) {
+            } else if (e_act == YG_ACT_SILU) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float sg = __frcp_rn(1.f + __expf(-pre[i]));
@@ -881,12 +917,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           for (int i = 0; i < 8; ++i) {
             const __nv_bfloat162 pk = __floats2bfloat162_rn(s1[2*i], s1[2*i+1]);
             reinterpret_cast<__nv_bfloat162*>(ob)[i] = pk;
-            if (p.bn_sums) {
+            if (e_bn_sums) {
               const float2 f2 = __bfloat1622float2(pk);
               s1[2*i] = f2.x; s1[2*i+1] = f2.y;
             }
           }
-          if (p.bn_sums) {
+          if (e_bn_sums) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float g = valid ? s1[i] : 0.f;
@@ -895,12 +931,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
           }
           const bool second_sum = has_bn;   // sum(g * xhat) only exists for BatchNorm layers; sum(g) alone = d(bias)
-          if (valid && !(p.debug & 1)) {
-            uint4* dst = reinterpret_cast<uint4*>(out + pix * p.OC + c0);
+          if (valid && !(e_dbg & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(out + pix * e_OC + c0);
             dst[0] = reinterpret_cast<uint4*>(ob)[0];
             dst[1] = reinterpret_cast<uint4*>(ob)[1];
           }
-          if (p.bn_sums) {
+          if (e_bn_sums) {
             const float t1 = lane_transpose_reduce16(s1, lane);
             if (lane < 16) atomicAdd(&s_stat[cl + lane], t1);
             if (second_sum) {
@@ -910,12 +946,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         }
       }
-      if (MODE == 0 && p.actmask_out && valid && j_end > half * nper) {
+      if (MODE == 0 && e_mask_out && valid && j_end > half * nper) {
         // one store per thread and tile: 2 bytes per chunk, contiguous because the chunks are
-        unsigned char* mp = reinterpret_cast<unsigned char*>(p.actmask_out) + ((pix * p.OC + nt * BN) >> 3) + half * nper * 2;
+        unsigned char* mp = reinterpret_cast<unsigned char*>(e_mask_out) + ((pix * e_OC + nt * BN) >> 3) + half * nper * 2;
         const int nmine = j_end - half * nper;
-        if (nmine == 4 && (p.OC & 63) == 0 && (BN & 63) == 0) *reinterpret_cast<unsigned long long*>(mp) = mbits_lo;
-        else if (nmine == 8 && (p.OC & 127) == 0 && (BN & 127) == 0) {
+        if (nmine == 4 && (e_OC & 63) == 0 && (BN & 63) == 0) *reinterpret_cast<unsigned long long*>(mp) = mbits_lo;
+        else if (nmine == 8 && (e_OC & 127) == 0 && (BN & 127) == 0) {
           reinterpret_cast<unsigned long long*>(mp)[0] = mbits_lo;
           reinterpret_cast<unsigned long long*>(mp)[1] = mbits_hi;
         } else if (nmine == 2) *reinterpret_cast<unsigned int*>(mp) = (unsigned int)mbits_lo;
@@ -930,21 +966,27 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       // with several N tiles per CTA the statistics must be flushed per tile (channels change)
-      if (p.n_ntiles > 1 && (p.stats || p.bn_sums)) {
+      if (e_nnt > 1 && (e_stats || e_bn_sums)) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        double* dst = MODE == 0 ? p.stats : p.bn_sums;
+        double* dst = MODE == 0 ? e_stats : e_bn_sums;
         for (int i = threadIdx.x - (PW + 1) * 32; i < BN; i += 256) {
           const float a1 = s_stat[i], a2 = s_stat[256 + i];
           if (a1 != 0.f || a2 != 0.f) {
-            atomicAdd(dst + (nt * BN + i) % p.OCr, (double)a1);
-            atomicAdd(dst + p.OCr + (nt * BN + i) % p.OCr, (double)a2);
+            atomicAdd(dst + (nt * BN + i) % e_OCr, (double)a1);
+            atomicAdd(dst + e_OCr + (nt * BN + i) % e_OCr, (double)a2);
           }
           s_stat[i] = 0.f; s_stat[256 + i] = 0.f;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == e_nacc) { acc = 0; acc_phase ^= 1u; }
+      ++ec_tiles;
     }
+    if (eprof && lane == 0 && blockIdx.x < 256) {
+      unsigned long long* d = g_tc_dbg + blockIdx.x * 16 + 8;
+      d[0] = ec_tfull; d[1] = ec_ld; d[2] = ec_pre; d[3] = ec_math; d[4] = ec_store; d[5] = ec_rest; d[6] = ec_tiles;
+    }
+
   }
 
   // ------------------------------------------------------------------------- teardown
@@ -1742,7 +1784,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
 
 int set_tc_options(int v) { g_tc_options = v; return 0; }
 int tc_debug_read(unsigned long long* out, int n) {
-  if (n > 256 * 8) n = 256 * 8;
+  if (n > 256 * 16) n = 256 * 16;
   YG_CUDA(cudaDeviceSynchronize());
   YG_CUDA(cudaMemcpyFromSymbol(out, g_tc_dbg, (size_t)n * sizeof(unsigned long long)));
   return YG_OK;
