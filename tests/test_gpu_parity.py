@@ -261,6 +261,15 @@ def test_leaky_relu_sign_mask_equals_saved_activation_path(shape, impl):
         kept = (keep > 0)[:, None, None, :].expand(N, H, W, Cin).cpu()
         # wherever the channel was not dropped the bit is the sign of the activation input
         assert torch.equal(bits[kept], (pre.float().cpu() > 0)[kept])
+        # the straight-line epilogue (taken when no pre-activation copy is requested): same output, bits = sign of it
+        y2 = torch.empty_like(y)
+        mask2 = torch.zeros_like(mask)
+        ep2 = L.FwdEpilogue(None, bp.data_ptr(), L.ACT_LRELU, keep.data_ptr(), None, None, mask2.data_ptr())
+        L.check(lib.yg_conv_fwd(xp.data_ptr(), wp.data_ptr(), y2.data_ptr(), 1, N, H, W, Cp, Cin, 3, 1, C.byref(ep2), L.stream()))
+        # (with a pre-activation copy the value is rounded to bf16 before the activation, without it after: <= 1 ulp apart)
+        torch.testing.assert_close(y2.float(), y.float(), rtol=2e-2, atol=1e-3)
+        bits2 = torch.from_numpy(np.unpackbits(mask2.cpu().numpy(), bitorder="little")).reshape(N, H, W, Cin).bool()
+        assert torch.equal(bits2[kept], (y2.float().cpu() > 0)[kept])
         # consumer: dgrad of the next conv with the activation backward fused, mask vs saved tensor
         Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
         dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).to(dt)

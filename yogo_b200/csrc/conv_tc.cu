@@ -267,6 +267,14 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                 "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, swizzled shared-memory matrix descriptor (sm_100 UMMA).  bits: start>>4 [0,14), LBO>>4 [16,30),
@@ -627,6 +635,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool eprof = (p.debug & 16) != 0 && warp == PW + 1;
     long long ec_tfull = 0, ec_ld = 0, ec_pre = 0, ec_math = 0, ec_store = 0, ec_rest = 0, ec_tiles = 0, eprev = clock64();
     const bool use_mask = MODE == 1 && p.actmask_in && e_act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (e_OC % 32) == 0;
+    // (dgrad fast path: the multiplication order differs from the generic path only by commuting g*ds*slope)
+    const bool fast_fwd = MODE == 0 && !e_head_out && !e_has_scale && !e_stats && !e_preact && (BN % 64) == 0 &&
+                          (e_act == YG_ACT_LRELU || e_act == YG_ACT_NONE) && !(p.debug & (4 | 16)) && out != nullptr;
+    const bool fast_bwd = MODE == 1 && use_mask && !e_bn_sums && (BN % 64) == 0 && !(p.debug & (4 | 16));
     for (int tile = blockIdx.x; tile < e_total; tile += gridDim.x) {
       int t = tile;
       const TcClass& C = p.cls[tile_class(p, t)]; t /= e_ncls;
@@ -684,6 +696,99 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int nchunks = (e_dbg & 4) ? 0 : BN / 16, nper = (nchunks + 1) >> 1;
       const int j_end = min(nchunks, (half + 1) * nper);
       unsigned long long mbits_lo = 0ull, mbits_hi = 0ull;   // forward: sign bits of this thread's chunks
+      // ---- straight-line fast paths for the common epilogue flavours: 32 columns per iteration, no branches inside,
+      // so the compiler can interleave 32 independent element chains (the generic loop below issues at IPC ~0.25)
+      if (MODE == 0 && fast_fwd) {
+        bf16* orow = out + pix * e_OC + nt * BN;
+        for (int j = half * nper; j < j_end; j += 2) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
+          tmem_ld16(taddr0 + (uint32_t)(j * 16 + 16), rb);
+          const int c0 = nt * BN + j * 16;
+          float v[32], k[32];
+          {
+            const float4* k4 = reinterpret_cast<const float4*>(s_k1 + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; k[4*i] = t4.x; k[4*i+1] = t4.y; k[4*i+2] = t4.z; k[4*i+3] = t4.w; }
+          }
+          tmem_ld_wait32(ra, rb);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(ra[i]) + k[i]; v[16 + i] = __uint_as_float(rb[i]) + k[16 + i]; }
+          if (e_act == YG_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
+          }
+          if (e_dropscale) {
+            const float4* k4 = reinterpret_cast<const float4*>(s_ds + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
+          }
+          __align__(16) uint32_t ob32[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+          if (e_mask_out) {
+            // sign bits from the packed outputs: bf16 > 0 <=> its bit pattern, read as int16, is > 0; sign(y) = sign(v)
+            // wherever the Dropout2d scale is non-zero (and a dropped channel's gradient is zero whatever the bit says)
+            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t t0 = __vcmpgts2(ob32[i], 0u) & 0x00010001u, t1 = __vcmpgts2(ob32[4 + i], 0u) & 0x00010001u;
+              const uint32_t t2 = __vcmpgts2(ob32[8 + i], 0u) & 0x00010001u, t3 = __vcmpgts2(ob32[12 + i], 0u) & 0x00010001u;
+              b0 |= ((t0 | (t0 >> 15)) & 3u) << (2 * i);
+              b1 |= ((t1 | (t1 >> 15)) & 3u) << (2 * i);
+              b2 |= ((t2 | (t2 >> 15)) & 3u) << (2 * i);
+              b3 |= ((t3 | (t3 >> 15)) & 3u) << (2 * i);
+            }
+            const unsigned long long bits = (unsigned long long)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+            const int jj = j - half * nper;
+            if (jj < 4) mbits_lo |= bits << (16 * jj);
+            else mbits_hi |= bits << (16 * (jj - 4));
+          }
+          if (valid && !(e_dbg & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+          }
+        }
+      } else if (MODE == 1 && fast_bwd) {
+        bf16* orow = out + pix * e_OC + nt * BN;
+        for (int j = half * nper; j < j_end; j += 2) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
+          tmem_ld16(taddr0 + (uint32_t)(j * 16 + 16), rb);
+          const int c0 = nt * BN + j * 16;
+          const int wi = j >> 1;   // j is even: one 32-bit mask word covers both chunks
+          uint32_t word = mk[0];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) word = (wi == w) ? mk[w] : word;
+          float v[32];
+          tmem_ld_wait32(ra, rb);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = __uint_as_float(ra[i]) * (((word >> i) & 1u) ? 1.f : 0.01f);
+            v[16 + i] = __uint_as_float(rb[i]) * (((word >> (16 + i)) & 1u) ? 1.f : 0.01f);
+          }
+          if (e_dropscale) {
+            const float4* k4 = reinterpret_cast<const float4*>(s_ds + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
+          }
+          __align__(16) uint32_t ob32[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+          if (valid && !(e_dbg & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+          }
+        }
+      } else {
       // software pipeline over the chunks: the TMEM load of chunk j+1 is in flight while chunk j is processed
       uint32_t rn[16];
       if (half * nper < j_end) tmem_ld16(taddr0 + (uint32_t)(half * nper * 16), rn);
@@ -946,6 +1051,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         }
       }
+      }   // generic chunk loop
       if (MODE == 0 && e_mask_out && valid && j_end > half * nper) {
         // one store per thread and tile: 2 bytes per chunk, contiguous because the chunks are
         unsigned char* mp = reinterpret_cast<unsigned char*>(e_mask_out) + ((pix * e_OC + nt * BN) >> 3) + half * nper * 2;
