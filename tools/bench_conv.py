@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--impl", default="auto")
     ap.add_argument("--stats", type=int, default=0)
-    ap.add_argument("--tc-options", type=int, default=8217)
+    ap.add_argument("--tc-options", type=int, default=24601)
     ap.add_argument("--no-saved", type=int, default=0)
     ap.add_argument("--mask", type=int, default=0)
     args = ap.parse_args()

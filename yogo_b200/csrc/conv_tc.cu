@@ -59,7 +59,9 @@ struct TcParams {
   int N, tiles_h, tiles_w, n_ntiles, total_tiles;
   int TH, TW, tw_shift;             // output tile in pixels (8 x 16 legacy, 16 x 8 with 2-D halo boxes), log2(TW)
   int bt_stride;                    // weight-tile slots per group in a streamed-weight stage
+  int cta2;                         // CTA pairs (cta_group::2): M = 256 per MMA, each CTA holds BN/2 rows of every weight tile
   int ncls, cls_rot;                // classes and the rotation period max(1, grid / ncls) (see tile_class)
+  unsigned long long fd_ncls, fd_rot, fd_nnt, fd_tw, fd_th;   // ceil(2^32 / d): division by multiply-high (decode_tile)
   TcClass cls[4];
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
@@ -98,10 +100,23 @@ __device__ unsigned long long g_tc_dbg[256 * 16];   // per CTA: 0-5 MMA warp, 8-
 // share dz and saved-activation lines in L2); the class of slot c rotates with the spatial index so that a
 // persistent CTA, whose stride gridDim.x is normally a multiple of ncls, cycles through all classes instead
 // of being stuck with the cheapest (1 tap) or the most expensive (4 taps) one.
+__device__ __forceinline__ int fdiv(int n, unsigned long long m) {   // n / d for n * d < 2^32, m = ceil(2^32 / d)
+  return (int)(((unsigned long long)(unsigned)n * m) >> 32);
+}
 __device__ __forceinline__ int tile_class(const TcParams& p, int tile) {
   if (p.ncls == 1) return 0;
-  const int sp = tile / p.ncls, c = tile - sp * p.ncls;
-  return (c + sp / p.cls_rot) % p.ncls;
+  const int sp = fdiv(tile, p.fd_ncls), c = tile - sp * p.ncls;
+  const int x = c + fdiv(sp, p.fd_rot);
+  return x - fdiv(x, p.fd_ncls) * p.ncls;
+}
+// tile index -> (class, N tile, tile column, tile row, image); the class is the fastest index.  Division by multiply-high:
+// every role decodes every tile, and four runtime integer divisions cost several hundred cycles of a single warp
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& tw, int& th, int& n) {
+  cls = tile_class(p, tile);
+  int t = fdiv(tile, p.fd_ncls);
+  int q = fdiv(t, p.fd_nnt); nt = t - q * p.n_ntiles; t = q;
+  q = fdiv(t, p.fd_tw); tw = t - q * p.tiles_w; t = q;
+  q = fdiv(t, p.fd_th); th = t - q * p.tiles_h; n = q;
 }
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -277,6 +292,63 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&a)[16], uint32_t (&b)[
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster execute one M = 256 MMA; each holds its own 128 A rows and HALF of B.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {   // shared::cluster address of saddr in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA, the transaction bytes are signalled on the LEADER's barrier
+__device__ __forceinline__ void tma2_load_4d_p(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,
+                                               int c2, int c3, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_lh2_p(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nsetp.ne.b32 q, %7, 0;\n"
+      "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_p(uint64_t* bar, uint32_t leader) {   // arrives on `bar` of BOTH CTAs
+  asm volatile(
+      "{\n.reg .pred q;\n.reg .b16 m;\nsetp.ne.b32 q, %1, 0;\nmov.b16 m, 3;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}\n"
+      ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+
 // K-major, swizzled shared-memory matrix descriptor (sm_100 UMMA).  bits: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout [61,64) (2 = SWIZZLE_128B, 4 = 64B, 6 = 32B).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
@@ -313,7 +385,7 @@ __device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(_
 // PROD = 0: A operand by TMA (one producer lane).  PROD = 1: A operand by cp.async from two producer warps
 // writing the swizzled layout by hand - for 16/32-channel tensors, whose 32/64-byte rows make TMA
 // request-rate bound (~4-8 cycles per row measured) - with all weights resident in shared memory.
-template <int KC, int MODE, int PROD>
+template <int KC, int MODE, int PROD, int CTA2 = 0>
 __global__ void __launch_bounds__((PROD ? 2 : 1) * 32 + 320, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   constexpr int PW = PROD ? 2 : 1;             // producer warps; MMA warp = PW; epilogue warps PW+1 .. PW+8
@@ -347,16 +419,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int BN = p.BN;
 
+  // CTA pair: rank 0 (leader) issues the MMAs for both; every barrier the MMA warp waits on lives in the leader
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const int total_tiles = CTA2 ? ((p.total_tiles + 1) & ~1) : p.total_tiles;   // both CTAs of a pair run the same iterations
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
     prefetch_tmap(&maps.b);
     for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], PROD ? 64 : 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTA2 ? 16 : 8); }
     mbar_init(&resb_bar[0], 1);
     *prod_iter = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (p.b_resident) {
+    if (p.b_resident && !CTA2) {
       // every (tap, K chunk) weight tile is fetched once and stays in shared memory
       mbar_expect_tx(&resb_bar[0], (uint32_t)(p.ntaps_total * p.kchunks * p.b_tap_bytes));
       for (int tap = 0; tap < p.ntaps_total; ++tap)
@@ -364,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           tma_load_3d(resb + (size_t)(tap * p.kchunks + kc) * p.b_tap_bytes, &maps.b, &resb_bar[0], kc * KC, 0, tap);
     }
   }
-  if (warp == PW) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == PW) { if (CTA2) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); }
   // epilogue constants and statistics accumulators (the N tile is fixed per CTA only when n_ntiles == 1,
   // so constants are indexed by absolute channel and reloaded per tile below when needed)
   for (int i = threadIdx.x; i < 2 * 256; i += NTHREADS) s_stat[i] = 0.f;
@@ -384,6 +459,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (CTA2) {
+    cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
+    if (warp == 0 && lane == 0) {
+      // resident weights of a pair: each CTA keeps BN/2 rows of every tile; all bytes are counted on the leader's barrier
+      const uint32_t lbar = map_to_cta(smem_u32(&resb_bar[0]), 0u);
+      if (cta_rank == 0) mbar_expect_tx(&resb_bar[0], 2u * (uint32_t)(p.ntaps_total * p.kchunks * p.b_tap_bytes));
+      for (int tap = 0; tap < p.ntaps_total; ++tap)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma2_load_3d(resb + (size_t)(tap * p.kchunks + kc) * p.b_tap_bytes, &maps.b, lbar, kc * KC,
+                       (int)cta_rank * (BN / 2), tap);
+    }
+  }
 
 
   if (warp < PW) {
@@ -396,15 +483,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         uint32_t phase = 0;
         int iter = 0;
         const int nstages = p.nstages, kchunks = p.kchunks, b_resident = p.b_resident;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           if (lane == 0) *prod_iter = iter;
           ++iter;
-          int t = tile;
-          const TcClass& C = p.cls[tile_class(p, t)]; t /= p.ncls;
-          const int nt = t % p.n_ntiles; t /= p.n_ntiles;
-          const int tw = t % p.tiles_w; t /= p.tiles_w;
-          const int th = t % p.tiles_h;
-          const int n = t / p.tiles_h;
+          int ci, nt, tw, th, n;
+          decode_tile(p, tile, ci, nt, tw, th, n);
+          const TcClass& C = p.cls[ci];
           const int cg0 = C.g0, cg1 = C.g0 + C.ng, gpi = C.gpi;
           for (int kc = 0; kc < kchunks; ++kc) {
             for (int g0 = cg0; g0 < cg1; g0 += gpi) {
@@ -419,6 +503,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               uint32_t bytes = 0;
               for (int gi = g0; gi < g0 + gpi; ++gi)
                 bytes += (uint32_t)(p.g[gi].rows * p.g[gi].cols * (int)ROW_BYTES + (b_resident ? 0 : p.g[gi].ntaps * p.b_tap_bytes));
+              if (CTA2) {
+                // both CTAs load their own A boxes; the bytes of both are expected on the leader's barrier
+                if (cta_rank == 0) mbar_expect_tx_p(&full_bar[stage], 2u * bytes, leader);
+                const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0u);
+                for (int gi = g0; gi < g0 + gpi; ++gi) {
+                  const TcGroup& g = p.g[gi];
+                  tma2_load_4d_p(sa + (size_t)(gi - g0) * p.a_box_bytes, &maps.a[g.map], lbar, kc * KC,
+                                 tw * p.TW + g.dw, th * p.TH + g.dh, n, leader);
+                }
+                if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                continue;
+              }
               mbar_expect_tx_p(&full_bar[stage], bytes, leader);
               for (int gi = g0; gi < g0 + gpi; ++gi) {
                 const TcGroup& g = p.g[gi];
@@ -497,12 +593,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   } else if (warp == PW) {
     // ===================================================================== MMA issuer
     // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (p.b_resident) mbar_wait(&resb_bar[0], 0, p.error_flag, 5);
+    if (p.b_resident && cta_rank == 0) mbar_wait(&resb_bar[0], 0, p.error_flag, 5);
     // descriptors differ only in their 14-bit start-address field (16-byte units): build one and add offsets
     const uint64_t desc0 = umma_desc(smem_u32(smem), SBO, LAYOUT);
     const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc0_lo = (uint32_t)desc0;
@@ -513,7 +609,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool prof = (p.debug & 16) != 0;
     const uint32_t leader = elect_one();
     long long c_tempty = 0, c_full = 0, c_issue = 0, c_commit = 0, c_rest = 0, c_items = 0, tprev = clock64();
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles && cta_rank == 0; tile += gridDim.x) {   // pair: the leader issues
       long long ta = 0;
       if (prof) ta = clock64();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, p.error_flag, 2);
@@ -542,21 +638,28 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (km == (1u << KSTEPS) - 1u) {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                umma_bf16_lh2_p(d_tmem, ad0 + 2u * k, a_hi, bd0 + 2u * k, desc_hi, idesc, started, leader);
+                if (CTA2) umma2_bf16_lh2_p(d_tmem, ad0 + 2u * k, a_hi, bd0 + 2u * k, desc_hi, idesc, started, leader);
+                else umma_bf16_lh2_p(d_tmem, ad0 + 2u * k, a_hi, bd0 + 2u * k, desc_hi, idesc, started, leader);
                 started = 1u;
               }
             } else {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
                 if (!((km >> k) & 1u)) continue;   // structurally zero weights (W-folded convolution)
-                umma_bf16_lh2_p(d_tmem, ad0 + 2u * k, a_hi, bd0 + 2u * k, desc_hi, idesc, started, leader);
+                if (CTA2) umma2_bf16_lh2_p(d_tmem, ad0 + 2u * k, a_hi, bd0 + 2u * k, desc_hi, idesc, started, leader);
+                else umma_bf16_lh2_p(d_tmem, ad0 + 2u * k, a_hi, bd0 + 2u * k, desc_hi, idesc, started, leader);
                 started = 1u;
               }
             }
           }
           if (prof) t2 = clock64();
-          umma_commit_p(&empty_bar[stage], leader);                                  // frees the smem slot when the MMAs retire
-          if (kc == kchunks - 1 && g0 + gpi >= cg1) umma_commit_p(&tfull_bar[acc], leader);  // accumulator complete
+          if (CTA2) {
+            umma2_commit_p(&empty_bar[stage], leader);                                 // both CTAs' slots and accumulators
+            if (kc == kchunks - 1 && g0 + gpi >= cg1) umma2_commit_p(&tfull_bar[acc], leader);
+          } else {
+            umma_commit_p(&empty_bar[stage], leader);                                  // frees the smem slot when the MMAs retire
+            if (kc == kchunks - 1 && g0 + gpi >= cg1) umma_commit_p(&tfull_bar[acc], leader);  // accumulator complete
+          }
           if (prof) {
             const long long t3 = clock64();
             c_rest += t0 - tprev; c_full += t1 - t0; c_issue += t2 - t1; c_commit += t3 - t2; tprev = t3; ++c_items;
@@ -631,29 +734,25 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool e_has_scale = p.scale != nullptr;
     const int e_act = p.act, e_OC = p.OC, e_OH = p.OH, e_OW = p.OW, e_dbg = p.debug, e_nnt = p.n_ntiles, e_OCr = p.OCr;
     const int e_TH = p.TH, e_TW = p.TW, e_osh = p.osh, e_osw = p.osw, e_total = p.total_tiles, e_nacc = p.nacc;
-    const int e_tiles_w = p.tiles_w, e_tiles_h = p.tiles_h, e_ncls = p.ncls;
     const bool eprof = (p.debug & 16) != 0 && warp == PW + 1;
     long long ec_tfull = 0, ec_ld = 0, ec_pre = 0, ec_math = 0, ec_store = 0, ec_rest = 0, ec_tiles = 0, eprev = clock64();
     const bool use_mask = MODE == 1 && p.actmask_in && e_act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (e_OC % 32) == 0;
     // (dgrad fast path: the multiplication order differs from the generic path only by commuting g*ds*slope)
     const bool fast_fwd = MODE == 0 && !e_head_out && !e_has_scale && !e_stats && !e_preact && (BN % 64) == 0 &&
-                          (e_act == YG_ACT_LRELU || e_act == YG_ACT_NONE) && !(p.debug & (4 | 16)) && out != nullptr;
-    const bool fast_bwd = MODE == 1 && use_mask && !e_bn_sums && (BN % 64) == 0 && !(p.debug & (4 | 16));
-    for (int tile = blockIdx.x; tile < e_total; tile += gridDim.x) {
-      int t = tile;
-      const TcClass& C = p.cls[tile_class(p, t)]; t /= e_ncls;
-      const int nt = t % e_nnt; t /= e_nnt;
-      const int tw = t % e_tiles_w; t /= e_tiles_w;
-      const int th = t % e_tiles_h;
-      const int n = t / e_tiles_h;
+                          (e_act == YG_ACT_LRELU || e_act == YG_ACT_NONE) && !(p.debug & 4) && out != nullptr;
+    const bool fast_bwd = MODE == 1 && use_mask && !e_bn_sums && (BN % 64) == 0 && !(p.debug & 4);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ci, nt, tw, th, n;
+      decode_tile(p, tile, ci, nt, tw, th, n);
+      const TcClass& C = p.cls[ci];
       const int a = th * e_TH + hl, b = tw * e_TW + wl;
       const int oh = a * e_osh + C.oh0, ow = b * e_osw + C.ow0;
-      const bool valid = a < C.TSH && b < C.TSW && oh < e_OH && ow < e_OW;
+      const bool valid = a < C.TSH && b < C.TSW && oh < e_OH && ow < e_OW && tile < e_total;   // (pair padding tile)
       const long long pix = ((long long)n * e_OH + oh) * e_OW + ow;
       if (e_dropscale && n != ds_n) {
         // Dropout2d scales are per (image, channel): stage the row of this image in smem once per image
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = threadIdx.x - (PW + 1) * 32; i < e_OC; i += 256) s_ds[i] = e_dropscale[(long long)n * e_OCr + i % e_OCr];
+        for (int i = threadIdx.x - (PW + 1) * 32; i < e_OC; i += 256) s_ds[i] = e_dropscale[(long long)(n < p.N ? n : p.N - 1) * e_OCr + i % e_OCr];
         asm volatile("bar.sync 1, 256;" ::: "memory");
         ds_n = n;
       }
@@ -662,12 +761,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // the 32-byte operand loads hit L2 instead of paying an HBM round trip per 16-column chunk
         const int tile2 = tile + 2 * (int)gridDim.x;
         if (tile2 < e_total) {
-          int t2 = tile2;
-          const TcClass& C2 = p.cls[tile_class(p, t2)]; t2 /= e_ncls;
-          const int nt2 = t2 % e_nnt; t2 /= e_nnt;
-          const int tw2 = t2 % e_tiles_w; t2 /= e_tiles_w;
-          const int th2 = t2 % e_tiles_h;
-          const int n2 = t2 / e_tiles_h;
+          int ci2, nt2, tw2, th2, n2;
+          decode_tile(p, tile2, ci2, nt2, tw2, th2, n2);
+          const TcClass& C2 = p.cls[ci2];
           const int a2 = th2 * e_TH + hl, b2 = tw2 * e_TW + wl;
           const int oh2 = a2 * e_osh + C2.oh0, ow2 = b2 * e_osw + C2.ow0;
           if (a2 < C2.TSH && b2 < C2.TSW && oh2 < e_OH && ow2 < e_OW) {
@@ -1070,7 +1166,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc]), 0u));   // the leader's MMA warp waits for both
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       // with several N tiles per CTA the statistics must be flushed per tile (channels change)
       if (e_nnt > 1 && (e_stats || e_bn_sums)) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1108,7 +1207,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
   }
-  if (warp == PW) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (CTA2) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == PW) { if (CTA2) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------ weights
@@ -1153,7 +1253,7 @@ __global__ void pack_weights_s2fold_kernel(const float* __restrict__ w, bf16* __
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int g_tc_options = 25 + 8192;  // bit 0: resident weights, bit 1: cp.async producer, bit 2: L2 prefetch warp, bit 3: W-fold,
+static int g_tc_options = 25 + 8192 + 16384;  // bit 0: resident weights, bit 1: cp.async producer, bit 2: L2 prefetch warp, bit 3: W-fold,
                                // bit 4: column-pair fold for stride-2 dgrad
 // W-fold factor for stride-1 convolutions with few channels (see pack_weights_kernel): fold while the folded
 // input channel count stays <= 64 and everything remains a legal UMMA shape.
@@ -1793,7 +1893,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   p.bt_stride = max_taps;
   // small-K layers: merge all tap groups of a K chunk into one pipeline item, so that the fixed per-item
   // cost (mbarrier round trips, MMA issue, commit) is paid once per tile instead of 3-6 times
-  p.b_tap_bytes = p.BN * KCc * 2;
+  p.b_tap_bytes = (p.cta2 ? p.BN / 2 : p.BN) * KCc * 2;
   if (p.ntaps_total == 0) p.ntaps_total = 9;
   const int resb = (p.ntaps_total * p.kchunks * p.b_tap_bytes + 1023) & ~1023;
   const int merge_limit = two_d ? 48 * 1024 : 32 * 1024;
@@ -1868,13 +1968,47 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (p.cta2) {
+    const int padded = (p.total_tiles + 1) & ~1;
+    grid = (padded < sms ? padded : sms) & ~1;
+    if (KCc != 64 || mode > 1 || grid < 2 || !p.b_resident || p.ncls != 1 || p.n_ntiles != 1) {
+      set_error("tcgen05 conv: CTA-pair configuration not supported");
+      return YG_ERR_INVALID;
+    }
+  }
   p.cls_rot = grid / p.ncls > 0 ? grid / p.ncls : 1;
+  {
+    auto magic = [](int d) { return ((1ull << 32) + (unsigned long long)d - 1) / (unsigned long long)d; };
+    p.fd_ncls = magic(p.ncls); p.fd_rot = magic(p.cls_rot); p.fd_nnt = magic(p.n_ntiles);
+    p.fd_tw = magic(p.tiles_w); p.fd_th = magic(p.tiles_h);
+    const long long dmax = std::max(std::max(p.ncls, p.n_ntiles), std::max(std::max(p.tiles_w, p.tiles_h), p.cls_rot));
+    if ((long long)p.total_tiles * dmax >= (1ll << 32)) { set_error("tcgen05 conv: %d tiles exceed the fast-division range", p.total_tiles); return YG_ERR_INVALID; }
+  }
 #define TC_LAUNCH(KCV, MODEV, PRODV)                                                                                    \
   do {                                                                                                                  \
     YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCV, MODEV, PRODV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     conv_tc_kernel<KCV, MODEV, PRODV><<<grid, (PRODV ? 2 : 1) * 32 + 320, smem, st>>>(maps, p);                         \
   } while (0)
-  if (mode == 0) {
+  if (p.cta2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(32 + 320, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (mode == 0) {
+      YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      YG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 0, 0, 1>, maps, p));
+    } else {
+      YG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      YG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 1, 0, 1>, maps, p));
+    }
+  } else if (mode == 0) {
     if (KCc == 64) TC_LAUNCH(64, 0, 0);
     else if (KCc == 32) { if (prod) TC_LAUNCH(32, 0, 1); else TC_LAUNCH(32, 0, 0); }
     else { if (prod) TC_LAUNCH(16, 0, 1); else TC_LAUNCH(16, 0, 0); }
@@ -1918,6 +2052,7 @@ static int fit_kc(int K, int BN, int max_rows) {
 // Needs all weights resident in shared memory (a streamed 9-tap stage would not fit).
 constexpr int T2_TH = 16, T2_TW = 8;
 static bool two_d_fits(int K, int BN, int n_ntiles, int ntaps_total, int box_px, int ngroups, int* kc_out) {
+  // (BN = weight rows kept per CTA: the whole N tile, or half of it for a CTA pair)
   if (!(g_tc_options & 8192) || !(g_tc_options & 1) || n_ntiles != 1) return false;
   const int kc = pick_kc(K);
   if (!kc) return false;
@@ -1984,8 +2119,14 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   const int BN = pick_bn(Cout);
   const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
   int kc2 = 0;
-  const bool two_d = two_d_fits(Cin, BN, Cout / BN, 9, stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1),
-                                stride == 1 ? 1 : 4, &kc2);
+  const bool two_d1 = two_d_fits(Cin, BN, Cout / BN, 9, stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1),
+                                 stride == 1 ? 1 : 4, &kc2);
+  bool two_d = two_d1;
+  // weights too large to stay resident in one CTA: a CTA pair keeps half of every weight tile each (cta_group::2)
+  bool cta2 = false;
+  if (!two_d && (g_tc_options & 16384) && stride == 1 && Cout == BN && BN % 32 == 0 && pick_kc(Cin) == 64 &&
+      two_d_fits(Cin, BN / 2, 1, 9, (T2_TH + 2) * (T2_TW + 2), 1, &kc2))
+    two_d = cta2 = true;
   const int KCc = two_d ? kc2 : fit_kc(Cin, BN, max_rows);
   if (!KCc) { set_error("conv_fwd_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
   bf16* wp = nullptr;
@@ -1995,10 +2136,11 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
     uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * Cout * 2};
-    uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
+    uint32_t box[3] = {(uint32_t)KCc, (uint32_t)(cta2 ? BN / 2 : BN), 1};
     rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
     if (rc) return rc;
   }
+  p.cta2 = cta2 ? 1 : 0;
   const bf16* xb = (const bf16*)x;
   int ngroups = 0;
   if (two_d && stride == 1) {
@@ -2114,8 +2256,12 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   const int BN = pick_bn(Cin);
   const int max_rows = stride == 1 ? TC_TH + 2 : TC_TH + 1;
   int kc2 = 0;
-  const bool two_d = two_d_fits(Cout, BN, Cin / BN, s2f ? 6 : 9,
-                                stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1), 1, &kc2);
+  const bool two_d1 = two_d_fits(Cout, BN, Cin / BN, s2f ? 6 : 9,
+                                 stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1), 1, &kc2);
+  bool two_d = two_d1, cta2 = false;
+  if (!two_d && (g_tc_options & 16384) && stride == 1 && Cin == BN && BN % 32 == 0 && pick_kc(Cout) == 64 &&
+      two_d_fits(Cout, BN / 2, 1, 9, (T2_TH + 2) * (T2_TW + 2), 1, &kc2))
+    two_d = cta2 = true;   // CTA pair, see conv_fwd_tc
   const int KCc = two_d ? kc2 : fit_kc(Cout, BN, max_rows);
   if (!KCc) { set_error("conv_dgrad_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
   bf16* wp = nullptr;
@@ -2129,10 +2275,11 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   {
     uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)(s2f ? 6 : 9)};
     uint64_t str[2] = {(uint64_t)Cout * 2, (uint64_t)Cin * Cout * 2};
-    uint32_t box[3] = {(uint32_t)KCc, (uint32_t)BN, 1};
+    uint32_t box[3] = {(uint32_t)KCc, (uint32_t)(cta2 ? BN / 2 : BN), 1};
     rc = make_map(&maps.b, wp, 3, dims, str, box, KCc);
     if (rc) return rc;
   }
+  p.cta2 = cta2 ? 1 : 0;
   // A maps over dz: map 0 has the tallest box of the problem, map 1 (stride 2 only) the 8-row box
   for (int mi = 0; mi < 2 && !two_d; ++mi) {
     const int rows = stride == 1 ? TC_TH + 2 : (mi == 0 ? TC_TH + 1 : TC_TH);
