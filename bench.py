@@ -296,7 +296,7 @@ def run_ours(args):
 def kernel_breakdown(trainer, dev_imgs, dev_labs, args, L):
     """Times every C-ABI call of a few steps with CUDA events on the launching stream."""
     lib = L.lib()
-    names = [n for n in L.EXPORTED_SYMBOLS if n.startswith(("yg_conv", "yg_bn_act", "yg_bn_bwd", "yg_head", "yg_yogo", "yg_adamw"))
+    names = [n for n in L.EXPORTED_SYMBOLS if n.startswith(("yg_conv", "yg_bn_act", "yg_bn_bwd", "yg_bn_stats", "yg_head", "yg_yogo", "yg_adamw"))
              and not n.endswith("workspace")]
     records = []
     originals = {}

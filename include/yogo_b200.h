@@ -147,10 +147,18 @@ int yg_bn_finalize(const double* stats, double count, const float* gamma, const 
 int yg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                     const float* running_var, const float* conv_bias, float eps,
                     float* scale, float* shift, int C, void* stream);
-/* a = act(y*scale[c] + shift[c]) * dropscale[n,c]   (elementwise, NHWC) */
+/* a = act(y*scale[c] + shift[c]) * dropscale[n,c]   (elementwise, NHWC); actmask (or NULL): sign bits of the
+ * activation input, same format as yg_fwd_epilogue.actmask (needs C % 8 == 0). */
 int yg_bn_act_apply(const void* y, void* a, int dtype, int N, int HW, int C,
                     const float* scale, const float* shift, int act, const float* dropscale,
-                    void* stream);
+                    void* actmask, void* stream);
+/* stats[0..C) += sum(y), stats[C..2C) += sum(y*y) over the N*HW pixels of an NHWC tensor (train-mode batch statistics
+ * of a convolution output in one streaming pass; the alternative is yg_fwd_epilogue.stats).  C % 8 == 0. */
+int yg_bn_stats(const void* y, int dtype, int N, int HW, int C, double* stats, void* stream);
+/* sums[0..C) += sum(g), sums[C..2C) += sum(g * xhat), xhat = (y - mean) * invstd: the two reductions of BatchNorm
+ * backward for a gradient g that already includes the activation backward (the alternative is yg_bwd_epilogue.bn_sums). */
+int yg_bn_bwd_sums(const void* g, const void* y, int dtype, int N, int HW, int C, const float* mean,
+                   const float* invstd, double* sums, void* stream);
 /* dz = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M) in place over g (batch_stats != 0), or
  * dz = gamma*invstd*g when the layer ran with running statistics (batch_stats == 0, BN in
  * eval mode inside a training graph: YOGO(tuning=True), model.py:69-70).  Also writes

@@ -43,7 +43,7 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 template <typename T>
 __global__ void bn_act_apply_kernel(const T* __restrict__ y, T* __restrict__ a, long long total, int HW, int C,
                                     const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                                    const float* __restrict__ dropscale) {
+                                    const float* __restrict__ dropscale, unsigned char* __restrict__ actmask) {
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i0 >= total) return;
   if ((C & 7) == 0) {
@@ -55,10 +55,12 @@ __global__ void bn_act_apply_kernel(const T* __restrict__ y, T* __restrict__ a, 
 #pragma unroll
     for (int v = 0; v < V; ++v)
       reinterpret_cast<uint4*>(in)[v] = reinterpret_cast<const uint4*>(y + i0)[v];
+    unsigned bits = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = c0 + k;
       float v = to_f<T>(in[k]) * scale[c] + shift[c];
+      bits |= (v > 0.f ? 1u : 0u) << k;
       v = act_fwd(v, act);
       if (dropscale) v *= dropscale[(long long)n * C + c];
       out[k] = from_f<T>(v);
@@ -66,6 +68,7 @@ __global__ void bn_act_apply_kernel(const T* __restrict__ y, T* __restrict__ a, 
 #pragma unroll
     for (int v = 0; v < V; ++v)
       reinterpret_cast<uint4*>(a + i0)[v] = reinterpret_cast<uint4*>(out)[v];
+    if (actmask) actmask[i0 >> 3] = (unsigned char)bits;   // sign bits of the activation input (yg_fwd_epilogue.actmask)
   } else {
     for (long long i = i0; i < i0 + 8 && i < total; ++i) {
       const int c = (int)(i % C);
@@ -123,6 +126,55 @@ __global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, 
   }
 }
 
+// Per-channel sums over an NHWC tensor with 16-byte loads: MODE 0: sum(y), sum(y*y) (BatchNorm batch statistics);
+// MODE 1: sum(g), sum(g * xhat) with xhat = (y - mean) * invstd (BatchNorm backward).  One streaming pass at HBM speed
+// (cheaper than a 31-shuffle transpose-reduce per 16-column chunk in the epilogue of the producing convolution).
+// Thread t owns the 8-channel group t % (C/8) and pixels t / (C/8) + k * stride.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bn_colsums_kernel(const T* __restrict__ a, const T* __restrict__ y, long long npix, int C,
+                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                         double* __restrict__ sums) {
+  extern __shared__ float red[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int groups = C / 8;
+  const int lanes = blockDim.x / groups;           // pixel lanes per block
+  const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float s1[8], s2[8], mu[8], is[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s1[k] = 0.f; s2[k] = 0.f;
+    mu[k] = (MODE == 1) ? mean[cg * 8 + k] : 0.f;
+    is[k] = (MODE == 1) ? invstd[cg * 8 + k] : 1.f;
+  }
+  if (pl < lanes) {
+    constexpr int V = (int)(sizeof(T) * 8 / 16);
+    for (long long px = (long long)blockIdx.x * lanes + pl; px < npix; px += (long long)gridDim.x * lanes) {
+      __align__(16) T av[8];
+      __align__(16) T yv[8];
+      const long long off = px * C + cg * 8;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        reinterpret_cast<uint4*>(av)[v] = __ldg(reinterpret_cast<const uint4*>(a + off) + v);
+        if (MODE == 1) reinterpret_cast<uint4*>(yv)[v] = __ldg(reinterpret_cast<const uint4*>(y + off) + v);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float x = to_f<T>(av[k]);
+        s1[k] += x;
+        s2[k] += (MODE == 0) ? x * x : x * ((to_f<T>(yv[k]) - mu[k]) * is[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&red[cg * 8 + k], s1[k]);
+      atomicAdd(&red[C + cg * 8 + k], s2[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)red[i]);
+}
+
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* dgamma, float* dbeta, int C, float clip) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -156,17 +208,50 @@ extern "C" int yg_bn_fold_eval(const float* gamma, const float* beta, const floa
 
 extern "C" int yg_bn_act_apply(const void* y, void* a, int dtype, int N, int HW, int C,
                                const float* scale, const float* shift, int act, const float* dropscale,
-                               void* stream) {
+                               void* actmask, void* stream) {
   YG_CHECK_ARG(y && a && scale && shift, "bn_act_apply: null pointer");
+  YG_CHECK_ARG(!actmask || (C & 7) == 0, "bn_act_apply: actmask needs C % 8 == 0");
   const long long total = (long long)N * HW * C;
   if (total == 0) return YG_OK;
   const int blocks = cdiv(cdiv(total, 8), 256);
   if (dtype == YG_BF16)
-    bn_act_apply_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, total, HW, C, scale, shift, act, dropscale);
+    bn_act_apply_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, total, HW, C, scale, shift, act, dropscale, (unsigned char*)actmask);
   else
-    bn_act_apply_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)y, (float*)a, total, HW, C, scale, shift, act, dropscale);
+    bn_act_apply_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)y, (float*)a, total, HW, C, scale, shift, act, dropscale, (unsigned char*)actmask);
   YG_LAUNCH_CHECK("bn_act_apply");
   return YG_OK;
+}
+
+static int bn_colsums(const void* a, const void* y, int dtype, long long npix, int C, const float* mean, const float* invstd,
+                      double* sums, int mode, cudaStream_t st) {
+  YG_CHECK_ARG(C % 8 == 0 && C / 8 <= 256, "bn sums: C must be a multiple of 8 and <= 2048, got %d", C);
+  if (npix == 0) return YG_OK;
+  const int lanes = 256 / (C / 8);
+  long long want = (npix + lanes - 1) / lanes;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  const size_t sm = (size_t)2 * C * sizeof(float);
+  if (dtype == YG_BF16) {
+    if (mode == 0) bn_colsums_kernel<bf16, 0><<<blocks, 256, sm, st>>>((const bf16*)a, nullptr, npix, C, nullptr, nullptr, sums);
+    else bn_colsums_kernel<bf16, 1><<<blocks, 256, sm, st>>>((const bf16*)a, (const bf16*)y, npix, C, mean, invstd, sums);
+  } else {
+    if (mode == 0) bn_colsums_kernel<float, 0><<<blocks, 256, sm, st>>>((const float*)a, nullptr, npix, C, nullptr, nullptr, sums);
+    else bn_colsums_kernel<float, 1><<<blocks, 256, sm, st>>>((const float*)a, (const float*)y, npix, C, mean, invstd, sums);
+  }
+  YG_LAUNCH_CHECK("bn_colsums");
+  return YG_OK;
+}
+
+extern "C" int yg_bn_stats(const void* y, int dtype, int N, int HW, int C, double* stats, void* stream) {
+  YG_CHECK_ARG(y && stats, "bn_stats: null pointer");
+  YG_CHECK_ARG(dtype == YG_F32 || dtype == YG_BF16, "bn_stats: dtype %d", dtype);
+  return bn_colsums(y, nullptr, dtype, (long long)N * HW, C, nullptr, nullptr, stats, 0, (cudaStream_t)stream);
+}
+
+extern "C" int yg_bn_bwd_sums(const void* g, const void* y, int dtype, int N, int HW, int C, const float* mean,
+                              const float* invstd, double* sums, void* stream) {
+  YG_CHECK_ARG(g && y && mean && invstd && sums, "bn_bwd_sums: null pointer");
+  YG_CHECK_ARG(dtype == YG_F32 || dtype == YG_BF16, "bn_bwd_sums: dtype %d", dtype);
+  return bn_colsums(g, y, dtype, (long long)N * HW, C, mean, invstd, sums, 1, (cudaStream_t)stream);
 }
 
 extern "C" int yg_bn_bwd_apply(void* g, const void* y, int dtype, int N, int HW, int C,

@@ -248,7 +248,10 @@ class Runner:
                             L.check(lib.yg_conv_first_stats_from_gram(gram.data_ptr(), wt.data_ptr(), L.ptr(bias),
                                                                       float(N * ho * wo), blk.cout, stats.data_ptr(), st))
                         else:
-                            conv(_fwd_ep(shift=bias, stats=stats), y_raw)  # pass 1: conv (+bias) and statistics
+                            # pass 1: conv (+bias) with the plain epilogue, then one streaming pass for sum / sum of squares
+                            # (cheaper than reducing inside the tensor-core epilogue, and keeps the MMAs at full rate)
+                            conv(_fwd_ep(shift=bias), y_raw)
+                            L.check(lib.yg_bn_stats(y_raw.data_ptr(), dcode, N, ho * wo, blk.cout, stats.data_ptr(), st))
                         L.check(lib.yg_bn_finalize(stats.data_ptr(), float(N * ho * wo), g.data_ptr(), b.data_ptr(),
                                                    bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                                    float(bn.momentum), float(bn.eps), mean.data_ptr(),
@@ -271,8 +274,12 @@ class Runner:
                         conv(_fwd_ep(scale=scale, shift=sh2, act=blk.act, dropscale=ds), out)
                         rec["fwd_shift"] = bias
                     else:
+                        mask = None
+                        if want_grad and blk.act == L.ACT_LRELU and blk.cout % 32 == 0 and dt == torch.bfloat16:
+                            mask = torch.empty(N * ho * wo * blk.cout // 8, dtype=torch.uint8, device=dev)
                         L.check(lib.yg_bn_act_apply(y_raw.data_ptr(), out.data_ptr(), dcode, N, ho * wo, blk.cout,
-                                                    scale.data_ptr(), shift.data_ptr(), blk.act, L.ptr(ds), st))
+                                                    scale.data_ptr(), shift.data_ptr(), blk.act, L.ptr(ds), L.ptr(mask), st))
+                        rec["actmask"] = mask
                     rec.update(saved=y_raw, mean=mean, invstd=invstd, scale=scale, shift=shift, gamma=g)
             rec["out"] = out
             saved["blocks"].append(rec)
@@ -329,7 +336,12 @@ class Runner:
             if rec["first_direct"]:
                 return None, None  # handled inside yg_conv_first_bwd (recomputation)
             sums = None
-            if blk.bn is not None:
+            if blk.bn is not None and rec.get("actmask") is not None:
+                # LeakyReLU after BatchNorm with a recorded sign mask: the producer only applies the activation backward
+                # (sign(out) = sign(BN output)); sum(g), sum(g*xhat) come from one streaming pass (yg_bn_bwd_sums)
+                ep = L.BwdEpilogue(rec["out"].data_ptr(), blk.act, L.ptr(rec["dropscale"]), None, None, None, None, None,
+                                   rec["actmask"].data_ptr())
+            elif blk.bn is not None:
                 sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
                 ep = L.BwdEpilogue(rec["saved"].data_ptr(), blk.act, L.ptr(rec["dropscale"]),
                                    rec["scale"].data_ptr(), rec["shift"].data_ptr(), rec["mean"].data_ptr(),
@@ -436,6 +448,10 @@ class Runner:
             if blk.bn is not None:
                 dgam = gbuf(blk.bn.weight)
                 dbet = gbuf(blk.bn.bias)
+                if sums is None:
+                    sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                    L.check(lib.yg_bn_bwd_sums(g.data_ptr(), rec["saved"].data_ptr(), dcode, N, ho * wo, blk.cout,
+                                               rec["mean"].data_ptr(), rec["invstd"].data_ptr(), sums.data_ptr(), st))
                 L.check(lib.yg_bn_bwd_apply(g.data_ptr(), rec["saved"].data_ptr(), dcode, N, ho * wo, blk.cout,
                                             sums.data_ptr(), rec["gamma"].data_ptr(), rec["mean"].data_ptr(),
                                             rec["invstd"].data_ptr(), dgam.data_ptr(), dbet.data_ptr(), clip,
