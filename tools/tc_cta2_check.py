@@ -45,3 +45,27 @@ for (N, H, W, Cin, Cout) in [(1, 16, 16, 128, 128), (2, 19, 35, 128, 128), (3, 3
     a, p2 = res["one"], res["pair"]
     print({"shape": (N, H, W, Cin, Cout), "fwd_maxdiff": (a[0] - p2[0]).abs().max().item(), "dgrad_maxdiff": (a[1] - p2[1]).abs().max().item(),
            "ms_one": a[3], "ms_pair": p2[3]}, flush=True)
+
+# stride-2 forward as CTA pairs (four parity boxes per K chunk)
+for (N, H, W, Cin, Cout) in [(2, 21, 37, 128, 128), (64, 193, 258, 128, 128)]:
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(N, H, W, Cin, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    outs = {}
+    for name, opt in (("one", OPT1), ("pair", OPT2)):
+        lib.yg_set_tc_options(opt)
+        y = torch.zeros(N, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
+        ep = L.FwdEpilogue(None, None, 1, None, None, None, None)
+        L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, 2, C.byref(ep), L.stream()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, 2, C.byref(ep), L.stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        outs[name] = (y.float(), round(e0.elapsed_time(e1) / 3, 4))
+    lib.yg_set_tc_options(OPT2)
+    print({"shape_s2": (N, H, W, Cin, Cout), "fwd_maxdiff": (outs["one"][0] - outs["pair"][0]).abs().max().item(),
+           "ms_one": outs["one"][1], "ms_pair": outs["pair"][1]}, flush=True)

@@ -2124,8 +2124,8 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   bool two_d = two_d1;
   // weights too large to stay resident in one CTA: a CTA pair keeps half of every weight tile each (cta_group::2)
   bool cta2 = false;
-  if (!two_d && (g_tc_options & 16384) && stride == 1 && Cout == BN && BN % 32 == 0 && pick_kc(Cin) == 64 &&
-      two_d_fits(Cin, BN / 2, 1, 9, (T2_TH + 2) * (T2_TW + 2), 1, &kc2))
+  if (!two_d && (g_tc_options & 16384) && Cout == BN && BN % 32 == 0 && pick_kc(Cin) == 64 &&
+      two_d_fits(Cin, BN / 2, 1, 9, stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1), stride == 1 ? 1 : 4, &kc2))
     two_d = cta2 = true;
   const int KCc = two_d ? kc2 : fit_kc(Cin, BN, max_rows);
   if (!KCc) { set_error("conv_fwd_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
