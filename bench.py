@@ -369,11 +369,11 @@ def roofline_from_breakdown(breakdown, calls_per_step, args, B):
         pad = k // 2
         Ho, Wo = (Hh + 2 * pad - k) // s + 1, (Ww + 2 * pad - k) // s + 1
         flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
-        # algorithmic bytes: every activation tensor the op must touch once (bf16); dgrad also reads the saved
-        # activation of the previous layer for the fused activation backward
+        # algorithmic bytes: every activation tensor the op must touch once (bf16); dgrad also reads what the fused
+        # activation backward of the previous layer needs
         nbytes = 2.0 * (N * Hh * Ww * Cin + N * Ho * Wo * Cout)
         if top.startswith("yg_conv_dgrad["):
-            nbytes += 2.0 * N * Hh * Ww * Cin
+            nbytes += N * Hh * Ww * Cin / 8.0   # + the 1-bit-per-element activation sign mask of the previous layer
         balance = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
         if flops / nbytes >= balance:
             ach = flops / (ms * 1e-3) / 1e12
@@ -385,6 +385,24 @@ def roofline_from_breakdown(breakdown, calls_per_step, args, B):
         return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"] + " (copy bandwidth)",
                 "ms_per_launch": ms, "algorithmic_bytes": nbytes, "flop_per_byte": flops / nbytes}
+    # the other kernels of the step stream their operands once: algorithmic bytes per launch at the bench geometry
+    H, W = 772, 1032
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    px1, px7 = B * Ho * Wo, B * 97 * 129
+    stream_bytes = {
+        "yg_conv_first_fwd": B * H * W + px1 * 16 * 2,              # uint8 image in, 16-channel bf16 out
+        "yg_conv_first_bwd": B * H * W + px1 * 16 * 2,              # image + d(activation) in, 16x9 sums out
+        "yg_conv_first_gram": B * H * W,
+        "yg_bn_act_apply": 2 * px7 * 128 * 2 + px7 * 16,            # y_raw in, activation + sign mask out
+        "yg_bn_bwd_apply": 3 * px7 * 128 * 2,                       # g, y_raw in, dz out
+        "yg_bn_bwd_sums": 2 * px7 * 128 * 2,
+        "yg_bn_stats": px7 * 128 * 2,
+    }
+    if top in stream_bytes:
+        ach = stream_bytes[top] / (ms * 1e-3) / 1e9
+        return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"] + " (copy bandwidth)",
+                "ms_per_launch": ms, "algorithmic_bytes": float(stream_bytes[top])}
     return {"kernel": top, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
             "traffic": traffic, "ms_per_launch": ms, "peak_source": peaks["source"]}
 

@@ -521,6 +521,162 @@ __global__ void __launch_bounds__(FL_THREADS, CO == 8 ? 3 : 2) first_bwd16_kerne
   if (threadIdx.x < CO) base[9 * FF_CO + co0 + threadIdx.x] = red[9 * CO + threadIdx.x];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight-gradient pass of the first layer on the (legacy, warp-level) tensor cores - uint8 image, 1 -> 16 channels, the
+// "raw P / Sg" mode of the Gram-matrix backward (dy_mean == NULL).  Per warp and 32 pixels (thread = pixel for the loads):
+//   X[px][16]  = the 9 taps of the pixel as bf16 (exact for uint8), a column of ones, zero padding        -> shared memory
+//   DA[px][16] = d(activation), bf16                                                                        -> shared memory
+//   acc^T[ch][px] = (W_hi + W_lo) . X^T        two mma.m16n8k16 per 8 pixels: the stencil recomputed with split-bf16
+//                                              weights (|error| ~ 2^-17 relative, the sign of the pre-activation is safe)
+//   g[ch][px]  = DA * act'(BN(acc)) * dropscale                      in the accumulator fragment layout ...
+//   P[ch][tap] += g . X                        ... which is exactly the A fragment layout of the second mma (k = pixels);
+//                                              the ones column makes P[:, 9] = sum(g)
+// ~6 warp instructions per pixel instead of ~17 of the SIMT kernel; 8 accumulator registers instead of 9 x 16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void hmma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+constexpr int FM_WARPS = 4;
+
+__global__ void __launch_bounds__(FM_WARPS * 32, 8) first_bwd_mma_kernel(
+    const uint8_t* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ da, int H, int W, int Ho, int Wo,
+    int stride, BwdEpi be, const float* __restrict__ fwd_shift, float* __restrict__ partial, int chunk, int cpi, int ntasks) {
+  __shared__ __align__(128) unsigned char tiles[FM_WARPS][2][32 * 32];   // per warp: X and DA tiles, 32 B per pixel row
+  __shared__ float red[10 * FF_CO];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  for (int i = threadIdx.x; i < 10 * FF_CO; i += FM_WARPS * 32) red[i] = 0.f;
+  // A fragments of the weights, split into two bf16 terms: A[m = ch][k = tap] (taps >= 9 are zero)
+  uint32_t whi[4], wlo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ch = g + (q & 1) * 8, t0 = 2 * j + (q >> 1) * 8;
+    float hi[2], lo[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float v = (t0 + e < 9) ? w[ch * 9 + t0 + e] : 0.f;
+      hi[e] = __bfloat162float(__float2bfloat16_rn(v));
+      lo[e] = v - hi[e];
+    }
+    whi[q] = pack_bf16(hi[0], hi[1]);
+    wlo[q] = pack_bf16(lo[0], lo[1]);
+  }
+  // per-channel constants of this thread's two channels (g, g + 8)
+  float c_fsh[2], c_scl[2], c_sft[2], c_ds[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int ch = g + e * 8;
+    c_fsh[e] = fwd_shift ? fwd_shift[ch] : 0.f;
+    c_scl[e] = be.bn_scale ? be.bn_scale[ch] : 1.f;
+    c_sft[e] = be.bn_shift ? be.bn_shift[ch] : 0.f;
+    c_ds[e] = 1.f;
+  }
+  const int act = be.act;
+  float P0[4] = {0.f, 0.f, 0.f, 0.f}, P1[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned char* xt = tiles[warp][0];
+  unsigned char* dt = tiles[warp][1];
+  const uint32_t xt_s = (uint32_t)__cvta_generic_to_shared(xt), dt_s = (uint32_t)__cvta_generic_to_shared(dt);
+  // this lane's row addresses for the three ldmatrix.x4 patterns (see the header comment); rows 4..7 of every group of 8
+  // keep their two 16-byte halves swapped so that 8 consecutive rows hit 8 different bank groups
+  const int lm = lane >> 3, lr = lane & 7;
+  auto row_addr = [](uint32_t base, int px, int half) { return base + (uint32_t)(px * 32 + ((half ^ ((px >> 2) & 1)) << 4)); };
+  __syncthreads();
+  const int npix = Ho * Wo;
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
+    const int p1 = min(p0 + chunk, npix);
+    if (be.dropscale) {
+      c_ds[0] = be.dropscale[(long long)n * FF_CO + g];
+      c_ds[1] = be.dropscale[(long long)n * FF_CO + g + 8];
+    }
+    const uint8_t* xim = x + (long long)n * H * W;
+    const bf16* dim = da + (long long)n * npix * FF_CO;
+    PixCursor cur;
+    cur.init(p0 + warp * 32 + lane, Wo);
+    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
+      // ---- stage the 32 pixels of this warp: thread = pixel
+      {
+        float v[9];
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        if (cur.p < p1) {
+          load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
+          const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)cur.p * FF_CO);
+          d0 = __ldg(gp); d1 = __ldg(gp + 1);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) v[t] = 0.f;
+        }
+        const uint4 x0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        const uint4 x1 = make_uint4(pack_bf16(v[8], 1.f), 0u, 0u, 0u);   // tap 8, the ones column, zero padding
+        const int sw = (lane >> 2) & 1;
+        __syncwarp();   // the previous iteration's ldmatrix reads are done
+        *reinterpret_cast<uint4*>(xt + lane * 32 + ((0 ^ sw) << 4)) = x0;
+        *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ sw) << 4)) = x1;
+        *reinterpret_cast<uint4*>(dt + lane * 32 + ((0 ^ sw) << 4)) = d0;
+        *reinterpret_cast<uint4*>(dt + lane * 32 + ((1 ^ sw) << 4)) = d1;
+        __syncwarp();
+      }
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {   // two blocks of 16 pixels
+        uint32_t b1[4], b2[4], dd[4];
+        ldsm_x4(b1, row_addr(xt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));      // MMA1 B: (k = taps, n = pixels), tiles 0 / 1
+        ldsm_x4_t(b2, row_addr(xt_s, kb * 16 + (lm & 1) * 8 + lr, lm >> 1));    // MMA2 B: (k = pixels, n = taps 0-7 / 8-15)
+        ldsm_x4_t(dd, row_addr(dt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));    // DA in the accumulator layout, tiles 0 / 1
+        uint32_t a2[4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {    // two tiles of 8 pixels
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          hmma16816(c, whi, b1[2 * t], b1[2 * t + 1]);
+          hmma16816(c, wlo, b1[2 * t], b1[2 * t + 1]);
+          float gv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int hc = e >> 1;                       // channel g (0) or g + 8 (1); pixel 2j + (e & 1) of the tile
+            const float yv = c[e] + c_fsh[hc];
+            const float pre = be.bn_scale ? yv * c_scl[hc] + c_sft[hc] : yv;
+            const uint32_t dword = dd[2 * t + hc];
+            const float dav = __uint_as_float((e & 1) ? (dword & 0xFFFF0000u) : (dword << 16));
+            gv[e] = dav * act_grad(pre, act) * c_ds[hc];
+          }
+          a2[2 * t] = pack_bf16(gv[0], gv[1]);
+          a2[2 * t + 1] = pack_bf16(gv[2], gv[3]);
+        }
+        hmma16816(P0, a2, b2[0], b2[1]);
+        hmma16816(P1, a2, b2[2], b2[3]);
+      }
+    }
+  }
+  // P fragment: (ch g, taps 2j, 2j+1), (ch g+8, same); second tile: taps 8 + 2j .. -> tap 8 and the sum(g) column
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int ch = g + (e >> 1) * 8, t = 2 * j + (e & 1);
+    atomicAdd(&red[ch * 9 + t], P0[e]);
+    if (j == 0) {
+      if ((e & 1) == 0) atomicAdd(&red[ch * 9 + 8], P1[e]);
+      else atomicAdd(&red[9 * FF_CO + ch], P1[e]);
+    }
+  }
+  __syncthreads();
+  float* base = partial + (long long)blockIdx.x * (10 * FF_CO);
+  for (int i = threadIdx.x; i < 10 * FF_CO; i += FM_WARPS * 32) base[i] = red[i];
+}
+
 constexpr int FL_BWD_BLOCKS = 592;
 
 }  // namespace yg
@@ -587,6 +743,18 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
       set_error("conv_first_bwd: workspace %zu < %zu", workspace_bytes, need);
       return YG_ERR_WORKSPACE;
     }
+  }
+  if (mode == 1 && Cin == 1 && Cout == FF_CO && dtype == YG_BF16 && x_dtype == YG_U8 && !bn_dy_mean && Wo >= 32 &&
+      (long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31) && yg_get_conv_impl() != YG_IMPL_SIMT) {
+    // raw P / Sg pass on the tensor cores (first_bwd_mma_kernel)
+    const int chunk = 64 * FM_WARPS * 32, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
+    const int grid1 = ntasks < FL_BWD_BLOCKS ? ntasks : FL_BWD_BLOCKS;
+    first_bwd_mma_kernel<<<grid1, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be,
+                                                          fwd_shift, (float*)workspace, chunk, cpi, ntasks);
+    YG_LAUNCH_CHECK("conv_first_bwd_mma");
+    wgrad_reduce_kernel2<<<cdiv(nw + Cout, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, grid1, clip);
+    YG_LAUNCH_CHECK("conv_first_bwd reduce");
+    return YG_OK;
   }
   if (mode == 1 && Cin == 1 && Cout == FF_CO && dtype == YG_BF16 && (long long)Ho * Wo < (1LL << 30) &&
       (long long)H * W < (1LL << 31)) {
