@@ -13,6 +13,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 import statistics
 import subprocess
 import sys
