@@ -1643,17 +1643,20 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
 // partials [cta][128]  (cta = unit + nunits * slice, unit = s + ncols * (mtile + n_mtiles * ntile))
 __global__ void wgrad_bias_reduce_kernel(const float* __restrict__ part, float* __restrict__ dbias, int Cout, int g,
                                          int ncols, int n_mtiles, int nunits, int grid, float clip) {
-  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per output channel: the lanes stride over the CTAs (independent loads in flight), then a shuffle reduction
+  const int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (co >= Cout) return;
   float acc = 0.f;
-  for (int b = 0; b < grid; ++b) {
+  for (int b = lane; b < grid; b += 32) {
     const int mt = ((b % nunits) / ncols) % n_mtiles;
     for (int q = 0; q < g; ++q) {
       const int cof = q * Cout + co;
       if (cof / 128 == mt) acc += part[(size_t)b * 128 + cof % 128];
     }
   }
-  dbias[co] = clampf(acc, clip);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) dbias[co] = clampf(acc, clip);
 }
 
 // Sums the per-CTA partials in a fixed order.  The kernel ran on (possibly W-folded) dimensions Coutf = g*Cout,
@@ -1860,7 +1863,7 @@ const int prodw = (kb <= 32 && nst >= 3 && (g_tc_options & 2)) ? 1 : 0;
                                                         p.nunits, p.nslices, clip);
   YG_LAUNCH_CHECK("wgrad_tc_reduce");
   if (bias_col) {
-    wgrad_bias_reduce_kernel<<<cdiv(Cout_r, 128), 128, 0, st>>>(p.bias_partial, dbias, Cout_r, fg, p.ncols, p.n_mtiles, p.nunits, grid, clip);
+    wgrad_bias_reduce_kernel<<<cdiv(Cout_r * 32, 256), 256, 0, st>>>(p.bias_partial, dbias, Cout_r, fg, p.ncols, p.n_mtiles, p.nunits, grid, clip);
     YG_LAUNCH_CHECK("wgrad_bias_reduce");
   } else if (dbias) {
     float* part = (float*)((char*)ws + (size_t)grid * 3 * 128 * p.BNW * sizeof(float));

@@ -239,11 +239,16 @@ __global__ void __launch_bounds__(FL_THREADS, 4) conv_first_bwd_kernel(
 
 __global__ void wgrad_reduce_kernel2(const float* __restrict__ partial, float* __restrict__ dw,
                                      float* __restrict__ dbias, long long nw, int Cout, int slices, float clip) {
+  // one warp per element (the first layer has 160 of them and ~600 slices): lanes stride over the slices
   const long long stride_slice = nw + Cout;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= nw + Cout) return;
   float s = 0.f;
-  for (int k = 0; k < slices; ++k) s += partial[k * stride_slice + i];
+  for (int k = lane; k < slices; k += 32) s += partial[k * stride_slice + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
   s = clampf(s, clip);
   if (i < nw) dw[i] = s;
   else if (dbias) dbias[i - nw] = s;
@@ -752,7 +757,7 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
     first_bwd_mma_kernel<<<grid1, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be,
                                                           fwd_shift, (float*)workspace, chunk, cpi, ntasks);
     YG_LAUNCH_CHECK("conv_first_bwd_mma");
-    wgrad_reduce_kernel2<<<cdiv(nw + Cout, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, grid1, clip);
+    wgrad_reduce_kernel2<<<cdiv((nw + Cout) * 32, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, grid1, clip);
     YG_LAUNCH_CHECK("conv_first_bwd reduce");
     return YG_OK;
   }
@@ -768,7 +773,7 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
       first_bwd16_kernel<float, 8><<<gridf, FL_THREADS, 0, st>>>((const float*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be,
                                                                  fwd_shift, bn_dy_mean, bn_dyx_mean, (float*)workspace, chunk, cpi, ntasks);
     YG_LAUNCH_CHECK("conv_first_bwd16");
-    wgrad_reduce_kernel2<<<cdiv(nw + Cout, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, grid1, clip);
+    wgrad_reduce_kernel2<<<cdiv((nw + Cout) * 32, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, grid1, clip);
     YG_LAUNCH_CHECK("conv_first_bwd reduce");
     return YG_OK;
   }
@@ -781,7 +786,7 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
 #undef LAUNCH
   YG_LAUNCH_CHECK("conv_first_bwd");
   if (mode == 1) {
-    wgrad_reduce_kernel2<<<cdiv(nw + Cout, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, blocks, clip);
+    wgrad_reduce_kernel2<<<cdiv((nw + Cout) * 32, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, blocks, clip);
     YG_LAUNCH_CHECK("conv_first_bwd reduce");
   }
   return YG_OK;

@@ -355,6 +355,17 @@ __global__ void head_reduce_kernel(const float* __restrict__ partial, float* __r
   else if (dbias) dbias[i - nw] = s;
 }
 
+// sum over the per-block partials [slices][D] of one element per warp (lanes stride over the slices)
+__global__ void head_bias_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dbias, int D, int slices, float clip) {
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int k = lane; k < slices; k += 32) s += partial[(long long)k * D + d];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dbias[d] = clampf(s, clip);
+}
+
 constexpr int HD_BWD_BLOCKS = 296;
 constexpr int HD_DP = 32;          // channels of the padded bf16 logit-gradient tensor fed to the tensor cores
 constexpr int HD_DT_BLOCKS = 592;
@@ -502,7 +513,7 @@ extern "C" int yg_head_bwd(const float* dpred, const float* t_raw, const void* x
     head_dt_kernel<<<nb, 256, 0, st>>>(dpred, t_raw, dt, dbp, npix, Sy, Sx, D, anchor_w, anchor_h, width_mult, height_mult);
     YG_LAUNCH_CHECK("head_dt");
     if (dbias) {
-      head_reduce_kernel<<<1, 256, 0, st>>>(dbp, nullptr, dbias, 0, D, nb, clip);
+      head_bias_reduce_kernel<<<cdiv(D * 32, 256), 256, 0, st>>>(dbp, dbias, D, nb, clip);
       YG_LAUNCH_CHECK("head_bias_reduce");
     }
     return head_bwd_tc(dt, x, w, dx, dw, N, Sy, Sx, Cin, D, be, clip, (char*)workspace + off_wg,
