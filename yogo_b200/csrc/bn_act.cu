@@ -134,9 +134,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) bn_colsums_kernel(const T* __restrict__ a, const T* __restrict__ y, long long npix, int C,
                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                                          double* __restrict__ sums) {
-  extern __shared__ float red[];   // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float red[];   // [lanes][2][C]: one row per pixel lane, summed in a fixed order in fp64
   const int groups = C / 8;
   const int lanes = blockDim.x / groups;           // pixel lanes per block
   const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
@@ -167,12 +165,16 @@ __global__ void __launch_bounds__(256) bn_colsums_kernel(const T* __restrict__ a
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&red[cg * 8 + k], s1[k]);
-      atomicAdd(&red[C + cg * 8 + k], s2[k]);
+      red[(size_t)pl * 2 * C + cg * 8 + k] = s1[k];
+      red[(size_t)pl * 2 * C + C + cg * 8 + k] = s2[k];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)red[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += (double)red[(size_t)l * 2 * C + i];
+    atomicAdd(&sums[i], acc);
+  }
 }
 
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* dgamma, float* dbeta, int C, float clip) {
@@ -229,7 +231,7 @@ static int bn_colsums(const void* a, const void* y, int dtype, long long npix, i
   const int lanes = 256 / (C / 8);
   long long want = (npix + lanes - 1) / lanes;
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-  const size_t sm = (size_t)2 * C * sizeof(float);
+  const size_t sm = (size_t)lanes * 2 * C * sizeof(float);   // <= 256/(C/8) * 2C * 4 = 16 KB
   if (dtype == YG_BF16) {
     if (mode == 0) bn_colsums_kernel<bf16, 0><<<blocks, 256, sm, st>>>((const bf16*)a, nullptr, npix, C, nullptr, nullptr, sums);
     else bn_colsums_kernel<bf16, 1><<<blocks, 256, sm, st>>>((const bf16*)a, (const bf16*)y, npix, C, mean, invstd, sums);
