@@ -498,3 +498,16 @@ def test_trainer_step_matches_torch_adamw_and_graph_replay():
             torch.testing.assert_close(p.detach(), rp.detach(), rtol=2e-5, atol=2e-7)
     assert tr_b.graph_launches > 20
     assert int(net_a.model[0][1].num_batches_tracked) == int(net_b.model[0][1].num_batches_tracked) == 3
+
+
+def test_device_prefetcher_yields_batches_in_order():
+    """DevicePrefetcher (the pin_memory + non_blocking loader pattern of train.py:288-291): every batch arrives, in
+    order, bit-identical, while the next copy is already in flight."""
+    from yogo_b200.train import DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    host = [(torch.randint(0, 255, (2, 1, 32, 48), generator=g, dtype=torch.uint8).pin_memory(),
+             torch.rand(2, 6, 4, 6, generator=g).pin_memory()) for _ in range(5)]
+    got = [(x.cpu(), y.cpu()) for x, y in DevicePrefetcher(iter(host), DEV)]
+    assert len(got) == len(host)
+    for (hx, hy), (dx, dy) in zip(host, got):
+        assert torch.equal(hx, dx) and torch.equal(hy, dy)

@@ -251,3 +251,44 @@ class DataParallelTrainer:
         self._static_labels.copy_(labels, non_blocking=True)
         self._graph.replay()
         return self._graph_loss
+
+
+class DevicePrefetcher:
+    """Feeds pinned host batches to the GPU one step ahead of the consumer (what `DataLoader(pin_memory=True)` +
+    `.to(device, non_blocking=True)` does in the reference's training loop, train.py:288-291, made explicit): the
+    host->device copy of batch i+1 runs on a side stream while step i computes, so the copy leaves the critical path.
+    Iterating yields `(images, labels)` device tensors that are safe to use on the current stream."""
+
+    def __init__(self, batches, device):
+        self.batches = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._next = None
+        self._fetch()
+
+    def _fetch(self):
+        try:
+            img, lab = next(self.batches)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            x = img.to(self.device, non_blocking=True)
+            y = lab.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._next = (x, y, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        x, y, ev = self._next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        x.record_stream(cur)
+        y.record_stream(cur)
+        self._fetch()   # the next copy overlaps with the step the caller is about to run
+        return x, y
