@@ -69,3 +69,29 @@ for (N, H, W, Cin, Cout) in [(2, 21, 37, 128, 128), (64, 193, 258, 128, 128)]:
     lib.yg_set_tc_options(OPT2)
     print({"shape_s2": (N, H, W, Cin, Cout), "fwd_maxdiff": (outs["one"][0] - outs["pair"][0]).abs().max().item(),
            "ms_one": outs["one"][1], "ms_pair": outs["pair"][1]}, flush=True)
+
+# stride-2 dgrad as CTA pairs (four parity classes, class-per-round tile order)
+for (N, H, W, Cin, Cout) in [(2, 21, 37, 128, 128), (3, 20, 28, 128, 128), (64, 193, 258, 128, 128)]:
+    g = torch.Generator().manual_seed(3)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(dev).bfloat16()
+    xs = torch.randn(N, H, W, Cin, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev)
+    outs = {}
+    for name, opt in (("one", OPT1), ("pair", OPT2)):
+        lib.yg_set_tc_options(opt)
+        dx = torch.full((N, H, W, Cin), float("nan"), device=dev, dtype=torch.bfloat16)
+        be = L.BwdEpilogue(xs.data_ptr(), 1, None, None, None, None, None, None, None)
+        L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, 2, C.byref(be), L.stream()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, 2, C.byref(be), L.stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        outs[name] = (dx.float(), round(e0.elapsed_time(e1) / 3, 4))
+    lib.yg_set_tc_options(OPT2)
+    d = (outs["one"][0] - outs["pair"][0]).abs()
+    print({"dgrad_s2": (N, H, W, Cin, Cout), "maxdiff": d.max().item(), "nan": int(torch.isnan(outs["pair"][0]).sum()),
+           "ms_one": outs["one"][1], "ms_pair": outs["pair"][1]}, flush=True)

@@ -62,6 +62,10 @@ struct TcParams {
   int cta2;                         // CTA pairs (cta_group::2): M = 256 per MMA, each CTA holds BN/2 rows of every weight tile
   int ncls, cls_rot;                // classes and the rotation period max(1, grid / ncls) (see tile_class)
   unsigned long long fd_ncls, fd_rot, fd_nnt, fd_tw, fd_th;   // ceil(2^32 / d): division by multiply-high (decode_tile)
+  // class-per-round tile order (CTA pairs with parity classes): round k of the persistent grid works on class k % ncls
+  // for every CTA (a pair always shares its class, sibling classes of a spatial tile run in consecutive rounds)
+  int cls_round, grid, tpc;           // flag, grid size, tiles per class
+  unsigned long long fd_grid;
   TcClass cls[4];
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
@@ -105,15 +109,30 @@ __device__ __forceinline__ int fdiv(int n, unsigned long long m) {   // n / d fo
 }
 __device__ __forceinline__ int tile_class(const TcParams& p, int tile) {
   if (p.ncls == 1) return 0;
+  if (p.cls_round) {
+    const int round = fdiv(tile, p.fd_grid);
+    return round - fdiv(round, p.fd_ncls) * p.ncls;
+  }
   const int sp = fdiv(tile, p.fd_ncls), c = tile - sp * p.ncls;
   const int x = c + fdiv(sp, p.fd_rot);
   return x - fdiv(x, p.fd_ncls) * p.ncls;
 }
 // tile index -> (class, N tile, tile column, tile row, image); the class is the fastest index.  Division by multiply-high:
-// every role decodes every tile, and four runtime integer divisions cost several hundred cycles of a single warp
+// every role decodes every tile, and four runtime integer divisions cost several hundred cycles of a single warp.
+// Padding tiles (CTA pairs, class-per-round order) decode to n >= N: all their loads are out of bounds (zero fill) and
+// the epilogue stores nothing.
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& tw, int& th, int& n) {
-  cls = tile_class(p, tile);
-  int t = fdiv(tile, p.fd_ncls);
+  int t;
+  if (p.cls_round) {
+    const int round = fdiv(tile, p.fd_grid), b = tile - round * p.grid;
+    const int rc = fdiv(round, p.fd_ncls);
+    cls = round - rc * p.ncls;
+    t = rc * p.grid + b;                       // spatial index inside the class
+    if (t >= p.tpc) { nt = 0; tw = 0; th = 0; n = p.N; return; }
+  } else {
+    cls = tile_class(p, tile);
+    t = fdiv(tile, p.fd_ncls);
+  }
   int q = fdiv(t, p.fd_nnt); nt = t - q * p.n_ntiles; t = q;
   q = fdiv(t, p.fd_tw); tw = t - q * p.tiles_w; t = q;
   q = fdiv(t, p.fd_th); th = t - q * p.tiles_h; n = q;
@@ -747,7 +766,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const TcClass& C = p.cls[ci];
       const int a = th * e_TH + hl, b = tw * e_TW + wl;
       const int oh = a * e_osh + C.oh0, ow = b * e_osw + C.ow0;
-      const bool valid = a < C.TSH && b < C.TSW && oh < e_OH && ow < e_OW && tile < e_total;   // (pair padding tile)
+      const bool valid = a < C.TSH && b < C.TSW && oh < e_OH && ow < e_OW && n < p.N;   // (n >= N: padding tile)
       const long long pix = ((long long)n * e_OH + oh) * e_OW + ow;
       if (e_dropscale && n != ds_n) {
         // Dropout2d scales are per (image, channel): stage the row of this image in smem once per image
@@ -1972,9 +1991,19 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (p.cta2) {
-    const int padded = (p.total_tiles + 1) & ~1;
-    grid = (padded < sms ? padded : sms) & ~1;
-    if (KCc != 64 || mode > 1 || grid < 2 || !p.b_resident || p.ncls != 1 || p.n_ntiles != 1) {
+    if (p.ncls > 1) {
+      // class-per-round order: total = ncls * rounds * grid tiles, spatial indices >= tpc are padding
+      p.tpc = p.total_tiles / p.ncls;
+      const int padded = (p.tpc + 1) & ~1;
+      grid = (padded < sms ? padded : sms) & ~1;
+      p.cls_round = 1;
+      p.grid = grid;
+      p.total_tiles = p.ncls * cdiv(p.tpc, grid) * grid;
+    } else {
+      const int padded = (p.total_tiles + 1) & ~1;
+      grid = (padded < sms ? padded : sms) & ~1;
+    }
+    if (KCc != 64 || mode > 1 || grid < 2 || !p.b_resident || p.n_ntiles != 1) {
       set_error("tcgen05 conv: CTA-pair configuration not supported");
       return YG_ERR_INVALID;
     }
@@ -1983,8 +2012,8 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   {
     auto magic = [](int d) { return ((1ull << 32) + (unsigned long long)d - 1) / (unsigned long long)d; };
     p.fd_ncls = magic(p.ncls); p.fd_rot = magic(p.cls_rot); p.fd_nnt = magic(p.n_ntiles);
-    p.fd_tw = magic(p.tiles_w); p.fd_th = magic(p.tiles_h);
-    const long long dmax = std::max(std::max(p.ncls, p.n_ntiles), std::max(std::max(p.tiles_w, p.tiles_h), p.cls_rot));
+    p.fd_tw = magic(p.tiles_w); p.fd_th = magic(p.tiles_h); p.fd_grid = magic(grid);
+    const long long dmax = std::max(std::max(std::max(p.ncls, p.n_ntiles), grid), std::max(std::max(p.tiles_w, p.tiles_h), p.cls_rot));
     if ((long long)p.total_tiles * dmax >= (1ll << 32)) { set_error("tcgen05 conv: %d tiles exceed the fast-division range", p.total_tiles); return YG_ERR_INVALID; }
   }
 #define TC_LAUNCH(KCV, MODEV, PRODV)                                                                                    \
@@ -2262,8 +2291,11 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   const bool two_d1 = two_d_fits(Cout, BN, Cin / BN, s2f ? 6 : 9,
                                  stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1), 1, &kc2);
   bool two_d = two_d1, cta2 = false;
-  if (!two_d && (g_tc_options & 16384) && stride == 1 && Cin == BN && BN % 32 == 0 && pick_kc(Cout) == 64 &&
-      two_d_fits(Cout, BN / 2, 1, 9, (T2_TH + 2) * (T2_TW + 2), 1, &kc2))
+  // (stride-2 dgrad as pairs - four parity classes in class-per-round order, option bit 15 - is implemented and correct but
+  //  slower: 0.64 vs 0.47 ms on base L5; its tiles carry 8-32 MMAs each and the pair's barrier round trips dominate)
+  if (!two_d && (g_tc_options & 16384) && !s2f && (stride == 1 || (g_tc_options & 32768)) && Cin == BN && BN % 32 == 0 &&
+      pick_kc(Cout) == 64 &&
+      two_d_fits(Cout, BN / 2, 1, 9, stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1), 1, &kc2))
     two_d = cta2 = true;   // CTA pair, see conv_fwd_tc
   const int KCc = two_d ? kc2 : fit_kc(Cout, BN, max_rows);
   if (!KCc) { set_error("conv_dgrad_tc: no K chunk fits (Cin %d Cout %d)", Cin, Cout); return YG_ERR_INVALID; }
