@@ -44,39 +44,51 @@ template <typename T>
 __global__ void bn_act_apply_kernel(const T* __restrict__ y, T* __restrict__ a, long long total, int HW, int C,
                                     const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                     const float* __restrict__ dropscale, unsigned char* __restrict__ actmask) {
-  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (i0 >= total) return;
+  constexpr int U = 4;   // 8-element vectors per thread: all loads are issued before the first use (bytes in flight)
+  const long long base = ((long long)blockIdx.x * blockDim.x * U + threadIdx.x) * 8;
   if ((C & 7) == 0) {
-    const int c0 = (int)(i0 % C);
-    const int n = (int)(i0 / ((long long)HW * C));
-    __align__(16) T in[8];
-    __align__(16) T out[8];
     constexpr int V = (int)(sizeof(T) * 8 / 16);
+    __align__(16) T in[U][8];
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-      reinterpret_cast<uint4*>(in)[v] = reinterpret_cast<const uint4*>(y + i0)[v];
-    unsigned bits = 0;
+    for (int u = 0; u < U; ++u) {
+      const long long i0 = base + (long long)u * blockDim.x * 8;
+      if (i0 < total) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      float v = to_f<T>(in[k]) * scale[c] + shift[c];
-      bits |= (v > 0.f ? 1u : 0u) << k;
-      v = act_fwd(v, act);
-      if (dropscale) v *= dropscale[(long long)n * C + c];
-      out[k] = from_f<T>(v);
+        for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(in[u])[v] = __ldg(reinterpret_cast<const uint4*>(y + i0) + v);
+      }
     }
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-      reinterpret_cast<uint4*>(a + i0)[v] = reinterpret_cast<uint4*>(out)[v];
-    if (actmask) actmask[i0 >> 3] = (unsigned char)bits;   // sign bits of the activation input (yg_fwd_epilogue.actmask)
+    for (int u = 0; u < U; ++u) {
+      const long long i0 = base + (long long)u * blockDim.x * 8;
+      if (i0 >= total) continue;
+      const int c0 = (int)(i0 % C);
+      const int n = (int)(i0 / ((long long)HW * C));
+      __align__(16) T out[8];
+      unsigned bits = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        float v = to_f<T>(in[u][k]) * scale[c] + shift[c];
+        bits |= (v > 0.f ? 1u : 0u) << k;
+        v = act_fwd(v, act);
+        if (dropscale) v *= dropscale[(long long)n * C + c];
+        out[k] = from_f<T>(v);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(a + i0)[v] = reinterpret_cast<uint4*>(out)[v];
+      if (actmask) actmask[i0 >> 3] = (unsigned char)bits;   // sign bits of the activation input (yg_fwd_epilogue.actmask)
+    }
   } else {
-    for (long long i = i0; i < i0 + 8 && i < total; ++i) {
-      const int c = (int)(i % C);
-      const int n = (int)(i / ((long long)HW * C));
-      float v = to_f<T>(y[i]) * scale[c] + shift[c];
-      v = act_fwd(v, act);
-      if (dropscale) v *= dropscale[(long long)n * C + c];
-      a[i] = from_f<T>(v);
+    for (int u = 0; u < U; ++u) {
+      const long long i0 = base + (long long)u * blockDim.x * 8;
+      for (long long i = i0; i < i0 + 8 && i < total; ++i) {
+        const int c = (int)(i % C);
+        const int n = (int)(i / ((long long)HW * C));
+        float v = to_f<T>(y[i]) * scale[c] + shift[c];
+        v = act_fwd(v, act);
+        if (dropscale) v *= dropscale[(long long)n * C + c];
+        a[i] = from_f<T>(v);
+      }
     }
   }
 }
@@ -98,31 +110,44 @@ __global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, 
     kc[2 * C + c] = gi * (m2 * invstd[c] * mean[c] - m1);
   }
   __syncthreads();
-  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < total;
-       i0 += (long long)gridDim.x * blockDim.x * 8) {
-    if ((C & 7) == 0) {
-      const int c0 = (int)(i0 % C);
-      __align__(16) T gin[8];
-      __align__(16) T yin[8];
-      constexpr int V = (int)(sizeof(T) * 8 / 16);
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  if ((C & 7) == 0) {
+    constexpr int U = 2;   // two independent 8-element vectors per iteration: four 16-byte loads in flight per thread
+    constexpr int V = (int)(sizeof(T) * 8 / 16);
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < total; i0 += U * stride) {
+      __align__(16) T gin[U][8];
+      __align__(16) T yin[U][8];
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        reinterpret_cast<uint4*>(gin)[v] = reinterpret_cast<const uint4*>(g + i0)[v];
-        reinterpret_cast<uint4*>(yin)[v] = reinterpret_cast<const uint4*>(y + i0)[v];
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < total) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            reinterpret_cast<uint4*>(gin[u])[v] = reinterpret_cast<const uint4*>(g + i)[v];
+            reinterpret_cast<uint4*>(yin[u])[v] = __ldg(reinterpret_cast<const uint4*>(y + i) + v);
+          }
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int c = c0 + k;
-        gin[k] = from_f<T>(to_f<T>(gin[k]) * kc[c] + to_f<T>(yin[k]) * kc[C + c] + kc[2 * C + c]);
-      }
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        if (i >= total) continue;
+        const int c0 = (int)(i % C);
 #pragma unroll
-      for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(g + i0)[v] = reinterpret_cast<uint4*>(gin)[v];
-    } else {
+        for (int k = 0; k < 8; ++k) {
+          const int c = c0 + k;
+          gin[u][k] = from_f<T>(to_f<T>(gin[u][k]) * kc[c] + to_f<T>(yin[u][k]) * kc[C + c] + kc[2 * C + c]);
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(g + i)[v] = reinterpret_cast<uint4*>(gin[u])[v];
+      }
+    }
+  } else {
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < total; i0 += stride)
       for (long long i = i0; i < i0 + 8 && i < total; ++i) {
         const int c = (int)(i % C);
         g[i] = from_f<T>(to_f<T>(g[i]) * kc[c] + to_f<T>(y[i]) * kc[C + c] + kc[2 * C + c]);
       }
-    }
   }
 }
 
@@ -215,7 +240,7 @@ extern "C" int yg_bn_act_apply(const void* y, void* a, int dtype, int N, int HW,
   YG_CHECK_ARG(!actmask || (C & 7) == 0, "bn_act_apply: actmask needs C % 8 == 0");
   const long long total = (long long)N * HW * C;
   if (total == 0) return YG_OK;
-  const int blocks = cdiv(cdiv(total, 8), 256);
+  const int blocks = cdiv(cdiv(total, 8), 256 * 4);   // 4 vectors of 8 elements per thread
   if (dtype == YG_BF16)
     bn_act_apply_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, total, HW, C, scale, shift, act, dropscale, (unsigned char*)actmask);
   else
