@@ -398,7 +398,12 @@ def test_eval_and_inference_forward_match_reference_golden(golden_dir, dtype, to
         with torch.no_grad():
             a = net(torch.from_numpy(z["img"]).to(DEV))
             b = net(torch.from_numpy(z["img"]).float().to(DEV))
-        assert torch.equal(a, b)
+        if dtype == torch.float32:
+            assert torch.equal(a, b)
+        else:
+            # bf16: the uint8 path runs the first layer on the tensor cores with split-bf16 weights (2^-17 relative), the
+            # float path on the FMA pipe; both round to the same bf16 activations except at rounding boundaries
+            assert _rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-2
 
 
 def test_full_size_train_step_vs_oracle_fp32():

@@ -682,6 +682,178 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_bwd_mma_kernel(
   for (int i = threadIdx.x; i < 10 * FF_CO; i += FM_WARPS * 32) base[i] = red[i];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Forward and Gram-matrix passes of the first layer on the warp-level tensor cores (uint8 image, 1 -> 16 channels),
+// same staging as first_bwd_mma_kernel: per warp and 32 pixels the taps go to shared memory as an exact bf16 tile X[px][16]
+// (9 taps, a ones column, zeros).
+//   forward: acc^T[ch][px] = (W_hi + W_lo) . X^T, scale/shift/activation/Dropout2d in the accumulator layout, stmatrix.trans
+//            turns it back into pixel-major rows, each thread stores the 32 bytes of its pixel.
+//   Gram:    G = X^T . X (one mma per 16 pixels and 8 columns); the ones column makes G[:, 9] = S.  uint8 products are
+//            integers: the fp32 accumulators are flushed to fp64 before they can exceed 2^24, so G and S are EXACT.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stsm_x4_t(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+               ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+__device__ __forceinline__ void stage_taps_tile(unsigned char* xt, int lane, const float (&v)[9]) {
+  const uint4 x0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  const uint4 x1 = make_uint4(pack_bf16(v[8], 1.f), 0u, 0u, 0u);   // tap 8, the ones column, zero padding
+  const int sw = (lane >> 2) & 1;
+  *reinterpret_cast<uint4*>(xt + lane * 32 + ((0 ^ sw) << 4)) = x0;
+  *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ sw) << 4)) = x1;
+}
+
+__global__ void __launch_bounds__(FM_WARPS * 32, 8) first_fwd_mma_kernel(
+    const uint8_t* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int H, int W, int Ho, int Wo,
+    int stride, FwdEpi ep, int chunk, int cpi, int ntasks) {
+  __shared__ __align__(128) unsigned char tiles[FM_WARPS][2][32 * 32];   // per warp: X tile, output tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  uint32_t whi[4], wlo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ch = g + (q & 1) * 8, t0 = 2 * j + (q >> 1) * 8;
+    float hi[2], lo[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float v = (t0 + e < 9) ? w[ch * 9 + t0 + e] : 0.f;
+      hi[e] = __bfloat162float(__float2bfloat16_rn(v));
+      lo[e] = v - hi[e];
+    }
+    whi[q] = pack_bf16(hi[0], hi[1]);
+    wlo[q] = pack_bf16(lo[0], lo[1]);
+  }
+  float c_sc[2], c_sh[2], c_ds[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int ch = g + e * 8;
+    c_sc[e] = ep.scale ? ep.scale[ch] : 1.f;
+    c_sh[e] = ep.shift ? ep.shift[ch] : 0.f;
+    c_ds[e] = 1.f;
+  }
+  const int act = ep.act;
+  unsigned char* xt = tiles[warp][0];
+  unsigned char* yt = tiles[warp][1];
+  const uint32_t xt_s = (uint32_t)__cvta_generic_to_shared(xt), yt_s = (uint32_t)__cvta_generic_to_shared(yt);
+  const int lm = lane >> 3, lr = lane & 7;
+  auto row_addr = [](uint32_t base, int px, int half) { return base + (uint32_t)(px * 32 + ((half ^ ((px >> 2) & 1)) << 4)); };
+  const int npix = Ho * Wo;
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
+    const int p1 = min(p0 + chunk, npix);
+    if (ep.dropscale) {
+      c_ds[0] = ep.dropscale[(long long)n * FF_CO + g];
+      c_ds[1] = ep.dropscale[(long long)n * FF_CO + g + 8];
+    }
+    const uint8_t* xim = x + (long long)n * H * W;
+    bf16* yim = y + (long long)n * npix * FF_CO;
+    PixCursor cur;
+    cur.init(p0 + warp * 32 + lane, Wo);
+    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
+      float v[9];
+      if (cur.p < p1) load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
+      else {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = 0.f;
+      }
+      __syncwarp();
+      stage_taps_tile(xt, lane, v);
+      __syncwarp();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        uint32_t b1[4], o[4];
+        ldsm_x4(b1, row_addr(xt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          hmma16816(c, whi, b1[2 * t], b1[2 * t + 1]);
+          hmma16816(c, wlo, b1[2 * t], b1[2 * t + 1]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int hc = e >> 1;
+            c[e] = act_fwd(c[e] * c_sc[hc] + c_sh[hc], act) * c_ds[hc];
+          }
+          o[2 * t] = pack_bf16(c[0], c[1]);       // (ch g;     pixels 2j, 2j+1 of tile t)
+          o[2 * t + 1] = pack_bf16(c[2], c[3]);   // (ch g + 8; same pixels)
+        }
+        stsm_x4_t(row_addr(yt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1), o);
+      }
+      __syncwarp();
+      if (cur.p < p1) {
+        const int sw = (lane >> 2) & 1;
+        uint4* dst = reinterpret_cast<uint4*>(yim + (long long)cur.p * FF_CO);
+        dst[0] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((0 ^ sw) << 4));
+        dst[1] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((1 ^ sw) << 4));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FM_WARPS * 32, 8) first_gram_mma_kernel(const uint8_t* __restrict__ x, int H, int W, int Ho,
+                                                                          int Wo, int stride, double* __restrict__ gram,
+                                                                          int chunk, int cpi, int ntasks) {
+  __shared__ __align__(128) unsigned char tiles[FM_WARPS][32 * 32];
+  __shared__ double red[54];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  if (threadIdx.x < 54) red[threadIdx.x] = 0.0;
+  __syncthreads();
+  unsigned char* xt = tiles[warp];
+  const uint32_t xt_s = (uint32_t)__cvta_generic_to_shared(xt);
+  const int lm = lane >> 3, lr = lane & 7;
+  auto row_addr = [](uint32_t base, int px, int half) { return base + (uint32_t)(px * 32 + ((half ^ ((px >> 2) & 1)) << 4)); };
+  float D0[4] = {0.f, 0.f, 0.f, 0.f}, D1[4] = {0.f, 0.f, 0.f, 0.f};
+  // D0: (a = g | g+8, b = 2j, 2j+1);  D1: (a, b = 8 + 2j, 9 + 2j): b = 8 and the ones column b = 9 (= S[a]) for j == 0
+  auto flush = [&]() {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int a = g + (e >> 1) * 8, b = 2 * j + (e & 1);
+      if (a <= 8 && a <= b) atomicAdd(&red[9 + a * 9 - a * (a - 1) / 2 + (b - a)], (double)D0[e]);
+      if (a <= 8 && j == 0) {
+        if ((e & 1) == 0) atomicAdd(&red[9 + a * 9 - a * (a - 1) / 2 + (8 - a)], (double)D1[e]);   // G[a][8]
+        else atomicAdd(&red[a], (double)D1[e]);                                                         // S[a]
+      }
+      D0[e] = 0.f; D1[e] = 0.f;
+    }
+  };
+  const int npix = Ho * Wo;
+  int since_flush = 0;
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
+    const int p1 = min(p0 + chunk, npix);
+    const uint8_t* xim = x + (long long)n * H * W;
+    PixCursor cur;
+    cur.init(p0 + warp * 32 + lane, Wo);
+    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
+      float v[9];
+      if (cur.p < p1) load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
+      else {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = 0.f;
+      }
+      __syncwarp();
+      stage_taps_tile(xt, lane, v);
+      if (cur.p >= p1) *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ ((lane >> 2) & 1)) << 4)) = make_uint4(0, 0, 0, 0);   // no ones
+      __syncwarp();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        uint32_t a[4], b[4];
+        ldsm_x4_t(a, row_addr(xt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));   // A[m = tap][k = pixel]
+        ldsm_x4_t(b, row_addr(xt_s, kb * 16 + (lm & 1) * 8 + lr, lm >> 1));   // B[k = pixel][n = tap]
+        hmma16816(D0, a, b[0], b[1]);
+        hmma16816(D1, a, b[2], b[3]);
+      }
+      // 32 pixels add at most 32 * 255^2 < 2^21 to an accumulator: flushing every 7 iterations keeps it below 2^24 (exact)
+      if (++since_flush == 7) { flush(); since_flush = 0; }
+    }
+  }
+  flush();
+  __syncthreads();
+  if (threadIdx.x < 54) atomicAdd(&gram[threadIdx.x], red[threadIdx.x]);
+}
+
 constexpr int FL_BWD_BLOCKS = 592;
 
 }  // namespace yg
@@ -702,6 +874,14 @@ extern "C" int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, voi
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1 && Cout == FF_CO && dtype == YG_BF16 && !ep.preact && (long long)Ho * Wo < (1LL << 30) &&
       (long long)H * W < (1LL << 31)) {
+    if (x_dtype == YG_U8 && !ep.stats && y && yg_get_conv_impl() != YG_IMPL_SIMT) {
+      const int chunkm = 16 * FM_WARPS * 32, cpim = cdiv((long long)Ho * Wo, chunkm), ntasksm = N * cpim;
+      const int gridm = ntasksm < 148 * 8 ? ntasksm : 148 * 8;
+      first_fwd_mma_kernel<<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunkm, cpim,
+                                                            ntasksm);
+      YG_LAUNCH_CHECK("conv_first_fwd_mma");
+      return YG_OK;
+    }
     const int chunk = 16 * FL_THREADS, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
     const int grid1 = ntasks < 148 * 3 ? ntasks : 148 * 3;
 #define LAUNCHF(TX, ST) first_fwd16_kernel<TX, ST><<<grid1, FL_THREADS, 0, st>>>((const TX*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunk, cpi, ntasks)
@@ -923,6 +1103,13 @@ extern "C" int yg_conv_first_gram(const void* x, int x_dtype, int N, int H, int 
   if (N == 0) return YG_OK;
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   YG_CHECK_ARG((long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31), "conv_first_gram: image too large");
+  if (x_dtype == YG_U8 && yg_get_conv_impl() != YG_IMPL_SIMT) {
+    const int chunkm = 32 * FM_WARPS * 32, cpim = cdiv((long long)Ho * Wo, chunkm), ntasksm = N * cpim;
+    const int gridm = ntasksm < 148 * 8 ? ntasksm : 148 * 8;
+    first_gram_mma_kernel<<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, H, W, Ho, Wo, stride, gram, chunkm, cpim, ntasksm);
+    YG_LAUNCH_CHECK("first_gram_mma");
+    return YG_OK;
+  }
   const int chunk = 32 * GR_THREADS, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
   const int nblk = ntasks < 148 * 4 ? ntasks : 148 * 4;
   if (x_dtype == YG_U8)
