@@ -516,3 +516,50 @@ def test_device_prefetcher_yields_batches_in_order():
     assert len(got) == len(host)
     for (hx, hy), (dx, dy) in zip(host, got):
         assert torch.equal(hx, dx) and torch.equal(hy, dy)
+
+
+@pytest.mark.parametrize("shape", [(3, 33, 20, 128, 128, 3, 1), (1, 17, 9, 128, 128, 3, 1), (2, 21, 37, 128, 128, 3, 2),
+                                   (2, 19, 36, 64, 128, 3, 1), (3, 20, 36, 32, 64, 3, 2), (2, 19, 36, 16, 32, 3, 1)])
+def test_conv_outputs_stay_inside_their_buffers(shape):
+    """Guard regions around every output of the tensor-core paths (CTA pairs with a padding tile, 2-D halo boxes, parity
+    classes, W-folded views, sign masks): nothing outside the tensors may be written."""
+    import ctypes as C
+    N, H, W, Cin, Cout, k, s = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    dt = torch.bfloat16
+    lib = L.lib()
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+    GUARD = 4096
+
+    def guarded(numel, dtype, fill):
+        buf = torch.full((numel + 2 * GUARD,), fill, dtype=dtype, device=DEV)
+        return buf, buf[GUARD:GUARD + numel]
+
+    def intact(buf, numel, fill):
+        return bool((buf[:GUARD] == fill).all()) and bool((buf[GUARD + numel:] == fill).all())
+
+    x = torch.randn(N, H, W, Cin, generator=g).to(DEV).to(dt)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    ybuf, y = guarded(N * Ho * Wo * Cout, dt, 7.0)
+    mbuf, m = guarded(N * Ho * Wo * Cout // 8, torch.uint8, 0xA5)
+    ep = L.FwdEpilogue(None, b.data_ptr(), L.ACT_LRELU, None, None, None, m.data_ptr())
+    L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, k, s, C.byref(ep), L.stream()))
+    torch.cuda.synchronize()
+    assert intact(ybuf, y.numel(), 7.0) and intact(mbuf, m.numel(), 0xA5)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2).cpu(), w.cpu(), b.cpu(), stride=s, padding=1), 0.01)
+    assert _rel(y.float().reshape(N, Ho, Wo, Cout).permute(0, 3, 1, 2).cpu(), ref) < 6e-3
+    dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).to(dt)
+    dxbuf, dx = guarded(N * H * W * Cin, dt, 7.0)
+    xmask = torch.randint(0, 255, (N * H * W * Cin // 8,), dtype=torch.uint8, device=DEV)
+    be = L.BwdEpilogue(x.data_ptr(), L.ACT_LRELU, None, None, None, None, None, None, xmask.data_ptr())
+    L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, k, s, C.byref(be), L.stream()))
+    dwbuf, dw = guarded(w.numel(), torch.float32, 7.0)
+    dbbuf, db = guarded(Cout, torch.float32, 7.0)
+    nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, k, s)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
+    L.check(lib.yg_conv_wgrad(x.data_ptr(), dz.data_ptr(), dw.data_ptr(), db.data_ptr(), 1, N, H, W, Cin, Cout, k, s, 0.0,
+                              ws.data_ptr(), nb, L.stream()))
+    torch.cuda.synchronize()
+    assert intact(dxbuf, dx.numel(), 7.0) and intact(dwbuf, dw.numel(), 7.0) and intact(dbbuf, db.numel(), 7.0)
+    assert bool(torch.isfinite(dx.float()).all()) and bool(torch.isfinite(dw).all())
