@@ -1,21 +1,25 @@
 // tcgen05 implicit-GEMM convolution engine for sm_100a (bf16 NHWC activations, fp32 accumulate).
 //
-// One persistent, warp-specialised kernel serves fprop and dgrad of the 3x3 convolutions
+// One persistent, warp-specialised kernel serves fprop and dgrad of the 3x3 convolutions and the 1x1 head
 // (replacing cuDNN fprop/dgrad dispatched by nn.Conv2d, /root/reference/yogo/model_defns.py:34-64):
 //   GEMM view   D[128 pixels x BN channels] += A[128 pixels x KC] * B[BN x KC]^T  per (tap, K chunk)
-//   A operand   an output tile is an 8x16 pixel patch; for filter column s the TMA fetches ONE
-//               (8+2)x16 halo box per K chunk (4-D tiled tensor map over the NHWC tensor, OOB zero
-//               fill = the conv padding) and the three filter rows r reuse it by offsetting the
-//               UMMA descriptor start by r*16 rows (swizzle-atom aligned).  Stride-2 convolutions
-//               use four parity sub-grids of the input (one tensor map each), stride-2 dgrad runs
-//               as four output-parity classes.
-//   B operand   packed bf16 weights [tap][N][K] through a 3-D tensor map.
-//   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN<=256, accumulators double-buffered
-//               in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   epilogue    tcgen05.ld 32x32b -> registers -> fused bias/BN-fold/activation/Dropout2d scale,
-//               BatchNorm batch statistics (fwd) or activation/BN backward + BN sums (dgrad),
-//               16-byte bf16 stores.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+//   A operand   4-D tiled TMA maps over the NHWC tensor, OOB zero fill = the conv padding.  Two box schemes:
+//               * 2-D halo boxes (weights resident): the tile is 16 x 8 pixels, ONE (16+2) x (8+2) box per K chunk; a tap
+//                 (r, s) is a descriptor start offset of r * box_cols + s pixel rows (the swizzle is a function of the
+//                 absolute shared-memory address), SBO = the box row pitch;
+//               * per-filter-column boxes (streamed weights): the tile is 8 x 16 pixels, one (8+2) x 16 box per filter
+//                 column, the three filter rows reuse it with row offsets of 16 pixels.
+//               Stride-2 fprop reads four parity sub-grids of the input (one tensor map each); stride-2 dgrad runs as four
+//               (or, with folded column pairs, two) output-parity classes; small-channel stride-1 layers are W-folded.
+//   B operand   packed bf16 weights [tap][N][K] through a 3-D tensor map; resident in shared memory whenever they fit.
+//   MMA         tcgen05.mma.kind::f16, M = 128, N = BN <= 256, up to four accumulators in TMEM so the epilogue of tile i
+//               overlaps the MMAs of tiles i+1..; the producer and MMA warps issue warp-uniformly (elect.sync predicate
+//               inside the asm).  128 -> 128 layers run as CTA pairs: cta_group::2, M = 256, half of B per CTA.
+//   epilogue    tcgen05.ld 32x32b -> registers -> bias / folded BN / activation / Dropout2d scale / sign mask (fwd),
+//               activation backward from the sign mask or the saved tensor, optional BN sums (dgrad), 16-byte bf16
+//               stores; straight-line 32-column fast paths for the common flavours; the YOGO head transform.
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warp 10 optional
+// L2 prefetch.  The weight-gradient kernel (wgrad_tc_kernel, below) has its own header.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
