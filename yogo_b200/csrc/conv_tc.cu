@@ -851,17 +851,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           if (e_mask_out) {
             // sign bits from the packed outputs: bf16 > 0 <=> its bit pattern, read as int16, is > 0; sign(y) = sign(v)
             // wherever the Dropout2d scale is non-zero (and a dropped channel's gradient is zero whatever the bit says)
-            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            // word i holds elements 2i (low half) and 2i+1 (high half): select bit 2i of the low and bit 2i+1 of the high
+            // compare mask and OR everything together - one compare and one three-input logic op per word
+            uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t t0 = __vcmpgts2(ob32[i], 0u) & 0x00010001u, t1 = __vcmpgts2(ob32[4 + i], 0u) & 0x00010001u;
-              const uint32_t t2 = __vcmpgts2(ob32[8 + i], 0u) & 0x00010001u, t3 = __vcmpgts2(ob32[12 + i], 0u) & 0x00010001u;
-              b0 |= ((t0 | (t0 >> 15)) & 3u) << (2 * i);
-              b1 |= ((t1 | (t1 >> 15)) & 3u) << (2 * i);
-              b2 |= ((t2 | (t2 >> 15)) & 3u) << (2 * i);
-              b3 |= ((t3 | (t3 >> 15)) & 3u) << (2 * i);
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t sel = (1u << (2 * i)) | (1u << (2 * i + 17));
+              acc0 |= __vcmpgts2(ob32[i], 0u) & sel;
+              acc1 |= __vcmpgts2(ob32[8 + i], 0u) & sel;
             }
-            const unsigned long long bits = (unsigned long long)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+            const unsigned long long bits =
+                (unsigned long long)(((acc0 & 0xFFFFu) | (acc0 >> 16)) | ((((acc1 & 0xFFFFu) | (acc1 >> 16))) << 16));
             const int jj = j - half * nper;
             if (jj < 4) mbits_lo |= bits << (16 * jj);
             else mbits_hi |= bits << (16 * (jj - 4));
