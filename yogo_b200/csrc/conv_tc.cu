@@ -69,7 +69,7 @@ struct TcParams {
   // class-per-round tile order (CTA pairs with parity classes): round k of the persistent grid works on class k % ncls
   // for every CTA (a pair always shares its class, sibling classes of a spatial tile run in consecutive rounds)
   int cls_round, grid, tpc;           // flag, grid size, tiles per class
-  unsigned long long fd_grid;
+  unsigned long long fd_grid, fd_ocr;
   TcClass cls[4];
   int b_resident, resb_bytes;     // all weight tiles live in smem for the whole kernel
   TcSrc src[4];
@@ -435,7 +435,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   volatile int* prod_iter = reinterpret_cast<volatile int*>(tmem_slot + 1);  // producer's tile-loop counter
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
   float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
-  float* s_ds = s_const + 4 * 512;                          // [512] Dropout2d scales of the image being processed
 
   // warp index through a shuffle: the compiler then knows that role dispatch and everything derived from kernel
   // parameters inside a role is warp-uniform (uniform registers feed UTCHMMA / UTMALDG directly)
@@ -449,7 +448,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
     prefetch_tmap(&maps.b);
     for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], PROD ? 64 : 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTA2 ? 16 : 8); }
+    // the two epilogue warp groups alternate tiles (4 arrivals per accumulator and CTA); only with several N tiles per CTA and
+    // fused statistics do all eight warps share every tile (they then flush the statistics together)
+    const bool alt0 = !(p.n_ntiles > 1 && ((MODE == 0 ? p.stats : p.bn_sums) != nullptr));
+    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (alt0 ? 4 : 8) * (CTA2 ? 2 : 1)); }
     mbar_init(&resb_bar[0], 1);
     *prod_iter = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -730,15 +732,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
   } else {
     // ===================================================================== epilogue (8 warps)
-    // warp w may only touch TMEM lanes [32*(w&3), +32); two warps share a quarter and split the
-    // 16-column chunks between them (even / odd chunks).
+    // warp w may only touch TMEM lanes [32*(w&3), +32).  The eight warps form two groups of four (one warp per lane
+    // quarter); the groups ALTERNATE TILES, so the fixed per-tile work (decode, barrier waits, hand-back) is paid by four warps
+    // instead of eight - the epilogue, not the tensor pipe, bounds most layers.
     const int q = warp & 3;
     const int half = (warp - (PW + 1)) >> 2;
     const int m = q * 32 + lane;       // row of the tile = pixel
     const int hl = m >> p.tw_shift, wl = m & (p.TW - 1);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int ds_n = -1;
+    int acc_it = 0;
+    uint32_t acc_phase_it = 0;
+    int it = 0;
     bf16* out = reinterpret_cast<bf16*>(p.out);
     const float* s_k0 = s_const;             // fwd: scale      bwd: bn_scale
     const float* s_k1 = s_const + 512;       // fwd: shift      bwd: bn_shift
@@ -757,6 +760,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool e_has_scale = p.scale != nullptr;
     const int e_act = p.act, e_OC = p.OC, e_OH = p.OH, e_OW = p.OW, e_dbg = p.debug, e_nnt = p.n_ntiles, e_OCr = p.OCr;
     const int e_TH = p.TH, e_TW = p.TW, e_osh = p.osh, e_osw = p.osw, e_total = p.total_tiles, e_nacc = p.nacc;
+    const bool alt = !(e_nnt > 1 && ((MODE == 0 ? (const void*)e_stats : (const void*)e_bn_sums) != nullptr));
     const bool eprof = (p.debug & 16) != 0 && warp == PW + 1;
     long long ec_tfull = 0, ec_ld = 0, ec_pre = 0, ec_math = 0, ec_store = 0, ec_rest = 0, ec_tiles = 0, eprev = clock64();
     const bool use_mask = MODE == 1 && p.actmask_in && e_act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (e_OC % 32) == 0;
@@ -764,7 +768,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool fast_fwd = MODE == 0 && !e_head_out && !e_has_scale && !e_stats && !e_preact && (BN % 64) == 0 &&
                           (e_act == YG_ACT_LRELU || e_act == YG_ACT_NONE) && !(p.debug & 4) && out != nullptr;
     const bool fast_bwd = MODE == 1 && use_mask && !e_bn_sums && (BN % 64) == 0 && !(p.debug & 4);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = acc_it;
+      const uint32_t acc_phase = acc_phase_it;
+      if (++acc_it == e_nacc) { acc_it = 0; acc_phase_it ^= 1u; }
+      if (alt && (it & 1) != half) continue;   // the other warp group's tile
       int ci, nt, tw, th, n;
       decode_tile(p, tile, ci, nt, tw, th, n);
       const TcClass& C = p.cls[ci];
@@ -772,14 +780,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int oh = a * e_osh + C.oh0, ow = b * e_osw + C.ow0;
       const bool valid = a < C.TSH && b < C.TSW && oh < e_OH && ow < e_OW && n < p.N;   // (n >= N: padding tile)
       const long long pix = ((long long)n * e_OH + oh) * e_OW + ow;
-      if (e_dropscale && n != ds_n) {
-        // Dropout2d scales are per (image, channel): stage the row of this image in smem once per image
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = threadIdx.x - (PW + 1) * 32; i < e_OC; i += 256) s_ds[i] = e_dropscale[(long long)(n < p.N ? n : p.N - 1) * e_OCr + i % e_OCr];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        ds_n = n;
-      }
-      if (MODE == 1 && e_saved && half == 0 && !use_mask) {
+      // Dropout2d scales of this image: read through L1 per chunk (16 consecutive channels; folded layers index modulo
+      // the real channel count)
+      const float* dsrow = e_dropscale ? e_dropscale + (long long)(n < p.N ? n : p.N - 1) * e_OCr : nullptr;
+      if (MODE == 1 && e_saved && (alt || half == 0) && !use_mask) {
         // pull the saved-activation rows of the tile after next into L2 now: by the time its epilogue runs,
         // the 32-byte operand loads hit L2 instead of paying an HBM round trip per 16-column chunk
         const int tile2 = tile + 2 * (int)gridDim.x;
@@ -813,13 +817,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
       // the two warps of a TMEM lane quarter split the 16-column chunks into a lower and an upper contiguous half
       const int nchunks = (e_dbg & 4) ? 0 : BN / 16, nper = (nchunks + 1) >> 1;
-      const int j_end = min(nchunks, (half + 1) * nper);
-      unsigned long long mbits_lo = 0ull, mbits_hi = 0ull;   // forward: sign bits of this thread's chunks
+      const int jb = alt ? 0 : half * nper;
+      const int j_end = alt ? nchunks : min(nchunks, (half + 1) * nper);
+      unsigned long long mbits0 = 0ull, mbits1 = 0ull, mbits2 = 0ull, mbits3 = 0ull;   // forward: sign bits of this thread's chunks
       // ---- straight-line fast paths for the common epilogue flavours: 32 columns per iteration, no branches inside,
       // so the compiler can interleave 32 independent element chains (the generic loop below issues at IPC ~0.25)
       if (MODE == 0 && fast_fwd) {
         bf16* orow = out + pix * e_OC + nt * BN;
-        for (int j = half * nper; j < j_end; j += 2) {
+        for (int j = jb; j < j_end; j += 2) {
           uint32_t ra[16], rb[16];
           tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
           tmem_ld16(taddr0 + (uint32_t)(j * 16 + 16), rb);
@@ -838,7 +843,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
           }
           if (e_dropscale) {
-            const float4* k4 = reinterpret_cast<const float4*>(s_ds + c0);
+            const float4* k4 = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
           }
@@ -862,9 +867,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
             const unsigned long long bits =
                 (unsigned long long)(((acc0 & 0xFFFFu) | (acc0 >> 16)) | ((((acc1 & 0xFFFFu) | (acc1 >> 16))) << 16));
-            const int jj = j - half * nper;
-            if (jj < 4) mbits_lo |= bits << (16 * jj);
-            else mbits_hi |= bits << (16 * (jj - 4));
+            const int jj = j - jb, mb = jj >> 2, sh = 16 * (jj & 3);
+            if (mb == 0) mbits0 |= bits << sh;
+            else if (mb == 1) mbits1 |= bits << sh;
+            else if (mb == 2) mbits2 |= bits << sh;
+            else mbits3 |= bits << sh;
           }
           if (valid && !(e_dbg & 1)) {
             uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
@@ -874,7 +881,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       } else if (MODE == 1 && fast_bwd) {
         bf16* orow = out + pix * e_OC + nt * BN;
-        for (int j = half * nper; j < j_end; j += 2) {
+        for (int j = jb; j < j_end; j += 2) {
           uint32_t ra[16], rb[16];
           tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
           tmem_ld16(taddr0 + (uint32_t)(j * 16 + 16), rb);
@@ -891,7 +898,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             v[16 + i] = __uint_as_float(rb[i]) * (((word >> (16 + i)) & 1u) ? 1.f : 0.01f);
           }
           if (e_dropscale) {
-            const float4* k4 = reinterpret_cast<const float4*>(s_ds + c0);
+            const float4* k4 = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
           }
@@ -910,15 +917,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       } else {
       // software pipeline over the chunks: the TMEM load of chunk j+1 is in flight while chunk j is processed
       uint32_t rn[16];
-      if (half * nper < j_end) tmem_ld16(taddr0 + (uint32_t)(half * nper * 16), rn);
-      for (int j = half * nper; j < j_end; ++j) {
+      if (jb < j_end) tmem_ld16(taddr0 + (uint32_t)(jb * 16), rn);
+      for (int j = jb; j < j_end; ++j) {
         uint32_t r[16];
         const int cl = j * 16;          // channel inside the N tile
         const int c0 = nt * BN + cl;    // absolute output channel
         // global operands of this chunk are fetched while the TMEM load is in flight
         float ds[16];
         if (e_dropscale) {
-          const float4* dp = reinterpret_cast<const float4*>(s_ds + c0);
+          const float4* dp = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 v4 = dp[i];
@@ -1035,9 +1042,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             uint32_t bits = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) bits |= (__uint_as_float(r[i]) > 0.f ? 1u : 0u) << i;
-            const int jj = j - half * nper;
-            if (jj < 4) mbits_lo |= (unsigned long long)bits << (16 * jj);
-            else mbits_hi |= (unsigned long long)bits << (16 * (jj - 4));
+            const int jj = j - jb, mb = jj >> 2, sh = 16 * (jj & 3);
+            if (mb == 0) mbits0 |= (unsigned long long)bits << sh;
+            else if (mb == 1) mbits1 |= (unsigned long long)bits << sh;
+            else if (mb == 2) mbits2 |= (unsigned long long)bits << sh;
+            else mbits3 |= (unsigned long long)bits << sh;
           }
           if (e_act == YG_ACT_LRELU) {
 #pragma unroll
@@ -1171,19 +1180,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
       }   // generic chunk loop
-      if (MODE == 0 && e_mask_out && valid && j_end > half * nper) {
+      if (MODE == 0 && e_mask_out && valid && j_end > jb) {
         // one store per thread and tile: 2 bytes per chunk, contiguous because the chunks are
-        unsigned char* mp = reinterpret_cast<unsigned char*>(e_mask_out) + ((pix * e_OC + nt * BN) >> 3) + half * nper * 2;
-        const int nmine = j_end - half * nper;
-        if (nmine == 4 && (e_OC & 63) == 0 && (BN & 63) == 0) *reinterpret_cast<unsigned long long*>(mp) = mbits_lo;
-        else if (nmine == 8 && (e_OC & 127) == 0 && (BN & 127) == 0) {
-          reinterpret_cast<unsigned long long*>(mp)[0] = mbits_lo;
-          reinterpret_cast<unsigned long long*>(mp)[1] = mbits_hi;
-        } else if (nmine == 2) *reinterpret_cast<unsigned int*>(mp) = (unsigned int)mbits_lo;
+        unsigned char* mp = reinterpret_cast<unsigned char*>(e_mask_out) + ((pix * e_OC + nt * BN) >> 3) + jb * 2;
+        const int nmine = j_end - jb;
+        const bool al8 = (e_OC & 63) == 0 && (BN & 63) == 0;   // 8-byte aligned rows
+        if (nmine == 4 && al8) *reinterpret_cast<unsigned long long*>(mp) = mbits0;
+        else if (nmine == 8 && al8) {
+          reinterpret_cast<unsigned long long*>(mp)[0] = mbits0;
+          reinterpret_cast<unsigned long long*>(mp)[1] = mbits1;
+        } else if (nmine == 16 && al8) {
+          reinterpret_cast<unsigned long long*>(mp)[0] = mbits0;
+          reinterpret_cast<unsigned long long*>(mp)[1] = mbits1;
+          reinterpret_cast<unsigned long long*>(mp)[2] = mbits2;
+          reinterpret_cast<unsigned long long*>(mp)[3] = mbits3;
+        } else if (nmine == 2) *reinterpret_cast<unsigned int*>(mp) = (unsigned int)mbits0;
         else {
-          for (int c = 0; c < nmine; ++c)
-            reinterpret_cast<unsigned short*>(mp)[c] =
-                (unsigned short)((c < 4 ? mbits_lo >> (16 * c) : mbits_hi >> (16 * (c - 4))) & 0xFFFFull);
+          for (int c = 0; c < nmine; ++c) {
+            const unsigned long long wv = (c >> 2) == 0 ? mbits0 : ((c >> 2) == 1 ? mbits1 : ((c >> 2) == 2 ? mbits2 : mbits3));
+            reinterpret_cast<unsigned short*>(mp)[c] = (unsigned short)((wv >> (16 * (c & 3))) & 0xFFFFull);
+          }
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -1207,7 +1223,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      if (++acc == e_nacc) { acc = 0; acc_phase ^= 1u; }
       ++ec_tiles;
     }
     if (eprof && lane == 0 && blockIdx.x < 256) {
@@ -2016,7 +2031,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   {
     auto magic = [](int d) { return ((1ull << 32) + (unsigned long long)d - 1) / (unsigned long long)d; };
     p.fd_ncls = magic(p.ncls); p.fd_rot = magic(p.cls_rot); p.fd_nnt = magic(p.n_ntiles);
-    p.fd_tw = magic(p.tiles_w); p.fd_th = magic(p.tiles_h); p.fd_grid = magic(grid);
+    p.fd_tw = magic(p.tiles_w); p.fd_th = magic(p.tiles_h); p.fd_grid = magic(grid); p.fd_ocr = magic(p.OCr > 0 ? p.OCr : 1);
     const long long dmax = std::max(std::max(std::max(p.ncls, p.n_ntiles), grid), std::max(std::max(p.tiles_w, p.tiles_h), p.cls_rot));
     if ((long long)p.total_tiles * dmax >= (1ll << 32)) { set_error("tcgen05 conv: %d tiles exceed the fast-division range", p.total_tiles); return YG_ERR_INVALID; }
   }
