@@ -435,6 +435,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   volatile int* prod_iter = reinterpret_cast<volatile int*>(tmem_slot + 1);  // producer's tile-loop counter
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
   float* s_const = s_stat + 2 * 256;                        // [4][512] per-channel epilogue constants
+  float* s_ds = s_const + 4 * 512;                          // [2][256] Dropout2d scales of the image each epilogue group works on
 
   // warp index through a shuffle: the compiler then knows that role dispatch and everything derived from kernel
   // parameters inside a role is warp-uniform (uniform registers feed UTCHMMA / UTMALDG directly)
@@ -741,7 +742,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int hl = m >> p.tw_shift, wl = m & (p.TW - 1);
     int acc_it = 0;
     uint32_t acc_phase_it = 0;
-    int it = 0;
+    int it = 0, ds_n = -1;
     bf16* out = reinterpret_cast<bf16*>(p.out);
     const float* s_k0 = s_const;             // fwd: scale      bwd: bn_scale
     const float* s_k1 = s_const + 512;       // fwd: shift      bwd: bn_shift
@@ -761,6 +762,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int e_act = p.act, e_OC = p.OC, e_OH = p.OH, e_OW = p.OW, e_dbg = p.debug, e_nnt = p.n_ntiles, e_OCr = p.OCr;
     const int e_TH = p.TH, e_TW = p.TW, e_osh = p.osh, e_osw = p.osw, e_total = p.total_tiles, e_nacc = p.nacc;
     const bool alt = !(e_nnt > 1 && ((MODE == 0 ? (const void*)e_stats : (const void*)e_bn_sums) != nullptr));
+    const bool ds_smem = e_dropscale != nullptr && alt && e_OC <= 256;   // else the scales are read through L1 per chunk
     const bool eprof = (p.debug & 16) != 0 && warp == PW + 1;
     long long ec_tfull = 0, ec_ld = 0, ec_pre = 0, ec_math = 0, ec_store = 0, ec_rest = 0, ec_tiles = 0, eprev = clock64();
     const bool use_mask = MODE == 1 && p.actmask_in && e_act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (e_OC % 32) == 0;
@@ -783,6 +785,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // Dropout2d scales of this image: read through L1 per chunk (16 consecutive channels; folded layers index modulo
       // the real channel count)
       const float* dsrow = e_dropscale ? e_dropscale + (long long)(n < p.N ? n : p.N - 1) * e_OCr : nullptr;
+      if (ds_smem && n != ds_n) {
+        // stage the row of this image in this group's half of the shared buffer, already expanded to folded channels
+        const int tg = (int)threadIdx.x - (PW + 1) * 32 - half * 128;
+        if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int i = tg; i < e_OC; i += 128) s_ds[half * 256 + i] = dsrow[i - fdiv(i, p.fd_ocr) * e_OCr];
+        if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        ds_n = n;
+      }
       if (MODE == 1 && e_saved && (alt || half == 0) && !use_mask) {
         // pull the saved-activation rows of the tile after next into L2 now: by the time its epilogue runs,
         // the 32-byte operand loads hit L2 instead of paying an HBM round trip per 16-column chunk
@@ -843,7 +853,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
           }
           if (e_dropscale) {
-            const float4* k4 = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+            const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
           }
@@ -898,7 +908,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             v[16 + i] = __uint_as_float(rb[i]) * (((word >> (16 + i)) & 1u) ? 1.f : 0.01f);
           }
           if (e_dropscale) {
-            const float4* k4 = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+            const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
           }
@@ -925,7 +935,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // global operands of this chunk are fetched while the TMEM load is in flight
         float ds[16];
         if (e_dropscale) {
-          const float4* dp = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+          const float4* dp = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 v4 = dp[i];
