@@ -28,7 +28,11 @@ int conv_fwd_tc(const void*, const float*, void*, int, int, int, int, int, int, 
 int conv_dgrad_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const BwdEpi&, cudaStream_t);
 int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace(int, int, int, int, int, int, int);
+bool wgrad_hmma_supported(int dtype, int W, int Cin, int Cout, int ks, int stride);
+size_t wgrad_hmma_workspace(int Cin, int Cout);
+int conv_wgrad_hmma(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
 int set_tc_options(int);
+int get_tc_options();
 int tc_debug_read(unsigned long long*, int);
 
 static int check_conv_args(const char* who, int dtype, int N, int H, int W, int Cin, int Cout, int ks, int stride) {
@@ -64,6 +68,7 @@ extern "C" int yg_set_conv_impl(int impl) {
   return YG_OK;
 }
 extern "C" int yg_get_conv_impl(void) { return g_conv_impl; }
+static int yg_get_tc_options_raw() { return get_tc_options(); }
 extern "C" int yg_set_tc_options(int v) { return set_tc_options(v); }
 extern "C" int yg_tc_debug_read(unsigned long long* out, int n) { return tc_debug_read(out, n); }
 
@@ -125,6 +130,7 @@ extern "C" int yg_conv_dgrad(const void* dz, const float* w, void* dx, int dtype
 extern "C" size_t yg_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ks, int stride) {
   size_t a = simt_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
   size_t b = tc_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
+  if (wgrad_hmma_supported(YG_BF16, W, Cin, Cout, ks, stride)) { const size_t c = wgrad_hmma_workspace(Cin, Cout); if (c > b) b = c; }
   return a > b ? a : b;
 }
 
@@ -140,6 +146,9 @@ extern "C" int yg_conv_wgrad(const void* x, const void* dz, float* dw, float* db
     set_error("conv_wgrad: tcgen05 path forced but shape unsupported");
     return YG_ERR_INVALID;
   }
+  // small-channel layers: warp-level tensor cores, HBM-bound (wgrad_hmma.cu); option bit 16 of yg_set_tc_options enables it
+  if (g_conv_impl != YG_IMPL_SIMT && (yg_get_tc_options_raw() & 65536) && wgrad_hmma_supported(dtype, W, Cin, Cout, ks, stride))
+    return conv_wgrad_hmma(x, dz, dw, dbias, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);
   if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
     return conv_wgrad_tc(x, dz, dw, dbias, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);
   return conv_wgrad_simt(x, dz, dw, dbias, dtype, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -2084,6 +2084,7 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
 }
 
 int set_tc_options(int v) { g_tc_options = v; return 0; }
+int get_tc_options() { return g_tc_options; }
 int tc_debug_read(unsigned long long* out, int n) {
   if (n > 256 * 16) n = 256 * 16;
   YG_CUDA(cudaDeviceSynchronize());
