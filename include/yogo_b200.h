@@ -48,7 +48,9 @@ int yg_get_conv_impl(void);
  * bit 1 = cp.async producer for 16/32-channel operands, bit 2 = L2 prefetch warp, bit 3 = W-fold of small-channel
  * stride-1 layers, bit 4 = column-pair fold of small-channel stride-2 dgrad, bits 5-6 = cap the K chunk at 32 / 16,
  * bits 7-11 = profiling knobs of tools/bench_conv.py (skip stores / MMAs / epilogue / TMA, cycle counters),
- * bit 12 = swizzle-phase experiment, bit 13 = 2-D halo boxes, bit 14 = CTA pairs (cta_group::2) for 128->128 layers. */
+ * bit 12 = swizzle-phase experiment, bit 13 = 2-D halo boxes, bit 14 = CTA pairs (cta_group::2) for 128->128 layers,
+ * bit 15 = CTA pairs for stride-2 dgrad (slower), bit 16 = mma.sync wgrad also for 32->64 stride 2 (slower),
+ * bit 17 = no mma.sync wgrad at all. */
 int yg_set_tc_options(int options);
 /* profiling hook: copies n (<= 2048) cycle counters written by the engine's MMA warps (8 per CTA) to host memory. */
 int yg_tc_debug_read(unsigned long long* out, int n);

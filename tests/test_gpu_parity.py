@@ -563,3 +563,33 @@ def test_conv_outputs_stay_inside_their_buffers(shape):
     torch.cuda.synchronize()
     assert intact(dxbuf, dx.numel(), 7.0) and intact(dwbuf, dw.numel(), 7.0) and intact(dbbuf, db.numel(), 7.0)
     assert bool(torch.isfinite(dx.float()).all()) and bool(torch.isfinite(dw).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 19, 35, 16, 32, 1), (1, 8, 32, 16, 32, 1), (3, 21, 37, 32, 64, 2), (2, 40, 70, 16, 32, 1)])
+def test_small_channel_wgrad_on_mma_sync_matches_autograd(shape):
+    """wgrad_hmma.cu (16->32 by default, 32->64 stride 2 with option bit 16) against autograd of the CPU convolution."""
+    N, H, W, Cin, Cout, s = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    lib = L.lib()
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.zeros(Cout)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+    xr = xd.float().permute(0, 3, 1, 2).cpu()
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xr, wr, br, stride=s, padding=1)
+    dz = torch.randn(y.shape, generator=g)
+    dzd = dz.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+    y.backward(dzd.float().permute(0, 3, 1, 2).cpu())
+    lib.yg_set_tc_options(25 + 8192 + 16384 + 65536)
+    try:
+        dw = torch.empty(Cout, Cin, 3, 3, device=DEV)
+        db = torch.empty(Cout, device=DEV)
+        nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, 3, s)
+        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
+        L.check(lib.yg_conv_wgrad(xd.data_ptr(), dzd.data_ptr(), dw.data_ptr(), db.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, 0.0,
+                                  ws.data_ptr(), nb, L.stream()))
+        assert _rel(dw.cpu(), wr.grad) < 1e-4 and _rel(db.cpu(), br.grad) < 1e-4
+    finally:
+        lib.yg_set_tc_options(25 + 8192 + 16384)

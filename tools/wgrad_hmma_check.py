@@ -9,7 +9,7 @@ for (N,H,W,Cin,Cout,s) in [(1,8,32,16,32,1),(2,19,35,16,32,1),(1,8,64,32,64,2),(
     x = torch.randn(N,H,W,Cin,generator=g).to(dev).bfloat16()
     dz = torch.randn(N,Ho,Wo,Cout,generator=g).to(dev).bfloat16()
     res = {}
-    for name,opt in (("tc", 24601), ("hmma", 24601 + 65536)):
+    for name,opt in (("tc", 24601 + 131072), ("hmma", 24601 + 65536)):
         lib.yg_set_tc_options(opt)
         dw = torch.zeros(Cout,Cin,3,3,device=dev); db = torch.zeros(Cout,device=dev)
         nb = lib.yg_conv_wgrad_workspace(N,H,W,Cin,Cout,3,s); ws = torch.empty(max(nb,16),dtype=torch.uint8,device=dev)
