@@ -288,6 +288,73 @@ def test_leaky_relu_sign_mask_equals_saved_activation_path(shape, impl):
         L.set_conv_impl("auto")
 
 
+@pytest.mark.parametrize("shape", [(2, 20, 36, 32, 64, 3, 2), (2, 19, 37, 32, 64, 3, 1), (2, 12, 20, 64, 128, 3, 1),
+                                   (1, 21, 37, 128, 128, 3, 2), (2, 13, 18, 128, 128, 3, 1)])
+@pytest.mark.parametrize("with_bn", [False, True])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_silu_epilogues_vs_torch(shape, with_bn, impl):
+    """silu_model blocks (model_defns.py:80-127): forward = conv + bias + SiLU + Dropout2d with the bf16 pre-activation kept,
+    backward = the next conv's dgrad with SiLU' (through the BatchNorm affine when the block has one) fused into its epilogue."""
+    import ctypes as C
+    N, H, W, Cin, Cout, k, s = shape
+    g = torch.Generator().manual_seed(sum(shape) + int(with_bn))
+    dt = torch.bfloat16
+    lib = L.lib()
+    L.set_conv_impl(impl)
+    try:
+        Cp = 16
+        xp = torch.randn(N, H, W, Cp, generator=g).to(DEV).to(dt)
+        wp = (torch.randn(Cin, Cp, 3, 3, generator=g) / 12)
+        bp = (torch.randn(Cin, generator=g) * 0.1)
+        keep = ((torch.rand(N, Cin, generator=g) > 0.2).float() / 0.8)
+        y = torch.empty(N, H, W, Cin, device=DEV, dtype=dt)
+        pre = torch.empty_like(y)
+        wpd, bpd, kd = wp.to(DEV), bp.to(DEV), keep.to(DEV).contiguous()
+        ep = L.FwdEpilogue(None, bpd.data_ptr(), L.ACT_SILU, kd.data_ptr(), None, pre.data_ptr(), None)
+        L.check(lib.yg_conv_fwd(xp.data_ptr(), wpd.data_ptr(), y.data_ptr(), 1, N, H, W, Cp, Cin, 3, 1, C.byref(ep), L.stream()))
+        pre_ref = torch.nn.functional.conv2d(xp.float().cpu().permute(0, 3, 1, 2), wp, bp, padding=1).permute(0, 2, 3, 1)
+        assert _rel(pre.float().cpu(), pre_ref) < 6e-3
+        # the activation is taken from the rounded pre-activation: compare with torch on exactly that tensor
+        pr = pre.float().cpu()
+        y_ref = torch.nn.functional.silu(pr) * keep[:, None, None, :]
+        torch.testing.assert_close(y.float().cpu(), y_ref, rtol=1e-2, atol=1e-3)
+        # consumer: dx = dgrad(dz) * SiLU'(pre or scale * saved + shift) * dropscale
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).to(dt)
+        w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5)
+        wd = w.to(DEV)
+        sc = (torch.rand(Cin, generator=g) + 0.5)
+        sh = torch.randn(Cin, generator=g) * 0.2
+        mean = torch.randn(Cin, generator=g) * 0.1
+        istd = torch.rand(Cin, generator=g) + 0.5
+        scd, shd, md, isd = sc.to(DEV), sh.to(DEV), mean.to(DEV), istd.to(DEV)
+        dx = torch.empty(N, H, W, Cin, device=DEV, dtype=dt)
+        if with_bn:
+            be = L.BwdEpilogue(pre.data_ptr(), L.ACT_SILU, kd.data_ptr(), scd.data_ptr(), shd.data_ptr(), md.data_ptr(),
+                               isd.data_ptr(), None, None)
+        else:
+            be = L.BwdEpilogue(pre.data_ptr(), L.ACT_SILU, kd.data_ptr(), None, None, None, None, None, None)
+        L.check(lib.yg_conv_dgrad(dz.data_ptr(), wd.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, k, s, C.byref(be), L.stream()))
+        a = (pr * sc + sh) if with_bn else pr
+        a = a.clone().requires_grad_(True)
+        xin = torch.nn.functional.silu(a) * keep[:, None, None, :]
+        torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2), w, None, stride=s, padding=k // 2).backward(
+            dz.float().cpu().permute(0, 3, 1, 2))
+        assert _rel(dx.float().cpu(), a.grad) < 6e-3, _rel(dx.float().cpu(), a.grad)
+        # with the BN sums requested (generic epilogue) the result is the same up to bf16 rounding of the last factor
+        if with_bn:
+            sums = torch.zeros(2 * Cin, dtype=torch.float64, device=DEV)
+            dx2 = torch.empty_like(dx)
+            be2 = L.BwdEpilogue(pre.data_ptr(), L.ACT_SILU, kd.data_ptr(), scd.data_ptr(), shd.data_ptr(), md.data_ptr(),
+                                isd.data_ptr(), sums.data_ptr(), None)
+            L.check(lib.yg_conv_dgrad(dz.data_ptr(), wd.data_ptr(), dx2.data_ptr(), 1, N, H, W, Cin, Cout, k, s, C.byref(be2), L.stream()))
+            torch.testing.assert_close(dx2.float(), dx.float(), rtol=2e-2, atol=2e-3)
+            gsum = a.grad.double().sum((0, 1, 2))
+            assert _rel(sums[:Cin].cpu(), gsum) < 2e-2
+    finally:
+        L.set_conv_impl("auto")
+
+
 # ----------------------------------------------------------------------------- whole model vs golden
 def _build_from_golden(z, name, sdprefix="sd.", dtype=torch.float32, inference=False):
     sd = {k[len(sdprefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(sdprefix)}

@@ -305,6 +305,13 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
+// 1 / (1 + 2^(-x log2 e)) on the SFU: one ex2.approx and one rcp.approx (x -> -inf gives 1 / inf = 0, x -> +inf gives 1)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&a)[16], uint32_t (&b)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
@@ -770,6 +777,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool fast_fwd = MODE == 0 && !e_head_out && !e_has_scale && !e_stats && !e_preact && (BN % 64) == 0 &&
                           (e_act == YG_ACT_LRELU || e_act == YG_ACT_NONE) && !(p.debug & 4) && out != nullptr;
     const bool fast_bwd = MODE == 1 && use_mask && !e_bn_sums && (BN % 64) == 0 && !(p.debug & 4);
+    // SiLU flavours (silu_model): forward = bias + SiLU (+ Dropout2d) with the bf16 pre-activation saved for backward,
+    // backward = SiLU'(saved pre-activation, or saved raw output through the BatchNorm affine) without the BN sums
+    const bool fast_fwd_silu = MODE == 0 && !e_head_out && !e_has_scale && !e_stats && e_preact && e_act == YG_ACT_SILU &&
+                               alt && (BN % 32) == 0 && !(p.debug & 4) && out != nullptr && !e_mask_out;
+    const bool fast_bwd_silu = MODE == 1 && !use_mask && e_saved && e_act == YG_ACT_SILU && !e_bn_sums && alt &&
+                               (BN % 32) == 0 && !(p.debug & 4);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = acc_it;
       const uint32_t acc_phase = acc_phase_it;
@@ -917,6 +930,117 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           for (int i = 0; i < 16; ++i) {
             const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
             ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+          if (valid && !(e_dbg & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+          }
+        }
+      } else if (MODE == 0 && fast_fwd_silu) {
+        bf16* orow = out + pix * e_OC + nt * BN;
+        bf16* prow = reinterpret_cast<bf16*>(e_preact) + pix * e_OC + nt * BN;
+        for (int j = jb; j < j_end; j += 2) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
+          tmem_ld16(taddr0 + (uint32_t)(j * 16 + 16), rb);
+          const int c0 = nt * BN + j * 16;
+          float v[32];
+          {
+            const float4* k4 = reinterpret_cast<const float4*>(s_k1 + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] = t4.x; v[4*i+1] = t4.y; v[4*i+2] = t4.z; v[4*i+3] = t4.w; }
+          }
+          tmem_ld_wait32(ra, rb);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] += __uint_as_float(ra[i]); v[16 + i] += __uint_as_float(rb[i]); }
+          // the saved pre-activation is bf16; the activation is taken from the rounded value (what backward will see)
+          __align__(16) uint32_t pb32[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            pb32[i] = *reinterpret_cast<const uint32_t*>(&pk);
+            const float2 f2 = __bfloat1622float2(pk);
+            v[2 * i] = f2.x; v[2 * i + 1] = f2.y;
+          }
+          if (valid && !(e_dbg & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(prow + j * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(pb32)[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= fast_sigmoid(v[i]);
+          if (e_dropscale) {
+            const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
+          }
+          __align__(16) uint32_t ob32[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+          if (valid && !(e_dbg & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+          }
+        }
+      } else if (MODE == 1 && fast_bwd_silu) {
+        bf16* orow = out + pix * e_OC + nt * BN;
+        const bf16* srow = reinterpret_cast<const bf16*>(e_saved) + pix * e_OC + nt * BN;
+        // the saved row of the next chunk pair is requested one iteration ahead (it sits in L2: prefetched two tiles ago)
+        uint4 nx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nx[i] = (valid && jb < j_end) ? __ldg(reinterpret_cast<const uint4*>(srow + jb * 16) + i) : make_uint4(0, 0, 0, 0);
+        for (int j = jb; j < j_end; j += 2) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
+          tmem_ld16(taddr0 + (uint32_t)(j * 16 + 16), rb);
+          const int c0 = nt * BN + j * 16;
+          uint4 cu[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cu[i] = nx[i];
+          if (j + 2 < j_end && valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nx[i] = __ldg(reinterpret_cast<const uint4*>(srow + (j + 2) * 16) + i);
+          }
+          float pre[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 f2 = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(cu)[i]);
+            pre[2 * i] = f2.x; pre[2 * i + 1] = f2.y;
+          }
+          if (has_bn) {
+            const float4* k0 = reinterpret_cast<const float4*>(s_k0 + c0);
+            const float4* k1 = reinterpret_cast<const float4*>(s_k1 + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a4 = k0[i], b4 = k1[i];
+              pre[4*i] = pre[4*i] * a4.x + b4.x; pre[4*i+1] = pre[4*i+1] * a4.y + b4.y;
+              pre[4*i+2] = pre[4*i+2] * a4.z + b4.z; pre[4*i+3] = pre[4*i+3] * a4.w + b4.w;
+            }
+          }
+          // d(SiLU)/d(pre) = s (1 + pre (1 - s)), times the Dropout2d scale of the channel
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sg = fast_sigmoid(pre[i]);
+            pre[i] = sg * (1.f + pre[i] * (1.f - sg));
+          }
+          if (e_dropscale) {
+            const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; pre[4*i] *= t4.x; pre[4*i+1] *= t4.y; pre[4*i+2] *= t4.z; pre[4*i+3] *= t4.w; }
+          }
+          tmem_ld_wait32(ra, rb);
+          __align__(16) uint32_t ob32[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 pa = __floats2bfloat162_rn(__uint_as_float(ra[2 * i]) * pre[2 * i], __uint_as_float(ra[2 * i + 1]) * pre[2 * i + 1]);
+            const __nv_bfloat162 pb = __floats2bfloat162_rn(__uint_as_float(rb[2 * i]) * pre[16 + 2 * i], __uint_as_float(rb[2 * i + 1]) * pre[16 + 2 * i + 1]);
+            ob32[i] = *reinterpret_cast<const uint32_t*>(&pa);
+            ob32[8 + i] = *reinterpret_cast<const uint32_t*>(&pb);
           }
           if (valid && !(e_dbg & 1)) {
             uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);

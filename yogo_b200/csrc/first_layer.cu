@@ -559,44 +559,57 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 constexpr int FM_WARPS = 4;
 
-__global__ void __launch_bounds__(FM_WARPS * 32, 8) first_bwd_mma_kernel(
+// NM = number of 16-channel M tiles (Cout = 16 NM): the X tile and its two B fragments are shared by all of them
+template <int NM>
+__global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 5) first_bwd_mma_kernel(
     const uint8_t* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ da, int H, int W, int Ho, int Wo,
     int stride, BwdEpi be, const float* __restrict__ fwd_shift, float* __restrict__ partial, int chunk, int cpi, int ntasks) {
-  __shared__ __align__(128) unsigned char tiles[FM_WARPS][2][32 * 32];   // per warp: X and DA tiles, 32 B per pixel row
-  __shared__ float red[10 * FF_CO];
+  constexpr int CO = 16 * NM;
+  __shared__ __align__(128) unsigned char tiles[FM_WARPS][1 + NM][32 * 32];   // per warp: X tile, NM DA tiles (32 B per pixel row)
+  __shared__ float red[10 * CO];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, j = lane & 3;
-  for (int i = threadIdx.x; i < 10 * FF_CO; i += FM_WARPS * 32) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 10 * CO; i += FM_WARPS * 32) red[i] = 0.f;
   // A fragments of the weights, split into two bf16 terms: A[m = ch][k = tap] (taps >= 9 are zero)
-  uint32_t whi[4], wlo[4];
+  uint32_t whi[NM][4], wlo[NM][4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int ch = g + (q & 1) * 8, t0 = 2 * j + (q >> 1) * 8;
-    float hi[2], lo[2];
+  for (int m = 0; m < NM; ++m) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ch = 16 * m + g + (q & 1) * 8, t0 = 2 * j + (q >> 1) * 8;
+      float hi[2], lo[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = (t0 + e < 9) ? w[ch * 9 + t0 + e] : 0.f;
+        hi[e] = __bfloat162float(__float2bfloat16_rn(v));
+        lo[e] = v - hi[e];
+      }
+      whi[m][q] = pack_bf16(hi[0], hi[1]);
+      wlo[m][q] = pack_bf16(lo[0], lo[1]);
+    }
+  }
+  // per-channel constants of this thread's channels (16 m + g, 16 m + g + 8)
+  float c_fsh[NM][2], c_scl[NM][2], c_sft[NM][2], c_ds[NM][2];
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float v = (t0 + e < 9) ? w[ch * 9 + t0 + e] : 0.f;
-      hi[e] = __bfloat162float(__float2bfloat16_rn(v));
-      lo[e] = v - hi[e];
+      const int ch = 16 * m + g + e * 8;
+      c_fsh[m][e] = fwd_shift ? fwd_shift[ch] : 0.f;
+      c_scl[m][e] = be.bn_scale ? be.bn_scale[ch] : 1.f;
+      c_sft[m][e] = be.bn_shift ? be.bn_shift[ch] : 0.f;
+      c_ds[m][e] = 1.f;
     }
-    whi[q] = pack_bf16(hi[0], hi[1]);
-    wlo[q] = pack_bf16(lo[0], lo[1]);
-  }
-  // per-channel constants of this thread's two channels (g, g + 8)
-  float c_fsh[2], c_scl[2], c_sft[2], c_ds[2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int ch = g + e * 8;
-    c_fsh[e] = fwd_shift ? fwd_shift[ch] : 0.f;
-    c_scl[e] = be.bn_scale ? be.bn_scale[ch] : 1.f;
-    c_sft[e] = be.bn_shift ? be.bn_shift[ch] : 0.f;
-    c_ds[e] = 1.f;
   }
   const int act = be.act;
-  float P0[4] = {0.f, 0.f, 0.f, 0.f}, P1[4] = {0.f, 0.f, 0.f, 0.f};
+  float P0[NM][4], P1[NM][4];
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { P0[m][e] = 0.f; P1[m][e] = 0.f; }
+  }
   unsigned char* xt = tiles[warp][0];
-  unsigned char* dt = tiles[warp][1];
-  const uint32_t xt_s = (uint32_t)__cvta_generic_to_shared(xt), dt_s = (uint32_t)__cvta_generic_to_shared(dt);
+  const uint32_t xt_s = (uint32_t)__cvta_generic_to_shared(xt);
   // this lane's row addresses for the three ldmatrix.x4 patterns (see the header comment); rows 4..7 of every group of 8
   // keep their two 16-byte halves swapped so that 8 consecutive rows hit 8 different bank groups
   const int lm = lane >> 3, lr = lane & 7;
@@ -607,22 +620,28 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_bwd_mma_kernel(
     const int n = task / cpi, p0 = (task - n * cpi) * chunk;
     const int p1 = min(p0 + chunk, npix);
     if (be.dropscale) {
-      c_ds[0] = be.dropscale[(long long)n * FF_CO + g];
-      c_ds[1] = be.dropscale[(long long)n * FF_CO + g + 8];
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        c_ds[m][0] = be.dropscale[(long long)n * CO + 16 * m + g];
+        c_ds[m][1] = be.dropscale[(long long)n * CO + 16 * m + g + 8];
+      }
     }
     const uint8_t* xim = x + (long long)n * H * W;
-    const bf16* dim = da + (long long)n * npix * FF_CO;
+    const bf16* dim = da + (long long)n * npix * CO;
     PixCursor cur;
     cur.init(p0 + warp * 32 + lane, Wo);
     for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
       // ---- stage the 32 pixels of this warp: thread = pixel
       {
         float v[9];
-        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        uint4 d[2 * NM];
+#pragma unroll
+        for (int i = 0; i < 2 * NM; ++i) d[i] = make_uint4(0, 0, 0, 0);
         if (cur.p < p1) {
           load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
-          const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)cur.p * FF_CO);
-          d0 = __ldg(gp); d1 = __ldg(gp + 1);
+          const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)cur.p * CO);
+#pragma unroll
+          for (int i = 0; i < 2 * NM; ++i) d[i] = __ldg(gp + i);
         } else {
 #pragma unroll
           for (int t = 0; t < 9; ++t) v[t] = 0.f;
@@ -633,53 +652,65 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_bwd_mma_kernel(
         __syncwarp();   // the previous iteration's ldmatrix reads are done
         *reinterpret_cast<uint4*>(xt + lane * 32 + ((0 ^ sw) << 4)) = x0;
         *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ sw) << 4)) = x1;
-        *reinterpret_cast<uint4*>(dt + lane * 32 + ((0 ^ sw) << 4)) = d0;
-        *reinterpret_cast<uint4*>(dt + lane * 32 + ((1 ^ sw) << 4)) = d1;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          unsigned char* dt = tiles[warp][1 + m];
+          *reinterpret_cast<uint4*>(dt + lane * 32 + ((0 ^ sw) << 4)) = d[2 * m];
+          *reinterpret_cast<uint4*>(dt + lane * 32 + ((1 ^ sw) << 4)) = d[2 * m + 1];
+        }
         __syncwarp();
       }
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {   // two blocks of 16 pixels
-        uint32_t b1[4], b2[4], dd[4];
+        uint32_t b1[4], b2[4];
         ldsm_x4(b1, row_addr(xt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));      // MMA1 B: (k = taps, n = pixels), tiles 0 / 1
         ldsm_x4_t(b2, row_addr(xt_s, kb * 16 + (lm & 1) * 8 + lr, lm >> 1));    // MMA2 B: (k = pixels, n = taps 0-7 / 8-15)
-        ldsm_x4_t(dd, row_addr(dt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));    // DA in the accumulator layout, tiles 0 / 1
-        uint32_t a2[4];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {    // two tiles of 8 pixels
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
-          hmma16816(c, whi, b1[2 * t], b1[2 * t + 1]);
-          hmma16816(c, wlo, b1[2 * t], b1[2 * t + 1]);
-          float gv[4];
+        for (int m = 0; m < NM; ++m) {
+          uint32_t dd[4];
+          const uint32_t dt_s = xt_s + (uint32_t)((1 + m) * 32 * 32);
+          ldsm_x4_t(dd, row_addr(dt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));    // DA in the accumulator layout, tiles 0 / 1
+          uint32_t a2[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int hc = e >> 1;                       // channel g (0) or g + 8 (1); pixel 2j + (e & 1) of the tile
-            const float yv = c[e] + c_fsh[hc];
-            const float pre = be.bn_scale ? yv * c_scl[hc] + c_sft[hc] : yv;
-            const uint32_t dword = dd[2 * t + hc];
-            const float dav = __uint_as_float((e & 1) ? (dword & 0xFFFF0000u) : (dword << 16));
-            gv[e] = dav * act_grad(pre, act) * c_ds[hc];
+          for (int t = 0; t < 2; ++t) {    // two tiles of 8 pixels
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            hmma16816(c, whi[m], b1[2 * t], b1[2 * t + 1]);
+            hmma16816(c, wlo[m], b1[2 * t], b1[2 * t + 1]);
+            float gv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int hc = e >> 1;                       // channel g (0) or g + 8 (1); pixel 2j + (e & 1) of the tile
+              const float yv = c[e] + c_fsh[m][hc];
+              const float pre = be.bn_scale ? yv * c_scl[m][hc] + c_sft[m][hc] : yv;
+              const uint32_t dword = dd[2 * t + hc];
+              const float dav = __uint_as_float((e & 1) ? (dword & 0xFFFF0000u) : (dword << 16));
+              gv[e] = dav * act_grad(pre, act) * c_ds[m][hc];
+            }
+            a2[2 * t] = pack_bf16(gv[0], gv[1]);
+            a2[2 * t + 1] = pack_bf16(gv[2], gv[3]);
           }
-          a2[2 * t] = pack_bf16(gv[0], gv[1]);
-          a2[2 * t + 1] = pack_bf16(gv[2], gv[3]);
+          hmma16816(P0[m], a2, b2[0], b2[1]);
+          hmma16816(P1[m], a2, b2[2], b2[3]);
         }
-        hmma16816(P0, a2, b2[0], b2[1]);
-        hmma16816(P1, a2, b2[2], b2[3]);
       }
     }
   }
   // P fragment: (ch g, taps 2j, 2j+1), (ch g+8, same); second tile: taps 8 + 2j .. -> tap 8 and the sum(g) column
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int ch = g + (e >> 1) * 8, t = 2 * j + (e & 1);
-    atomicAdd(&red[ch * 9 + t], P0[e]);
-    if (j == 0) {
-      if ((e & 1) == 0) atomicAdd(&red[ch * 9 + 8], P1[e]);
-      else atomicAdd(&red[9 * FF_CO + ch], P1[e]);
+  for (int m = 0; m < NM; ++m) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ch = 16 * m + g + (e >> 1) * 8, t = 2 * j + (e & 1);
+      atomicAdd(&red[ch * 9 + t], P0[m][e]);
+      if (j == 0) {
+        if ((e & 1) == 0) atomicAdd(&red[ch * 9 + 8], P1[m][e]);
+        else atomicAdd(&red[9 * CO + ch], P1[m][e]);
+      }
     }
   }
   __syncthreads();
-  float* base = partial + (long long)blockIdx.x * (10 * FF_CO);
-  for (int i = threadIdx.x; i < 10 * FF_CO; i += FM_WARPS * 32) base[i] = red[i];
+  float* base = partial + (long long)blockIdx.x * (10 * CO);
+  for (int i = threadIdx.x; i < 10 * CO; i += FM_WARPS * 32) base[i] = red[i];
 }
 
 
@@ -705,38 +736,42 @@ __device__ __forceinline__ void stage_taps_tile(unsigned char* xt, int lane, con
   *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ sw) << 4)) = x1;
 }
 
-__global__ void __launch_bounds__(FM_WARPS * 32, 8) first_fwd_mma_kernel(
+template <int NM>
+__global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 6) first_fwd_mma_kernel(
     const uint8_t* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int H, int W, int Ho, int Wo,
     int stride, FwdEpi ep, int chunk, int cpi, int ntasks) {
-  __shared__ __align__(128) unsigned char tiles[FM_WARPS][2][32 * 32];   // per warp: X tile, output tile
+  constexpr int CO = 16 * NM;
+  __shared__ __align__(128) unsigned char tiles[FM_WARPS][1 + NM][32 * 32];   // per warp: X tile, NM output tiles of 16 channels
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, j = lane & 3;
-  uint32_t whi[4], wlo[4];
+  uint32_t whi[NM][4], wlo[NM][4];
+  float c_sc[NM][2], c_sh[NM][2], c_ds[NM][2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int ch = g + (q & 1) * 8, t0 = 2 * j + (q >> 1) * 8;
-    float hi[2], lo[2];
+  for (int m = 0; m < NM; ++m) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ch = 16 * m + g + (q & 1) * 8, t0 = 2 * j + (q >> 1) * 8;
+      float hi[2], lo[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = (t0 + e < 9) ? w[ch * 9 + t0 + e] : 0.f;
+        hi[e] = __bfloat162float(__float2bfloat16_rn(v));
+        lo[e] = v - hi[e];
+      }
+      whi[m][q] = pack_bf16(hi[0], hi[1]);
+      wlo[m][q] = pack_bf16(lo[0], lo[1]);
+    }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float v = (t0 + e < 9) ? w[ch * 9 + t0 + e] : 0.f;
-      hi[e] = __bfloat162float(__float2bfloat16_rn(v));
-      lo[e] = v - hi[e];
+      const int ch = 16 * m + g + e * 8;
+      c_sc[m][e] = ep.scale ? ep.scale[ch] : 1.f;
+      c_sh[m][e] = ep.shift ? ep.shift[ch] : 0.f;
+      c_ds[m][e] = 1.f;
     }
-    whi[q] = pack_bf16(hi[0], hi[1]);
-    wlo[q] = pack_bf16(lo[0], lo[1]);
-  }
-  float c_sc[2], c_sh[2], c_ds[2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int ch = g + e * 8;
-    c_sc[e] = ep.scale ? ep.scale[ch] : 1.f;
-    c_sh[e] = ep.shift ? ep.shift[ch] : 0.f;
-    c_ds[e] = 1.f;
   }
   const int act = ep.act;
   unsigned char* xt = tiles[warp][0];
-  unsigned char* yt = tiles[warp][1];
-  const uint32_t xt_s = (uint32_t)__cvta_generic_to_shared(xt), yt_s = (uint32_t)__cvta_generic_to_shared(yt);
+  const uint32_t xt_s = (uint32_t)__cvta_generic_to_shared(xt);
   const int lm = lane >> 3, lr = lane & 7;
   auto row_addr = [](uint32_t base, int px, int half) { return base + (uint32_t)(px * 32 + ((half ^ ((px >> 2) & 1)) << 4)); };
   const int npix = Ho * Wo;
@@ -744,11 +779,14 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_fwd_mma_kernel(
     const int n = task / cpi, p0 = (task - n * cpi) * chunk;
     const int p1 = min(p0 + chunk, npix);
     if (ep.dropscale) {
-      c_ds[0] = ep.dropscale[(long long)n * FF_CO + g];
-      c_ds[1] = ep.dropscale[(long long)n * FF_CO + g + 8];
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        c_ds[m][0] = ep.dropscale[(long long)n * CO + 16 * m + g];
+        c_ds[m][1] = ep.dropscale[(long long)n * CO + 16 * m + g + 8];
+      }
     }
     const uint8_t* xim = x + (long long)n * H * W;
-    bf16* yim = y + (long long)n * npix * FF_CO;
+    bf16* yim = y + (long long)n * npix * CO;
     PixCursor cur;
     cur.init(p0 + warp * 32 + lane, Wo);
     for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
@@ -763,29 +801,37 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_fwd_mma_kernel(
       __syncwarp();
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
-        uint32_t b1[4], o[4];
+        uint32_t b1[4];
         ldsm_x4(b1, row_addr(xt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1));
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
-          hmma16816(c, whi, b1[2 * t], b1[2 * t + 1]);
-          hmma16816(c, wlo, b1[2 * t], b1[2 * t + 1]);
+        for (int m = 0; m < NM; ++m) {
+          uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int hc = e >> 1;
-            c[e] = act_fwd(c[e] * c_sc[hc] + c_sh[hc], act) * c_ds[hc];
+          for (int t = 0; t < 2; ++t) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            hmma16816(c, whi[m], b1[2 * t], b1[2 * t + 1]);
+            hmma16816(c, wlo[m], b1[2 * t], b1[2 * t + 1]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int hc = e >> 1;
+              c[e] = act_fwd(c[e] * c_sc[m][hc] + c_sh[m][hc], act) * c_ds[m][hc];
+            }
+            o[2 * t] = pack_bf16(c[0], c[1]);       // (ch 16 m + g;     pixels 2j, 2j+1 of tile t)
+            o[2 * t + 1] = pack_bf16(c[2], c[3]);   // (ch 16 m + g + 8; same pixels)
           }
-          o[2 * t] = pack_bf16(c[0], c[1]);       // (ch g;     pixels 2j, 2j+1 of tile t)
-          o[2 * t + 1] = pack_bf16(c[2], c[3]);   // (ch g + 8; same pixels)
+          stsm_x4_t(row_addr(xt_s + (uint32_t)((1 + m) * 32 * 32), kb * 16 + (lm >> 1) * 8 + lr, lm & 1), o);
         }
-        stsm_x4_t(row_addr(yt_s, kb * 16 + (lm >> 1) * 8 + lr, lm & 1), o);
       }
       __syncwarp();
       if (cur.p < p1) {
         const int sw = (lane >> 2) & 1;
-        uint4* dst = reinterpret_cast<uint4*>(yim + (long long)cur.p * FF_CO);
-        dst[0] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((0 ^ sw) << 4));
-        dst[1] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((1 ^ sw) << 4));
+        uint4* dst = reinterpret_cast<uint4*>(yim + (long long)cur.p * CO);
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          const unsigned char* yt = tiles[warp][1 + m];
+          dst[2 * m] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((0 ^ sw) << 4));
+          dst[2 * m + 1] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((1 ^ sw) << 4));
+        }
       }
     }
   }
@@ -872,16 +918,20 @@ extern "C" int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, voi
   FwdEpi ep = make_fwd_epi(epp);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 1 && (Cout == 16 || Cout == 32 || Cout == 48) && dtype == YG_BF16 && !ep.preact && (long long)Ho * Wo < (1LL << 30) &&
+      (long long)H * W < (1LL << 31) && x_dtype == YG_U8 && !ep.stats && y && yg_get_conv_impl() != YG_IMPL_SIMT) {
+    // warp-level tensor cores, one M tile per 16 output channels (base 16, double_filters 32, triple_filters 48)
+    const int chunkm = 16 * FM_WARPS * 32, cpim = cdiv((long long)Ho * Wo, chunkm), ntasksm = N * cpim;
+    const int per_sm = Cout == 16 ? 8 : 6;
+    const int gridm = ntasksm < 148 * per_sm ? ntasksm : 148 * per_sm;
+#define LAUNCHM(NM) first_fwd_mma_kernel<NM><<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunkm, cpim, ntasksm)
+    if (Cout == 16) LAUNCHM(1); else if (Cout == 32) LAUNCHM(2); else LAUNCHM(3);
+#undef LAUNCHM
+    YG_LAUNCH_CHECK("conv_first_fwd_mma");
+    return YG_OK;
+  }
   if (Cin == 1 && Cout == FF_CO && dtype == YG_BF16 && !ep.preact && (long long)Ho * Wo < (1LL << 30) &&
       (long long)H * W < (1LL << 31)) {
-    if (x_dtype == YG_U8 && !ep.stats && y && yg_get_conv_impl() != YG_IMPL_SIMT) {
-      const int chunkm = 16 * FM_WARPS * 32, cpim = cdiv((long long)Ho * Wo, chunkm), ntasksm = N * cpim;
-      const int gridm = ntasksm < 148 * 8 ? ntasksm : 148 * 8;
-      first_fwd_mma_kernel<<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunkm, cpim,
-                                                            ntasksm);
-      YG_LAUNCH_CHECK("conv_first_fwd_mma");
-      return YG_OK;
-    }
     const int chunk = 16 * FL_THREADS, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
     const int grid1 = ntasks < 148 * 3 ? ntasks : 148 * 3;
 #define LAUNCHF(TX, ST) first_fwd16_kernel<TX, ST><<<grid1, FL_THREADS, 0, st>>>((const TX*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunk, cpi, ntasks)
@@ -929,13 +979,14 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
       return YG_ERR_WORKSPACE;
     }
   }
-  if (mode == 1 && Cin == 1 && Cout == FF_CO && dtype == YG_BF16 && x_dtype == YG_U8 && !bn_dy_mean && Wo >= 32 &&
-      (long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31) && yg_get_conv_impl() != YG_IMPL_SIMT) {
-    // raw P / Sg pass on the tensor cores (first_bwd_mma_kernel)
+  if (mode == 1 && Cin == 1 && (Cout == 16 || Cout == 32 || Cout == 48) && dtype == YG_BF16 && x_dtype == YG_U8 && !bn_dy_mean &&
+      Wo >= 32 && (long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31) && yg_get_conv_impl() != YG_IMPL_SIMT) {
+    // raw P / Sg pass on the tensor cores (first_bwd_mma_kernel), one M tile per 16 output channels
     const int chunk = 64 * FM_WARPS * 32, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
     const int grid1 = ntasks < FL_BWD_BLOCKS ? ntasks : FL_BWD_BLOCKS;
-    first_bwd_mma_kernel<<<grid1, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be,
-                                                          fwd_shift, (float*)workspace, chunk, cpi, ntasks);
+#define LAUNCHM(NM) first_bwd_mma_kernel<NM><<<grid1, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be, fwd_shift, (float*)workspace, chunk, cpi, ntasks)
+    if (Cout == 16) LAUNCHM(1); else if (Cout == 32) LAUNCHM(2); else LAUNCHM(3);
+#undef LAUNCHM
     YG_LAUNCH_CHECK("conv_first_bwd_mma");
     wgrad_reduce_kernel2<<<cdiv((nw + Cout) * 32, 256), 256, 0, st>>>((const float*)workspace, dw, dshift, nw, Cout, grid1, clip);
     YG_LAUNCH_CHECK("conv_first_bwd reduce");

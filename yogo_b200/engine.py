@@ -342,10 +342,14 @@ class Runner:
                 ep = L.BwdEpilogue(rec["out"].data_ptr(), blk.act, L.ptr(rec["dropscale"]), None, None, None, None, None,
                                    rec["actmask"].data_ptr())
             elif blk.bn is not None:
-                sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                # SiLU (or LeakyReLU without a mask) after BatchNorm: the epilogue recomputes the BN output from the saved raw
+                # conv output.  With 8-channel-aligned rows the two BN sums come from the streaming pass (yg_bn_bwd_sums),
+                # which keeps the epilogue on its straight-line path; otherwise it reduces them itself.
+                if blk.cout % 8 != 0:
+                    sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
                 ep = L.BwdEpilogue(rec["saved"].data_ptr(), blk.act, L.ptr(rec["dropscale"]),
                                    rec["scale"].data_ptr(), rec["shift"].data_ptr(), rec["mean"].data_ptr(),
-                                   rec["invstd"].data_ptr(), sums.data_ptr())
+                                   rec["invstd"].data_ptr(), L.ptr(sums))
             else:
                 sv = rec["saved"] if blk.act != L.ACT_NONE else None
                 # d(bias) of this block comes from its own wgrad call (a ones column in the tcgen05 kernel)
