@@ -355,6 +355,60 @@ def test_silu_epilogues_vs_torch(shape, with_bn, impl):
         L.set_conv_impl("auto")
 
 
+@pytest.mark.parametrize("Cout", [16, 32, 48])
+@pytest.mark.parametrize("act", [1, 2])
+def test_first_layer_tensor_core_kernels_vs_torch(Cout, act):
+    """1 -> 16 / 32 / 48 channels, stride 2, uint8 image (base / double_filters / triple_filters, model_defns.py:39, 139, 189):
+    forward = conv * scale + shift -> activation -> Dropout2d scale; backward = raw sums P[c][t] = sum g x_t and sum g with
+    g = da * act'(pre) * dropscale, both on mma.sync with split-bf16 weights (first_layer.cu)."""
+    import ctypes as C
+    N, H, W = 3, 70, 90
+    g = torch.Generator().manual_seed(Cout + act)
+    lib = L.lib()
+    img = torch.randint(0, 256, (N, 1, H, W), dtype=torch.uint8, generator=g)
+    w = torch.randn(Cout, 1, 3, 3, generator=g) / 300.0
+    sc = torch.rand(Cout, generator=g) + 0.5
+    sh = torch.randn(Cout, generator=g) * 0.3
+    keep = ((torch.rand(N, Cout, generator=g) > 0.2).float() / 0.8)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    xd, wd, scd, shd, kd = img.to(DEV), w.to(DEV), sc.to(DEV), sh.to(DEV), keep.to(DEV).contiguous()
+    y = torch.empty(N, Ho, Wo, Cout, device=DEV, dtype=torch.bfloat16)
+    ep = L.FwdEpilogue(scd.data_ptr(), shd.data_ptr(), act, kd.data_ptr(), None, None)
+    L.check(lib.yg_conv_first_fwd(xd.data_ptr(), L.YG_U8, wd.data_ptr(), y.data_ptr(), 1, N, H, W, 1, Cout, 2, C.byref(ep), L.stream()))
+    z = torch.nn.functional.conv2d(img.float(), w, None, stride=2, padding=1)
+    pre = (z * sc[None, :, None, None] + sh[None, :, None, None]).requires_grad_(True)
+    a = O._act(pre, {1: "lrelu", 2: "silu"}[act]) * keep[:, :, None, None]
+    assert _rel(y.float().cpu().permute(0, 3, 1, 2), a.detach()) < 4e-3
+    da = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).bfloat16()
+    a.backward(da.float().cpu().permute(0, 3, 1, 2))
+    gpre = pre.grad
+    dw_ref = torch.nn.grad.conv2d_weight(img.float(), (Cout, 1, 3, 3), gpre, stride=2, padding=1)
+    ds_ref = gpre.sum((0, 2, 3))
+    dw = torch.empty(Cout, 1, 3, 3, device=DEV)
+    dsh = torch.empty(Cout, device=DEV)
+    nb = lib.yg_conv_first_bwd_workspace(1, Cout)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    be = L.BwdEpilogue(None, act, kd.data_ptr(), scd.data_ptr(), shd.data_ptr(), None, None, None, None)
+    L.check(lib.yg_conv_first_bwd(xd.data_ptr(), L.YG_U8, wd.data_ptr(), da.data_ptr(), 1, N, H, W, 1, Cout, 2, C.byref(be),
+                                  None, None, None, dw.data_ptr(), dsh.data_ptr(), 0.0, ws.data_ptr(), nb, L.stream()))
+    # g is rounded to bf16 before the P = g . X product (2^-9 relative per term, random sign)
+    assert _rel(dw.cpu(), dw_ref) < 3e-3, _rel(dw.cpu(), dw_ref)
+    assert _rel(dsh.cpu(), ds_ref) < 3e-3
+    # the SIMT kernels (any channel count) agree
+    L.set_conv_impl("simt")
+    try:
+        y2 = torch.empty_like(y)
+        L.check(lib.yg_conv_first_fwd(xd.data_ptr(), L.YG_U8, wd.data_ptr(), y2.data_ptr(), 1, N, H, W, 1, Cout, 2, C.byref(ep), L.stream()))
+        dw2 = torch.empty_like(dw)
+        dsh2 = torch.empty_like(dsh)
+        L.check(lib.yg_conv_first_bwd(xd.data_ptr(), L.YG_U8, wd.data_ptr(), da.data_ptr(), 1, N, H, W, 1, Cout, 2, C.byref(be),
+                                      None, None, None, dw2.data_ptr(), dsh2.data_ptr(), 0.0, ws.data_ptr(), nb, L.stream()))
+    finally:
+        L.set_conv_impl("auto")
+    assert _rel(y2.float().cpu(), y.float().cpu()) < 4e-3
+    assert _rel(dw2.cpu(), dw_ref) < 3e-3 and _rel(dsh2.cpu(), ds_ref) < 3e-3
+
+
 # ----------------------------------------------------------------------------- whole model vs golden
 def _build_from_golden(z, name, sdprefix="sd.", dtype=torch.float32, inference=False):
     sd = {k[len(sdprefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(sdprefix)}

@@ -151,6 +151,108 @@ __global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, 
   }
 }
 
+// Channel-group variants of the two elementwise passes (C % 8 == 0): thread = (8-channel group, pixel lane) like
+// bn_colsums_kernel, so the per-channel constants are loaded ONCE into registers and the inner loop is
+// 16-byte load(s) -> 8 FMAs -> 16-byte store.  (The flat-index kernels above fetch every constant per element with a
+// lane stride of 8 floats: 8 L1 wavefronts / 8-way bank conflicts per load, which capped them at ~1.8 TB/s.)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_apply_cg_kernel(const T* __restrict__ y, T* __restrict__ a, long long npix, int HW,
+                                                              int C, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int act,
+                                                              const float* __restrict__ dropscale,
+                                                              unsigned char* __restrict__ actmask) {
+  const int groups = C >> 3, lanes = blockDim.x / groups;
+  const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+  if (pl >= lanes) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+  constexpr int U = 4;
+  constexpr int V = (int)(sizeof(T) * 8 / 16);
+  const long long pstride = (long long)gridDim.x * lanes;
+  for (long long px0 = (long long)blockIdx.x * lanes + pl; px0 < npix; px0 += U * pstride) {
+    __align__(16) T in[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long px = px0 + u * pstride;
+      if (px < npix) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(in[u])[v] = __ldg(reinterpret_cast<const uint4*>(y + px * C + cg * 8) + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long px = px0 + u * pstride;
+      if (px >= npix) break;
+      const float* dsr = dropscale ? dropscale + (px / HW) * C + cg * 8 : nullptr;
+      __align__(16) T out[8];
+      unsigned bits = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = to_f<T>(in[u][k]) * sc[k] + sh[k];
+        bits |= (v > 0.f ? 1u : 0u) << k;
+        v = act_fwd(v, act);
+        if (dsr) v *= dsr[k];
+        out[k] = from_f<T>(v);
+      }
+      const long long i0 = px * C + cg * 8;
+#pragma unroll
+      for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(a + i0)[v] = reinterpret_cast<uint4*>(out)[v];
+      if (actmask) actmask[i0 >> 3] = (unsigned char)bits;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_cg_kernel(T* __restrict__ g, const T* __restrict__ y, long long npix, int C,
+                                                              double M, const double* __restrict__ sums,
+                                                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, int batch_stats) {
+  extern __shared__ float kc[];  // [3][C]: A, B, K (same constants as bn_bwd_apply_kernel)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m1 = batch_stats ? (float)(sums[c] / M) : 0.f, m2 = batch_stats ? (float)(sums[C + c] / M) : 0.f;
+    const float gi = (gamma ? gamma[c] : 1.f) * invstd[c];
+    kc[c] = gi;
+    kc[C + c] = -gi * m2 * invstd[c];
+    kc[2 * C + c] = gi * (m2 * invstd[c] * mean[c] - m1);
+  }
+  __syncthreads();
+  const int groups = C >> 3, lanes = blockDim.x / groups;
+  const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+  if (pl >= lanes) return;
+  float ka[8], kb[8], kk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { ka[k] = kc[cg * 8 + k]; kb[k] = kc[C + cg * 8 + k]; kk[k] = kc[2 * C + cg * 8 + k]; }
+  constexpr int U = 4;
+  constexpr int V = (int)(sizeof(T) * 8 / 16);
+  const long long pstride = (long long)gridDim.x * lanes;
+  for (long long px0 = (long long)blockIdx.x * lanes + pl; px0 < npix; px0 += U * pstride) {
+    __align__(16) T gin[U][8];
+    __align__(16) T yin[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long px = px0 + u * pstride;
+      if (px < npix) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          reinterpret_cast<uint4*>(gin[u])[v] = reinterpret_cast<const uint4*>(g + px * C + cg * 8)[v];
+          reinterpret_cast<uint4*>(yin[u])[v] = __ldg(reinterpret_cast<const uint4*>(y + px * C + cg * 8) + v);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long px = px0 + u * pstride;
+      if (px >= npix) break;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        gin[u][k] = from_f<T>(to_f<T>(gin[u][k]) * ka[k] + to_f<T>(yin[u][k]) * kb[k] + kk[k]);
+#pragma unroll
+      for (int v = 0; v < V; ++v) reinterpret_cast<uint4*>(g + px * C + cg * 8)[v] = reinterpret_cast<uint4*>(gin[u])[v];
+    }
+  }
+}
+
 // Per-channel sums over an NHWC tensor with 16-byte loads: MODE 0: sum(y), sum(y*y) (BatchNorm batch statistics);
 // MODE 1: sum(g), sum(g * xhat) with xhat = (y - mean) * invstd (BatchNorm backward).  One streaming pass at HBM speed
 // (cheaper than a 31-shuffle transpose-reduce per 16-column chunk in the epilogue of the producing convolution).
@@ -172,20 +274,31 @@ __global__ void __launch_bounds__(256) bn_colsums_kernel(const T* __restrict__ a
   }
   if (pl < lanes) {
     constexpr int V = (int)(sizeof(T) * 8 / 16);
-    for (long long px = (long long)blockIdx.x * lanes + pl; px < npix; px += (long long)gridDim.x * lanes) {
-      __align__(16) T av[8];
-      __align__(16) T yv[8];
-      const long long off = px * C + cg * 8;
+    constexpr int U = 4;   // independent 16-byte loads in flight per thread; the per-thread summation order is unchanged
+    const long long pstride = (long long)gridDim.x * lanes;
+    for (long long px0 = (long long)blockIdx.x * lanes + pl; px0 < npix; px0 += U * pstride) {
+      __align__(16) T av[U][8];
+      __align__(16) T yv[U][8];
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        reinterpret_cast<uint4*>(av)[v] = __ldg(reinterpret_cast<const uint4*>(a + off) + v);
-        if (MODE == 1) reinterpret_cast<uint4*>(yv)[v] = __ldg(reinterpret_cast<const uint4*>(y + off) + v);
+      for (int u = 0; u < U; ++u) {
+        const long long off = (px0 + u * pstride) * C + cg * 8;
+        if (px0 + u * pstride < npix) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            reinterpret_cast<uint4*>(av[u])[v] = __ldg(reinterpret_cast<const uint4*>(a + off) + v);
+            if (MODE == 1) reinterpret_cast<uint4*>(yv[u])[v] = __ldg(reinterpret_cast<const uint4*>(y + off) + v);
+          }
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float x = to_f<T>(av[k]);
-        s1[k] += x;
-        s2[k] += (MODE == 0) ? x * x : x * ((to_f<T>(yv[k]) - mu[k]) * is[k]);
+      for (int u = 0; u < U; ++u) {
+        if (px0 + u * pstride >= npix) break;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float x = to_f<T>(av[u][k]);
+          s1[k] += x;
+          s2[k] += (MODE == 0) ? x * x : x * ((to_f<T>(yv[u][k]) - mu[k]) * is[k]);
+        }
       }
     }
 #pragma unroll
@@ -240,6 +353,18 @@ extern "C" int yg_bn_act_apply(const void* y, void* a, int dtype, int N, int HW,
   YG_CHECK_ARG(!actmask || (C & 7) == 0, "bn_act_apply: actmask needs C % 8 == 0");
   const long long total = (long long)N * HW * C;
   if (total == 0) return YG_OK;
+  if ((C & 7) == 0 && C / 8 <= 256) {
+    const long long npix = (long long)N * HW;
+    const int lanes = 256 / (C / 8);
+    long long want = cdiv(cdiv(npix, (long long)lanes), 4LL);
+    const int blocks_cg = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
+    if (dtype == YG_BF16)
+      bn_act_apply_cg_kernel<bf16><<<blocks_cg, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, npix, HW, C, scale, shift, act, dropscale, (unsigned char*)actmask);
+    else
+      bn_act_apply_cg_kernel<float><<<blocks_cg, 256, 0, (cudaStream_t)stream>>>((const float*)y, (float*)a, npix, HW, C, scale, shift, act, dropscale, (unsigned char*)actmask);
+    YG_LAUNCH_CHECK("bn_act_apply");
+    return YG_OK;
+  }
   const int blocks = cdiv(cdiv(total, 8), 256 * 4);   // 4 vectors of 8 elements per thread
   if (dtype == YG_BF16)
     bn_act_apply_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, total, HW, C, scale, shift, act, dropscale, (unsigned char*)actmask);
@@ -294,6 +419,17 @@ extern "C" int yg_bn_bwd_apply(void* g, const void* y, int dtype, int N, int HW,
     if (blocks > 148 * 8) blocks = 148 * 8;
     const double M = (double)N * HW;
     const size_t sm = (size_t)3 * C * sizeof(float);
+    if ((C & 7) == 0 && C / 8 <= 256) {
+      const long long npix = (long long)N * HW;
+      const int lanes = 256 / (C / 8);
+      long long want = cdiv(cdiv(npix, (long long)lanes), 4LL);
+      const int blocks_cg = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
+      if (dtype == YG_BF16)
+        bn_bwd_apply_cg_kernel<bf16><<<blocks_cg, 256, sm, st>>>((bf16*)g, (const bf16*)y, npix, C, M, sums, gamma, mean, invstd, batch_stats);
+      else
+        bn_bwd_apply_cg_kernel<float><<<blocks_cg, 256, sm, st>>>((float*)g, (const float*)y, npix, C, M, sums, gamma, mean, invstd, batch_stats);
+      YG_LAUNCH_CHECK("bn_bwd_apply");
+    } else
     if (dtype == YG_BF16)
       bn_bwd_apply_kernel<bf16><<<blocks, 256, sm, st>>>((bf16*)g, (const bf16*)y, total, C, M, sums, gamma, mean, invstd, batch_stats);
     else

@@ -561,7 +561,7 @@ constexpr int FM_WARPS = 4;
 
 // NM = number of 16-channel M tiles (Cout = 16 NM): the X tile and its two B fragments are shared by all of them
 template <int NM>
-__global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 5) first_bwd_mma_kernel(
+__global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : (NM == 2 ? 5 : 4)) first_bwd_mma_kernel(
     const uint8_t* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ da, int H, int W, int Ho, int Wo,
     int stride, BwdEpi be, const float* __restrict__ fwd_shift, float* __restrict__ partial, int chunk, int cpi, int ntasks) {
   constexpr int CO = 16 * NM;
