@@ -209,6 +209,14 @@ int yg_format_preds_batch(const float* preds, int B, int num_classes, int Sy, in
                           int* keep_count, float* rows, int* keep_index, long long* class_counts,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- evaluation matching ------------------------------------------------
+ * cost[i][j] = 1 - IoU(label box i, prediction box j), the matrix format_preds_and_labels_v2 gives to the Hungarian
+ * solver (utils/prediction_formatting.py:296-298, torchvision.ops.box_iou); bit-identical to the reference's.
+ * labels / preds: rows of label_stride / pred_stride floats whose first four are xyxy (pass labels + 1 for
+ * [mask, x1, y1, x2, y2, class] rows); cost (n_labels, n_preds) fp32, row-major. */
+int yg_box_iou_cost(const float* labels, int label_stride, int n_labels, const float* preds, int pred_stride,
+                    int n_preds, float* cost, void* stream);
+
 /* ---- optimizer: fused AdamW over one flat fp32 buffer ---------------
  * replaces torch.optim.AdamW.step (train.py:213-217, 324). grads are pre-scaled by
  * grad_scale (1/world_size after an all-reduce SUM). */

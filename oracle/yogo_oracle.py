@@ -492,6 +492,76 @@ def prediction_class_counts_np(
 
 
 # ----------------------------------------------------------------------------------------
+# Evaluation matching: format_preds_and_labels_v2
+# (/root/reference/yogo/utils/prediction_formatting.py:254-330; torchvision.ops.box_iou, boxes.py _box_inter_union)
+# ----------------------------------------------------------------------------------------
+def box_iou_cost_np(labels_xyxy: np.ndarray, preds_xyxy: np.ndarray) -> np.ndarray:
+    """1 - box_iou(labels, preds) in fp32, operation by operation as torchvision computes it."""
+    a = np.asarray(labels_xyxy, dtype=np.float32).reshape(-1, 4)
+    b = np.asarray(preds_xyxy, dtype=np.float32).reshape(-1, 4)
+    area1 = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area2 = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt = np.maximum(a[:, None, :2], b[None, :, :2])
+    rb = np.minimum(a[:, None, 2:], b[None, :, 2:])
+    wh = rb - lt
+    wh = np.where(wh < 0, np.float32(0), wh)
+    inter = wh[:, :, 0] * wh[:, :, 1]
+    union = (area1[:, None] + area2[None, :]) - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = inter / union
+    return (np.float32(1) - iou).astype(np.float32)
+
+
+def match_preds_and_labels_np(
+    pred: np.ndarray, label: np.ndarray, objectness_thresh: float = 0.5, min_class_confidence_threshold: float = 0.0
+):
+    """Returns (matched preds, matched labels, missed labels, extra predictions) like PredictionLabelMatch."""
+    from scipy.optimize import linear_sum_assignment
+
+    fp = format_preds_np(pred, objectness_thresh, 0.5, "xyxy", min_class_confidence_threshold)
+    Ls, Sy, Sx = label.shape
+    labels = np.asarray(label, dtype=np.float32).reshape(Ls, Sy * Sx).T
+    fl = labels[labels[:, 0] != 0]
+    cost = box_iou_cost_np(fl[:, 1:5], fp[:, :4])
+    rows, cols = linear_sum_assignment(cost)
+    pred_free = np.ones(fp.shape[0], dtype=bool)
+    pred_free[cols] = False
+    label_free = np.ones(fl.shape[0], dtype=bool)
+    label_free[rows] = False
+    return fp[cols], fl[rows], fl[label_free], fp[pred_free]
+
+
+def synth_labels_for_preds(pred: torch.Tensor, drop: float = 0.2, extra: int = 5, seed: int = 3) -> torch.Tensor:
+    """Label tensor (6, Sy, Sx) for one synthetic prediction tensor (5 + C, Sy, Sx): the boxes that survive
+    threshold + NMS, jittered by a few percent, minus a fraction `drop` (those predictions become extras), plus `extra`
+    anchor-sized labels at random empty cells (missed labels).  Layout [mask, x1, y1, x2, y2, class]."""
+    g = torch.Generator().manual_seed(seed)
+    D, Sy, Sx = pred.shape
+    rows = format_preds_np(pred.numpy(), 0.5, 0.5, "xyxy", 0.0)
+    lab = torch.zeros(6, Sy, Sx)
+    for r in rows:
+        if float(torch.rand((), generator=g)) < drop:
+            continue
+        jit = (torch.rand(4, generator=g) - 0.5) * 0.004
+        box = torch.from_numpy(r[:4].copy()) + jit
+        cx, cy = float((box[0] + box[2]) / 2), float((box[1] + box[3]) / 2)
+        i, j = min(max(int(cx * Sx), 0), Sx - 1), min(max(int(cy * Sy), 0), Sy - 1)
+        lab[0, j, i] = 1
+        lab[1:5, j, i] = box
+        lab[5, j, i] = float(int(np.argmax(r[5:])))
+    for _ in range(extra):
+        j = int(torch.randint(0, Sy, (), generator=g))
+        i = int(torch.randint(0, Sx, (), generator=g))
+        if lab[0, j, i] != 0:
+            continue
+        cx, cy = (i + 0.5) / Sx, (j + 0.5) / Sy
+        lab[0, j, i] = 1
+        lab[1:5, j, i] = torch.tensor([cx - ANCHOR_W / 2, cy - ANCHOR_H / 2, cx + ANCHOR_W / 2, cy + ANCHOR_H / 2])
+        lab[5, j, i] = float(int(torch.randint(0, D - 5, (), generator=g)))
+    return lab
+
+
+# ----------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY.md 8d) - shared by tests and bench so every arm sees the same data
 # ----------------------------------------------------------------------------------------
 ANCHOR_W = 0.04250100424705710  # default_hyperparams.py:12

@@ -35,6 +35,7 @@ def import_reference():
     from yogo.model_defns import get_model_func
     from yogo.yogo_loss import YOGOLoss
     from yogo.utils import format_preds
+    from yogo.utils.prediction_formatting import format_preds_and_labels_v2, format_to_numpy, PredictionLabelMatch
     from yogo.infer import get_prediction_class_counts, count_cells_for_formatted_preds
 
     return dict(
@@ -42,6 +43,9 @@ def import_reference():
         get_model_func=get_model_func,
         YOGOLoss=YOGOLoss,
         format_preds=format_preds,
+        format_preds_and_labels_v2=format_preds_and_labels_v2,
+        format_to_numpy=format_to_numpy,
+        PredictionLabelMatch=PredictionLabelMatch,
         get_prediction_class_counts=get_prediction_class_counts,
         count_cells_for_formatted_preds=count_cells_for_formatted_preds,
     )
@@ -167,6 +171,38 @@ def golden_nms(ref, out):
     cases["nmsD_offsets"] = np.array(offs, dtype=np.int64)
     cases["nmsD_counts"] = ref["get_prediction_class_counts"](p.clone()).numpy().astype(np.int64)
     np.savez_compressed(os.path.join(out, "nms.npz"), **cases)
+
+
+def golden_match(ref, out):
+    """format_preds_and_labels_v2 / convert_background_errors / format_to_numpy of the real reference."""
+    from oracle.yogo_oracle import synth_sparse_preds, synth_labels_for_preds
+
+    cases = {}
+    configs = [
+        # (Sy, Sx, C, K, seed, obj, mincls, drop, extra)
+        (20, 28, 7, 40, 41, 0.5, 0.0, 0.2, 5),
+        (97, 129, 7, 300, 42, 0.5, 0.0, 0.1, 12),
+        (16, 16, 4, 30, 43, 0.6, 0.5, 0.3, 3),
+        (12, 12, 7, 20, 44, 0.5, 0.0, 1.0, 4),   # labels only at empty cells: every match has cost 1 (ties)
+        (12, 12, 7, 6, 45, 0.5, 0.0, 0.0, 40),   # more labels than predictions: missed labels
+    ]
+    for ci, (Sy, Sx, C, K, seed, obj, mincls, drop, extra) in enumerate(configs):
+        p = synth_sparse_preds(1, Sy, Sx, C, K, seed=seed)[0]
+        lab = synth_labels_for_preds(p, drop=drop, extra=extra, seed=seed)
+        m = ref["format_preds_and_labels_v2"](p.clone(), lab.clone(), objectness_thresh=obj,
+                                              min_class_confidence_threshold=mincls)
+        cases[f"m{ci}_pred"] = p.numpy()
+        cases[f"m{ci}_label"] = lab.numpy()
+        cases[f"m{ci}_cfg"] = np.array([obj, mincls], dtype=np.float64)
+        cases[f"m{ci}_preds"] = m.preds.numpy()
+        cases[f"m{ci}_labels"] = m.labels.numpy()
+        cases[f"m{ci}_missed"] = m.missed_labels.numpy()
+        cases[f"m{ci}_extra"] = m.extra_predictions.numpy()
+        cb = m.convert_background_errors(C + 1)
+        cases[f"m{ci}_bg_preds"] = cb.preds.numpy()
+        cases[f"m{ci}_bg_labels"] = cb.labels.numpy()
+        cases[f"m{ci}_npy"] = ref["format_to_numpy"](7, p.numpy().copy(), 772, 1032)
+    np.savez_compressed(os.path.join(out, "match.npz"), **cases)
 
 
 GRAD_STRIDE = 5
@@ -303,8 +339,12 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     torch.use_deterministic_algorithms(True)
     ref = import_reference()
+    if "--only-match" in sys.argv:   # regenerate match.npz alone
+        golden_match(ref, HERE)
+        sys.exit(0)
     golden_loss(ref, HERE)
     golden_nms(ref, HERE)
+    golden_match(ref, HERE)
     golden_model(ref, HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

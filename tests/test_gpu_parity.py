@@ -160,6 +160,91 @@ def test_format_preds_dense_full_size_and_idempotence():
     assert np.array_equal(rows2[0, : kc[0]].cpu().numpy().view(np.uint32), rows[0, : kc[0]].cpu().numpy().view(np.uint32))
 
 
+# ----------------------------------------------------------------------------- evaluation matching
+@pytest.mark.parametrize("case", ["m0", "m1", "m2", "m3", "m4"])
+def test_format_preds_and_labels_v2_bit_exact_vs_reference_golden(golden_dir, case):
+    """prediction_formatting.py:254-330 (+ :96-156, :206-251) of the real reference vs the CUDA path: threshold + NMS kernel,
+    pairwise-IoU cost kernel, scipy assignment on the bit-identical matrix."""
+    from yogo_b200.utils import format_preds_and_labels_v2, format_to_numpy
+    z = _load(golden_dir, "match.npz")
+    obj, mincls = z[case + "_cfg"]
+    pred = torch.from_numpy(z[case + "_pred"]).to(DEV)
+    label = torch.from_numpy(z[case + "_label"]).to(DEV)
+    m = format_preds_and_labels_v2(pred, label, objectness_thresh=float(obj), min_class_confidence_threshold=float(mincls))
+    for got, key in ((m.preds, "_preds"), (m.labels, "_labels"), (m.missed_labels, "_missed"), (m.extra_predictions, "_extra")):
+        exp = z[case + key].astype(np.float32)
+        assert tuple(got.shape) == exp.shape, key
+        assert np.array_equal(got.cpu().numpy().view(np.uint32), exp.view(np.uint32)), key
+    C = pred.shape[0] - 5
+    cb = m.convert_background_errors(C + 1)
+    assert cb.missed_labels is None and cb.extra_predictions is None
+    assert np.array_equal(cb.preds.cpu().numpy(), z[case + "_bg_preds"].astype(np.float32))
+    assert np.array_equal(cb.labels.cpu().numpy(), z[case + "_bg_labels"].astype(np.float32))
+    npy = format_to_numpy(7, z[case + "_pred"], 772, 1032)
+    assert npy.dtype == z[case + "_npy"].dtype and np.array_equal(npy, z[case + "_npy"])
+
+
+def test_box_iou_cost_full_size_vs_oracle_and_torchvision():
+    from yogo_b200.utils import box_iou_cost
+    import torchvision.ops as ops
+    g = torch.Generator().manual_seed(5)
+    n, m = 700, 2347
+    def boxes(k):
+        c = torch.rand(k, 2, generator=g)
+        wh = torch.rand(k, 2, generator=g) * 0.08
+        return torch.cat([c - wh / 2, c + wh / 2], 1)
+    a, b = boxes(n), boxes(m)
+    a[3] = a[4]                      # duplicates
+    b[10, 2:] = b[10, :2]            # zero-area prediction
+    lab = torch.cat([torch.ones(n, 1), a, torch.zeros(n, 1)], 1).to(DEV)
+    rows = torch.cat([b, torch.rand(m, 8, generator=g)], 1).to(DEV)
+    cost = box_iou_cost(lab[:, 1:5], rows[:, :4]).cpu().numpy()
+    assert np.array_equal(cost.view(np.uint32), O.box_iou_cost_np(a.numpy(), b.numpy()).view(np.uint32))
+    assert np.array_equal(cost.view(np.uint32), (1 - ops.box_iou(a, b).numpy()).view(np.uint32))
+    assert box_iou_cost(lab[:0, 1:5], rows[:, :4]).shape == (0, m)
+
+
+def test_predict_loop_matches_direct_forward_and_writes_reference_format(tmp_path):
+    """infer.py:140-421 / :39-57: checkpoint -> predict() over a folder of PNGs == model forward + format_preds per image."""
+    from torchvision.io import write_png
+    torch.manual_seed(3)
+    H, W, C = 96, 128, 4
+    net = yogo_b200.YOGO((H, W), 0.1, 0.1, C, inference=True)
+    with torch.no_grad():
+        net.model[-1].bias[4] = 1.0   # objectness logits above threshold on part of the grid
+    pth = tmp_path / "m.pth"
+    torch.save({"step": 5, "model_state_dict": net.state_dict(), "model_version": "base_model", "class_names": list("abcd"),
+                "normalize_images": False}, pth)
+    imgs = torch.randint(0, 256, (5, 1, H, W), dtype=torch.uint8)
+    idir = tmp_path / "images"
+    idir.mkdir()
+    for i, im in enumerate(imgs):
+        write_png(im, str(idir / f"img_{i:03d}.png"))
+    odir = tmp_path / "out"
+    res = yogo_b200.predict(str(pth), path_to_images=idir, output_dir=str(odir), save_preds=True, count_predictions=True,
+                            batch_size=2, return_full_predictions=True, class_names=list("abcd"))
+    net = net.to(DEV).eval()
+    net.compute_dtype = torch.float32
+    with torch.no_grad():
+        direct = net(imgs.to(DEV)).cpu()
+    assert res.shape == direct.shape and _rel(res.numpy(), direct.numpy()) < 1e-5
+    # in-memory images give the same tensor
+    res2 = yogo_b200.predict(str(pth), images=imgs, batch_size=3, return_full_predictions=True)
+    assert torch.equal(res2, res)
+    for i in range(5):
+        rows = O.format_preds_np(res[i].numpy())
+        exp = "\n".join(f"{int(np.argmax(r[5:]))} {torch.tensor(r[0])} {torch.tensor(r[1])} {torch.tensor(r[2])} {torch.tensor(r[3])}"
+                        for r in rows)
+        assert (odir / f"img_{i:03d}.txt").read_text() == exp
+    with pytest.raises(ValueError):
+        yogo_b200.predict(str(pth), path_to_images=idir, save_preds=True)
+    with pytest.raises(ValueError):
+        yogo_b200.predict(str(pth), images=imgs, class_names=["a"])
+    # vertical crop: centre rows of the image through a resized model
+    res3 = yogo_b200.predict(str(pth), images=imgs, vertical_crop_height=0.5, return_full_predictions=True)
+    assert res3.shape[0] == 5 and res3.shape[2] < res.shape[2]
+
+
 # ----------------------------------------------------------------------------- conv kernels vs oracle
 def _conv_case(N, H, W, Cin, Cout, k, s, dtype, act, with_stats, seed=0):
     import ctypes as C

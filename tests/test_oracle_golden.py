@@ -43,6 +43,18 @@ def test_format_preds_oracle_bit_exact(golden_dir, case):
     assert np.array_equal(counts, z[f"{case}_counts"])
 
 
+@pytest.mark.parametrize("case", ["m0", "m1", "m2", "m3", "m4"])
+def test_matching_oracle_bit_exact(golden_dir, case):
+    """format_preds_and_labels_v2 of the real reference (prediction_formatting.py:254-330) vs the numpy restatement."""
+    z = np.load(os.path.join(golden_dir, "match.npz"))
+    obj, mincls = z[case + "_cfg"]
+    mp, ml, missed, extra = O.match_preds_and_labels_np(z[case + "_pred"], z[case + "_label"], float(obj), float(mincls))
+    for got, key in ((mp, "_preds"), (ml, "_labels"), (missed, "_missed"), (extra, "_extra")):
+        exp = z[case + key]
+        assert got.shape == exp.shape, key
+        assert np.array_equal(got.view(np.uint32), exp.astype(np.float32).view(np.uint32)), key
+
+
 def test_reference_known_answers_format_preds():
     # /root/reference/tests/test_utils_tensor_formatting.py:9-68
     none = np.zeros((12, 4, 4), np.float32)

@@ -2,10 +2,13 @@
 from .model import YOGO  # noqa: F401
 from .model_defns import MODELS, get_model_func, register_model  # noqa: F401
 from .yogo_loss import YOGOLoss  # noqa: F401
-from .utils import format_preds, format_preds_batch  # noqa: F401
-from .infer import get_prediction_class_counts, count_cells_for_formatted_preds  # noqa: F401
+from .utils import (  # noqa: F401
+    PredictionLabelMatch, box_iou_cost, format_preds, format_preds_and_labels_v2, format_preds_batch, format_to_numpy,
+)
+from .infer import get_prediction_class_counts, count_cells_for_formatted_preds, predict, save_predictions  # noqa: F401
 
 __all__ = [
     "YOGO", "YOGOLoss", "MODELS", "get_model_func", "register_model", "format_preds", "format_preds_batch",
-    "get_prediction_class_counts", "count_cells_for_formatted_preds",
+    "get_prediction_class_counts", "count_cells_for_formatted_preds", "predict", "save_predictions",
+    "PredictionLabelMatch", "box_iou_cost", "format_preds_and_labels_v2", "format_to_numpy",
 ]

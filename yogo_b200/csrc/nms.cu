@@ -294,3 +294,57 @@ extern "C" int yg_format_preds_batch(const float* preds, int B, int num_classes,
   YG_LAUNCH_CHECK("format_preds");
   return YG_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Pairwise matching cost between labels and formatted predictions:
+// cost[i][j] = 1 - box_iou(label_i, pred_j), the matrix format_preds_and_labels_v2 hands to the Hungarian solver
+// (/root/reference/yogo/utils/prediction_formatting.py:296-298; torchvision.ops.box_iou = _box_inter_union, boxes.py).
+// Every operation is a single correctly rounded fp32 operation in torchvision's order (never contracted to FMA), so the
+// matrix is bit-identical to the reference's and the assignment computed from it is the same.
+// ------------------------------------------------------------------------------------------------
+namespace yg {
+__global__ void box_iou_cost_kernel(const float* __restrict__ a, int a_stride, int na, const float* __restrict__ b, int b_stride,
+                                    int nb, float* __restrict__ cost) {
+  __shared__ float sb[256][5];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * 16;
+  // this thread's prediction box
+  float bx1 = 0.f, by1 = 0.f, bx2 = 0.f, by2 = 0.f, barea = 0.f;
+  if (j < nb) {
+    const float* r = b + (long long)j * b_stride;
+    bx1 = r[0]; by1 = r[1]; bx2 = r[2]; by2 = r[3];
+    barea = __fmul_rn(__fsub_rn(bx2, bx1), __fsub_rn(by2, by1));
+  }
+  // 16 label boxes of this block row through shared memory
+  if (threadIdx.x < 16 && i0 + threadIdx.x < na) {
+    const float* r = a + (long long)(i0 + threadIdx.x) * a_stride;
+    sb[threadIdx.x][0] = r[0]; sb[threadIdx.x][1] = r[1]; sb[threadIdx.x][2] = r[2]; sb[threadIdx.x][3] = r[3];
+    sb[threadIdx.x][4] = __fmul_rn(__fsub_rn(r[2], r[0]), __fsub_rn(r[3], r[1]));
+  }
+  __syncthreads();
+  if (j >= nb) return;
+  for (int k = 0; k < 16 && i0 + k < na; ++k) {
+    const float ax1 = sb[k][0], ay1 = sb[k][1], ax2 = sb[k][2], ay2 = sb[k][3], aarea = sb[k][4];
+    const float ltx = ax1 > bx1 ? ax1 : bx1, lty = ay1 > by1 ? ay1 : by1;
+    const float rbx = ax2 < bx2 ? ax2 : bx2, rby = ay2 < by2 ? ay2 : by2;
+    float w = __fsub_rn(rbx, ltx), h = __fsub_rn(rby, lty);
+    w = w < 0.f ? 0.f : w;   // clamp(min=0) keeps NaN
+    h = h < 0.f ? 0.f : h;
+    const float inter = __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    cost[(long long)(i0 + k) * nb + j] = __fsub_rn(1.f, __fdiv_rn(inter, uni));
+  }
+}
+}  // namespace yg
+
+extern "C" int yg_box_iou_cost(const float* labels, int label_stride, int n_labels, const float* preds, int pred_stride,
+                               int n_preds, float* cost, void* stream) {
+  YG_CHECK_ARG(n_labels >= 0 && n_preds >= 0 && label_stride >= 4 && pred_stride >= 4, "box_iou_cost: bad sizes");
+  if (n_labels == 0 || n_preds == 0) return YG_OK;
+  YG_CHECK_ARG(labels && preds && cost, "box_iou_cost: null pointer");
+  dim3 grid(cdiv(n_preds, 256), cdiv(n_labels, 16), 1);
+  yg::box_iou_cost_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, label_stride, n_labels, preds, pred_stride, n_preds, cost);
+  YG_LAUNCH_CHECK("box_iou_cost");
+  return YG_OK;
+}

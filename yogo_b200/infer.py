@@ -1,8 +1,15 @@
-"""Inference post-processing entry points of /root/reference/yogo/infer.py:60-124."""
+"""Inference entry points of /root/reference/yogo/infer.py: the per-class counts (:60-124), the YOGO-format
+prediction writer (:39-57) and the ``predict`` batch loop (:140-421) with the post-processing of a whole batch
+in one launch instead of one Python iteration per image."""
 from __future__ import annotations
 
-from typing import Optional
+import datetime
+import json
+import warnings
+from pathlib import Path
+from typing import List, Literal, Optional, Sequence, Union
 
+import numpy as np
 import torch
 
 from .utils.prediction_formatting import format_preds_batch
@@ -44,3 +51,191 @@ def count_cells_for_formatted_preds(
     values, indices = formatted_class_predictions.max(dim=1)
     mask = values > min_confidence_threshold
     return torch.nn.functional.one_hot(indices[mask], num_classes=n_classes).sum(dim=0)
+
+
+def save_predictions(fnames: Sequence, batch_preds: torch.Tensor, obj_thresh: float = 0.5, iou_thresh: float = 0.5) -> None:
+    """infer.py:39-57: one text file per image, a line ``<argmax class> <xc> <yc> <w> <h>`` per kept prediction in
+    ``format_preds`` order.  Threshold + NMS of the whole batch is one launch and one device->host copy."""
+    rows, keep_count, _, _ = format_preds_batch(batch_preds, obj_thresh=obj_thresh, iou_thresh=iou_thresh)
+    counts = keep_count.tolist()
+    nmax = max(counts) if counts else 0
+    host = rows[:, :nmax].cpu()
+    for fname, n, r in zip(fnames, counts, host):
+        lines = []
+        for pred in r[:n]:
+            cls = int(torch.argmax(pred[5:]))   # first maximum, like the reference's max(range(n), key=...)
+            lines.append(f"{cls} {pred[0]} {pred[1]} {pred[2]} {pred[3]}")
+        with open(fname, "w") as f:
+            f.write("\n".join(lines))
+
+
+def _list_images(path_to_images: Path) -> List[Path]:
+    p = Path(path_to_images)
+    if p.is_file():
+        return [p]
+    if not p.is_dir():
+        raise FileNotFoundError(f"{p} is neither an image nor a directory of images")
+    return sorted(q for q in p.iterdir() if q.suffix.lower() in (".png", ".npy"))
+
+
+def _read_image(path: Path) -> torch.Tensor:
+    """(1, H, W) uint8 - grayscale PNG (torchvision.io) or a .npy array; decoding is I/O around the path."""
+    if path.suffix.lower() == ".npy":
+        a = torch.from_numpy(np.load(path))
+        return a.reshape(1, *a.shape[-2:]).to(torch.uint8)
+    from torchvision.io import ImageReadMode, read_image
+
+    return read_image(str(path), ImageReadMode.GRAY)
+
+
+@torch.no_grad()
+def predict(
+    path_to_pth: str,
+    *,
+    path_to_images: Optional[Path] = None,
+    path_to_zarr: Optional[Path] = None,
+    output_dir: Optional[str] = None,
+    draw_boxes: bool = False,
+    save_preds: bool = False,
+    save_npy: bool = False,
+    class_names: Optional[List[str]] = None,
+    count_predictions: bool = False,
+    batch_size: int = 64,
+    obj_thresh: float = 0.5,
+    iou_thresh: float = 0.5,
+    vertical_crop_height: Optional[float] = None,
+    use_tqdm: bool = False,
+    device: Optional[Union[str, torch.device]] = None,
+    output_img_ftype: Literal[".png", ".tif", ".tiff"] = ".png",
+    requested_num_workers: Optional[int] = None,
+    min_class_confidence_threshold: float = 0.0,
+    half: bool = False,
+    return_full_predictions: bool = False,
+    images: Optional[torch.Tensor] = None,
+) -> Optional[torch.Tensor]:
+    """The ``yogo infer`` batch loop (infer.py:140-421) on the B200 path: checkpoint -> eval model, batches of uint8
+    images -> forward -> batched threshold / NMS / counts, optional YOGO-format text files, ``.npy`` export and the full
+    prediction tensor.  ``half`` selects bf16 compute (the reference's autocast), otherwise fp32.  ``images`` (N,1,H,W)
+    uint8 is an in-memory alternative to ``path_to_images``.  Box drawing and zarr input are outside the path and raise."""
+    from .model import YOGO
+    from .utils.prediction_formatting import split_formatted
+
+    if save_preds and draw_boxes:
+        raise ValueError("cannot save predictions in YOGO format and draw_boxes at the same time")
+    elif output_dir is not None and not (save_preds or draw_boxes or save_npy):
+        warnings.warn(
+            f"output dir is not None (is {output_dir}), but it will not be used "
+            "since save_preds and draw_boxes are both false"
+        )
+    elif output_dir is not None:
+        Path(output_dir).mkdir(exist_ok=True, parents=False)
+    elif save_preds:
+        raise ValueError("output_dir must not be None if save_preds is True")
+    elif output_img_ftype not in [".png", ".tif", ".tiff"]:
+        raise ValueError(
+            "only .png, .tif, and .tiff are supported for output img " f"filetype; got {output_img_ftype}"
+        )
+    if draw_boxes:
+        raise NotImplementedError("draw_boxes (matplotlib/PIL rendering) is outside the B200 hot path")
+    if path_to_zarr is not None:
+        raise NotImplementedError("zarr input is outside the B200 hot path; use path_to_images or images=")
+    if (path_to_images is None) == (images is None):
+        raise ValueError("exactly one of path_to_images and images must be given")
+
+    dev = torch.device(device or "cuda")
+    model, cfg = YOGO.from_pth(Path(path_to_pth), inference=True)
+    model.eval()
+    model.to(dev)
+    model.compute_dtype = torch.bfloat16 if half else torch.float32
+
+    img_h, img_w = model.get_img_size()
+    crop_h = None
+    if vertical_crop_height:
+        crop_h = int((vertical_crop_height * img_h).round().item())
+        model.resize_model(crop_h)
+        img_h = torch.tensor(crop_h)
+    in_h, in_w = int(model.img_size[0].item()), int(model.img_size[1].item())
+    num_classes = int(model.num_classes.item())
+    if class_names is not None and len(class_names) != num_classes:
+        raise ValueError(f"expected {num_classes} class names, got {len(class_names)}")
+
+    if images is not None:
+        n_images = images.shape[0]
+        fnames_all = [f"image_{i:06d}.png" for i in range(n_images)]
+    else:
+        paths = _list_images(Path(path_to_images))
+        n_images = len(paths)
+        fnames_all = [str(q) for q in paths]
+
+    def load_batch(lo: int, hi: int) -> torch.Tensor:
+        b = images[lo:hi] if images is not None else torch.stack([_read_image(q) for q in paths[lo:hi]])
+        if crop_h is not None:   # CenterCrop((crop_h, img_w))
+            top = int(round((b.shape[-2] - crop_h) / 2.0))
+            b = b[..., top:top + crop_h, :]
+        if b.shape[-2:] != (in_h, in_w):
+            raise RuntimeError(f"image size {tuple(b.shape[-2:])} does not match the model's {(in_h, in_w)}")
+        return b
+
+    results = None
+    np_results = []
+    tot_counts = torch.zeros(num_classes, dtype=torch.int64, device=dev) if count_predictions else None
+    pbar = None
+    if use_tqdm:
+        from tqdm import tqdm
+
+        pbar = tqdm(unit="images", total=n_images)
+    normalize = bool(model.normalize_images)
+    for i, lo in enumerate(range(0, n_images, batch_size)):
+        hi = min(lo + batch_size, n_images)
+        try:
+            img_batch = load_batch(lo, hi)
+        except RuntimeError as e:   # malformed images: warn and continue, like the reference
+            warnings.warn(f"got error {e}; continuing")
+            continue
+        x = img_batch.to(dev, non_blocking=True)
+        if normalize:
+            x = x.float() / 255.0
+        res = model(x)
+        if results is None and return_full_predictions:
+            results = torch.zeros((n_images, res.shape[1], res.shape[2], res.shape[3]))
+        if save_preds:
+            out_fnames = [Path(output_dir) / Path(f).with_suffix(".txt").name for f in fnames_all[lo:hi]]
+            save_predictions(out_fnames, res, obj_thresh=obj_thresh, iou_thresh=iou_thresh)
+        if save_npy:
+            rows, keep_count, _, _ = format_preds_batch(res, box_format="xyxy")
+            for j, r in enumerate(split_formatted(rows, keep_count)):
+                fp = r.cpu().numpy().T
+                n = fp.shape[1]
+                labels = np.argmax(fp[5:, :], axis=0).astype(np.uint8)
+                np_results.append(np.vstack((
+                    np.ones(n).astype(np.float32) * (lo + j), fp[0, :] * in_w, fp[1, :] * int(img_h.item()),
+                    fp[2, :] * in_w, fp[3, :] * int(img_h.item()), fp[4, :], labels.astype(np.float32),
+                    fp[5:, ][labels, np.arange(n)], fp[5:, :])))
+        if count_predictions:
+            _, _, _, counts = format_preds_batch(
+                res, obj_thresh=obj_thresh, iou_thresh=iou_thresh,
+                min_class_confidence_threshold=min_class_confidence_threshold)
+            tot_counts += counts
+        if return_full_predictions:
+            results[lo:hi, ...] = res.cpu()
+        if pbar is not None:
+            pbar.update(hi - lo)
+    if pbar is not None:
+        pbar.close()
+
+    if count_predictions:
+        print(list(zip(class_names or range(num_classes), map(int, tot_counts.cpu()))))
+
+    if save_npy:
+        pred_tensors = np.hstack(np_results) if np_results else np.zeros((8 + num_classes, 0), dtype=np.float32)
+        filename = Path(path_to_images).resolve().parent.stem if path_to_images else "predictions"
+        base = Path(output_dir).resolve() if output_dir is not None else Path.cwd().resolve()
+        fp_out = base / Path(filename).with_suffix(".npy")
+        np.save(fp_out, pred_tensors)
+        with open(fp_out.with_suffix(".json"), "w") as f:
+            json.dump(dict(run_name=fp_out.with_suffix("").name,
+                           model_name=torch.load(Path(path_to_pth), map_location="cpu").get("model_name", None),
+                           obj_thresh=obj_thresh, iou_thresh=iou_thresh, vertical_crop_height_px=int(img_h.item()),
+                           write_date=datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S")), f, indent=4)
+
+    return results if return_full_predictions else None
