@@ -169,7 +169,7 @@ def run_ours(args):
     import yogo_b200
     from yogo_b200 import _lib as L
     from yogo_b200.train import DataParallelTrainer
-    from oracle import yogo_oracle as O  # synthetic input generators only (shared with the tests)
+    from tools import synth as O  # seeded synthetic inputs (shared with the tests); the oracle is not imported on this arm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -277,7 +277,10 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic",
             "config": {
                 "workload": f"{args.model} training step: fwd + YOGOLoss + bwd + grad all-reduce + fused AdamW, "
-                            f"772x1032x1 uint8 images, 7 classes, batch {B}/GPU (BASELINE configs[1])",
+                            f"772x1032x1 uint8 images, 7 classes, batch {B}/GPU "
+                            + ("(BASELINE configs[1])" if args.model == "base_model" and B == 64 else
+                               "(BASELINE configs[3])" if args.model in ("double_filters", "silu_model") and B == 128 else
+                               "(parity / sweep configuration)"),
                 "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                 "l2_policy": "inputs+activations per step (>3 GB) far exceed the 126 MB L2; batches alternate",
                 "conv_impl": L.get_conv_impl(), "cuda_graph": bool(use_graph),

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import yogo_b200  # noqa: E402
 from yogo_b200.train import DataParallelTrainer  # noqa: E402
-from oracle import yogo_oracle as O  # noqa: E402
+from tools import synth as O  # noqa: E402  (seeded synthetic inputs)
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
