@@ -217,6 +217,19 @@ int yg_format_preds_batch(const float* preds, int B, int num_classes, int Sy, in
 int yg_box_iou_cost(const float* labels, int label_stride, int n_labels, const float* preds, int pred_stride,
                     int n_preds, float* cost, void* stream);
 
+/* ---- input side --------------------------------------------------------
+ * RandomHorizontal/VerticalFlipWithBBs (data/data_transforms.py:51-98) of a whole batch, out of place:
+ * images (N,C,H,W) uint8 (YG_U8) or fp32, labels (N,6,Sy,Sx) = [mask,x1,y1,x2,y2,class] with x1' = 1 - x2, x2' = 1 - x1
+ * (hflip) / y1' = 1 - y2, y2' = 1 - y1 (vflip) on every cell and the cells mirrored; both flips may be combined. */
+int yg_flip_images(const void* in, void* out, int dtype, int N, int C, int H, int W, int hflip, int vflip, void* stream);
+int yg_flip_labels(const float* in, float* out, int N, int Sy, int Sx, int hflip, int vflip, void* stream);
+/* format_labels_tensor (data/yogo_dataset.py:24-46) for a batch of ragged label lists: labels (total,5) =
+ * [class,x1,y1,x2,y2] rows of all images back to back, offsets[B+1] (int32) the row range of each image, max_labels the
+ * largest per-image count; out (B,6,Sy,Sx) fp32 overwritten; owner (B*Sy*Sx int32) is scratch; *err (device int) is set
+ * to 1 when a label centre falls outside the grid (the reference raises IndexError). */
+int yg_format_labels_batch(const float* labels, const int* offsets, int B, int max_labels, int Sy, int Sx,
+                           int* owner, float* out, int* err, void* stream);
+
 /* ---- optimizer: fused AdamW over one flat fp32 buffer ---------------
  * replaces torch.optim.AdamW.step (train.py:213-217, 324). grads are pre-scaled by
  * grad_scale (1/world_size after an all-reduce SUM). */

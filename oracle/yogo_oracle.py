@@ -562,6 +562,40 @@ def synth_labels_for_preds(pred: torch.Tensor, drop: float = 0.2, extra: int = 5
 
 
 # ----------------------------------------------------------------------------------------
+# Input side: bounding-box aware flips and label rasterisation
+# (/root/reference/yogo/data/data_transforms.py:51-98, /root/reference/yogo/data/yogo_dataset.py:24-46)
+# ----------------------------------------------------------------------------------------
+def flip_batch_np(img: np.ndarray, lab: np.ndarray, hflip: bool, vflip: bool):
+    img = np.asarray(img)
+    lab = np.asarray(lab, dtype=np.float32).copy()
+    one = np.float32(1)
+    if hflip:
+        x1, x2 = one - lab[:, 3], one - lab[:, 1]
+        lab[:, 1], lab[:, 3] = x1, x2
+        img, lab = img[..., ::-1], lab[..., ::-1]
+    if vflip:
+        y1, y2 = one - lab[:, 4], one - lab[:, 2]
+        lab[:, 2], lab[:, 4] = y1, y2
+        img, lab = img[..., ::-1, :], lab[..., ::-1, :]
+    return np.ascontiguousarray(img), np.ascontiguousarray(lab)
+
+
+def format_labels_tensor_np(labels: np.ndarray, Sx: int, Sy: int) -> np.ndarray:
+    """(n, 5) [class, x1, y1, x2, y2] -> (6, Sy, Sx) [mask, x1, y1, x2, y2, class]; later labels overwrite earlier ones."""
+    labels = np.asarray(labels, dtype=np.float32).reshape(-1, 5)
+    out = np.zeros((6, Sy, Sx), dtype=np.float32)
+    for lab in labels:
+        i = int(np.floor(((lab[1] + lab[3]) * np.float32(Sx)) / np.float32(2)))
+        j = int(np.floor(((lab[2] + lab[4]) * np.float32(Sy)) / np.float32(2)))
+        if not (-Sx <= i < Sx and -Sy <= j < Sy):
+            raise IndexError("label centre outside the grid")
+        out[0, j, i] = 1
+        out[1:5, j, i] = lab[1:]
+        out[5, j, i] = lab[0]
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY.md 8d) live in tools/synth.py (shared with bench.py); re-exported for the tests
 # ----------------------------------------------------------------------------------------
 from tools.synth import ANCHOR_H, ANCHOR_W, synth_images, synth_labels, synth_sparse_preds  # noqa: E402,F401

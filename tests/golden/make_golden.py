@@ -205,6 +205,54 @@ def golden_match(ref, out):
     np.savez_compressed(os.path.join(out, "match.npz"), **cases)
 
 
+def synth_label_lists(B, Sx, Sy, C, K, seed):
+    """ragged [class, x1, y1, x2, y2] lists; image 0 repeats a cell (last label wins) and has a box touching the border."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for b in range(B):
+        n = int(torch.randint(K // 2, K + 1, (), generator=g)) if K else 0
+        cx, cy = torch.rand(n, generator=g), torch.rand(n, generator=g)
+        w, h = 0.04 * (0.75 + 0.5 * torch.rand(n, generator=g)), 0.05 * (0.75 + 0.5 * torch.rand(n, generator=g))
+        cls = torch.randint(0, C, (n,), generator=g).float()
+        t = torch.stack([cls, cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+        if b == 0 and n >= 4:
+            t[3, 1:] = t[1, 1:] + 1e-4
+            t[2, 1:] = torch.tensor([0.0, 0.0, 0.03, 0.04])
+        out.append(t)
+    return out
+
+
+def golden_input(ref, out):
+    """RandomHorizontal/VerticalFlipWithBBs (p = 1) and format_labels_tensor of the real reference."""
+    from yogo.data.data_transforms import RandomHorizontalFlipWithBBs, RandomVerticalFlipWithBBs
+    from yogo.data.yogo_dataset import format_labels_tensor
+    from tools.synth import synth_images, synth_labels
+
+    cases = {}
+    hf, vf = RandomHorizontalFlipWithBBs(1.0), RandomVerticalFlipWithBBs(1.0)
+    for ci, (N, H, W, Sy, Sx, K, seed, as_float) in enumerate(
+        [(2, 16, 24, 6, 8, 10, 51, False), (3, 772 // 8, 1032 // 8, 13, 17, 40, 52, False), (2, 15, 21, 5, 7, 8, 53, True)]
+    ):
+        img = synth_images(N, H, W, seed=seed)
+        if as_float:
+            img = img.float() / 255.0
+        lab = synth_labels(N, Sy, Sx, 7, K, seed=seed)
+        cases[f"f{ci}_img"], cases[f"f{ci}_lab"] = img.numpy(), lab.numpy()
+        a, b = hf(img.clone(), lab.clone())
+        cases[f"f{ci}_h_img"], cases[f"f{ci}_h_lab"] = a.numpy(), b.numpy()
+        a, b = vf(img.clone(), lab.clone())
+        cases[f"f{ci}_v_img"], cases[f"f{ci}_v_lab"] = a.numpy(), b.numpy()
+        a, b = vf(*hf(img.clone(), lab.clone()))
+        cases[f"f{ci}_hv_img"], cases[f"f{ci}_hv_lab"] = a.numpy(), b.numpy()
+    for ci, (B, Sx, Sy, C, K, seed) in enumerate([(3, 8, 6, 7, 10, 61), (2, 129, 97, 7, 300, 62), (2, 5, 4, 3, 0, 63)]):
+        lists = synth_label_lists(B, Sx, Sy, C, K, seed)
+        cases[f"l{ci}_cfg"] = np.array([B, Sx, Sy], dtype=np.int64)
+        cases[f"l{ci}_counts"] = np.array([t.shape[0] for t in lists], dtype=np.int64)
+        cases[f"l{ci}_labels"] = torch.cat(lists).numpy() if sum(t.shape[0] for t in lists) else np.zeros((0, 5), np.float32)
+        cases[f"l{ci}_out"] = torch.stack([format_labels_tensor(t, Sx, Sy) for t in lists]).numpy()
+    np.savez_compressed(os.path.join(out, "input.npz"), **cases)
+
+
 GRAD_STRIDE = 5
 
 
@@ -342,9 +390,13 @@ if __name__ == "__main__":
     if "--only-match" in sys.argv:   # regenerate match.npz alone
         golden_match(ref, HERE)
         sys.exit(0)
+    if "--only-input" in sys.argv:   # regenerate input.npz alone
+        golden_input(ref, HERE)
+        sys.exit(0)
     golden_loss(ref, HERE)
     golden_nms(ref, HERE)
     golden_match(ref, HERE)
+    golden_input(ref, HERE)
     golden_model(ref, HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

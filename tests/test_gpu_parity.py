@@ -245,6 +245,48 @@ def test_predict_loop_matches_direct_forward_and_writes_reference_format(tmp_pat
     assert res3.shape[0] == 5 and res3.shape[2] < res.shape[2]
 
 
+# ----------------------------------------------------------------------------- input side
+def test_flips_and_label_rasterisation_bit_exact_vs_reference_golden(golden_dir):
+    """RandomHorizontal/VerticalFlipWithBBs (data_transforms.py:51-98) and format_labels_tensor (yogo_dataset.py:24-46)
+    of the real reference vs csrc/input.cu."""
+    from yogo_b200.data import flip_batch, format_labels_batch, format_labels_tensor
+    z = _load(golden_dir, "input.npz")
+    for ci in range(3):
+        img, lab = torch.from_numpy(z[f"f{ci}_img"]).to(DEV), torch.from_numpy(z[f"f{ci}_lab"]).to(DEV)
+        for tag, h, v in (("h", True, False), ("v", False, True), ("hv", True, True)):
+            a, b = flip_batch(img, lab, h, v)
+            assert np.array_equal(a.cpu().numpy(), z[f"f{ci}_{tag}_img"]), (ci, tag)
+            assert np.array_equal(b.cpu().numpy().view(np.uint32), z[f"f{ci}_{tag}_lab"].view(np.uint32)), (ci, tag)
+        # the inputs are untouched (out of place) and two flips are the identity on the image
+        assert np.array_equal(img.cpu().numpy(), z[f"f{ci}_img"])
+        a2, _ = flip_batch(*flip_batch(img, lab, True, True), True, True)
+        assert torch.equal(a2, img)
+    for ci in range(3):
+        B, Sx, Sy = (int(v) for v in z[f"l{ci}_cfg"])
+        offs = np.concatenate([[0], np.cumsum(z[f"l{ci}_counts"])])
+        lists = [torch.from_numpy(z[f"l{ci}_labels"][offs[b]:offs[b + 1]]) for b in range(B)]
+        out = format_labels_batch(lists, Sx, Sy)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), z[f"l{ci}_out"].view(np.uint32)), ci
+        assert torch.equal(format_labels_tensor(lists[0].to(DEV), Sx, Sy), out[0])
+    with pytest.raises(IndexError):
+        format_labels_tensor(torch.tensor([[0, 0.9, 0.9, 1.2, 1.2]]), 8, 6)
+
+
+def test_flip_modules_follow_the_host_rng_like_the_reference():
+    from yogo_b200.data import MultiArgSequential, RandomHorizontalFlipWithBBs, RandomVerticalFlipWithBBs, DualInputId
+    img = O.synth_images(4, 772, 1032).to(DEV)
+    lab = O.synth_labels(4).to(DEV)
+    tf = MultiArgSequential(RandomHorizontalFlipWithBBs(0.5), DualInputId(), RandomVerticalFlipWithBBs(0.5))
+    assert len(tf) == 2
+    for seed in range(4):
+        torch.manual_seed(seed)
+        h, v = bool(torch.rand(1) < 0.5), bool(torch.rand(1) < 0.5)
+        torch.manual_seed(seed)
+        a, b = tf(img, lab)
+        ea, eb = O.flip_batch_np(img.cpu().numpy(), lab.cpu().numpy(), h, v)
+        assert np.array_equal(a.cpu().numpy(), ea) and np.array_equal(b.cpu().numpy().view(np.uint32), eb.view(np.uint32))
+
+
 # ----------------------------------------------------------------------------- conv kernels vs oracle
 def _conv_case(N, H, W, Cin, Cout, k, s, dtype, act, with_stats, seed=0):
     import ctypes as C

@@ -55,6 +55,25 @@ def test_matching_oracle_bit_exact(golden_dir, case):
         assert np.array_equal(got.view(np.uint32), exp.astype(np.float32).view(np.uint32)), key
 
 
+def test_input_side_oracle_bit_exact(golden_dir):
+    """data_transforms.py:51-98 and yogo_dataset.py:24-46 of the real reference vs the numpy restatement."""
+    z = np.load(os.path.join(golden_dir, "input.npz"))
+    for ci in range(3):
+        img, lab = z[f"f{ci}_img"], z[f"f{ci}_lab"]
+        for tag, h, v in (("h", True, False), ("v", False, True), ("hv", True, True)):
+            a, b = O.flip_batch_np(img, lab, h, v)
+            assert np.array_equal(a, z[f"f{ci}_{tag}_img"]), (ci, tag)
+            assert np.array_equal(b.view(np.uint32), z[f"f{ci}_{tag}_lab"].view(np.uint32)), (ci, tag)
+    for ci in range(3):
+        B, Sx, Sy = (int(v) for v in z[f"l{ci}_cfg"])
+        offs = np.concatenate([[0], np.cumsum(z[f"l{ci}_counts"])])
+        for b in range(B):
+            got = O.format_labels_tensor_np(z[f"l{ci}_labels"][offs[b]:offs[b + 1]], Sx, Sy)
+            assert np.array_equal(got.view(np.uint32), z[f"l{ci}_out"][b].view(np.uint32)), (ci, b)
+    with pytest.raises(IndexError):
+        O.format_labels_tensor_np(np.array([[0, 0.9, 0.9, 1.2, 1.2]], np.float32), 8, 6)
+
+
 def test_reference_known_answers_format_preds():
     # /root/reference/tests/test_utils_tensor_formatting.py:9-68
     none = np.zeros((12, 4, 4), np.float32)

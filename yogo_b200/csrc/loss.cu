@@ -14,6 +14,9 @@ constexpr int LS_MAXC = 27;  // 5 + C <= 32
 __device__ __forceinline__ float sel_gt(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
 __device__ __forceinline__ float sel_lt(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
 
+// MAXC = compile-time bound of the class loops (4, 8, 16 or 27): the loops are fully unrolled and predicated on c < C, so a
+// bound of 27 for the usual 7 classes would spend most of the issue slots on predicated-off iterations
+template <int MAXC>
 __global__ void __launch_bounds__(LS_THREADS) yogo_loss_kernel(
     const float* __restrict__ pred, const float* __restrict__ label, float* __restrict__ dpred,
     double* __restrict__ partial, int N, int C, int SS, float no_obj_w, float iou_w, float cls_w,
@@ -38,21 +41,23 @@ __global__ void __launch_bounds__(LS_THREADS) yogo_loss_kernel(
     }
     // ---- classification: label-smoothed CE on raw logits, masked (yogo_loss.py:107-114)
     {
-      float lg[LS_MAXC];
+      float lg[MAXC];
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < LS_MAXC; ++c)
+      for (int c = 0; c < MAXC; ++c)
         if (c < C) { lg[c] = p[(long long)(5 + c) * SS]; mx = fmaxf(mx, lg[c]); }
       float se = 0.f, sl = 0.f;
+      float ex[MAXC];   // exp(logit - max), reused for the softmax of the gradient
 #pragma unroll
-      for (int c = 0; c < LS_MAXC; ++c)
-        if (c < C) { se += expf(lg[c] - mx); sl += lg[c]; }
+      for (int c = 0; c < MAXC; ++c)
+        if (c < C) { ex[c] = expf(lg[c] - mx); se += ex[c]; sl += lg[c]; }
       const float lse = mx + logf(se);
+      const float inv_se = 1.f / se;
       int tgt = (int)l[5LL * SS];  // .long() truncation
       tgt = tgt < 0 ? 0 : (tgt >= C ? C - 1 : tgt);
       float lt = 0.f;
 #pragma unroll
-      for (int c = 0; c < LS_MAXC; ++c)
+      for (int c = 0; c < MAXC; ++c)
         if (c == tgt) lt = lg[c];
       const float nll = lse - lt;
       const float smooth = lse - sl / (float)C;
@@ -60,9 +65,9 @@ __global__ void __launch_bounds__(LS_THREADS) yogo_loss_kernel(
       if (g) {
         const float f = m * cls_w * invN;
 #pragma unroll
-        for (int c = 0; c < LS_MAXC; ++c)
+        for (int c = 0; c < MAXC; ++c)
           if (c < C) {
-            const float sm = expf(lg[c] - lse);
+            const float sm = ex[c] * inv_se;
             const float td = (c == tgt ? (1.f - smoothing) : 0.f) + smoothing / (float)C;
             g[(long long)(5 + c) * SS] = f * (sm - td);
           }
@@ -191,8 +196,12 @@ extern "C" int yg_yogo_loss_fwd_bwd(const float* pred, const float* label, float
   const int SS = Sy * Sx;
   const int blocks = cdiv((long long)N * SS, LS_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
-  yogo_loss_kernel<<<blocks, LS_THREADS, 0, st>>>(pred, label, dpred, (double*)workspace, N, num_classes, SS,
-                                                  no_obj_weight, iou_weight, classify_weight, label_smoothing);
+#define YG_LOSS_LAUNCH(MC) yogo_loss_kernel<MC><<<blocks, LS_THREADS, 0, st>>>(pred, label, dpred, (double*)workspace, N, num_classes, SS, no_obj_weight, iou_weight, classify_weight, label_smoothing)
+  if (num_classes <= 4) YG_LOSS_LAUNCH(4);
+  else if (num_classes <= 8) YG_LOSS_LAUNCH(8);
+  else if (num_classes <= 16) YG_LOSS_LAUNCH(16);
+  else YG_LOSS_LAUNCH(LS_MAXC);
+#undef YG_LOSS_LAUNCH
   YG_LAUNCH_CHECK("yogo_loss");
   yogo_loss_finalize_kernel<<<1, 256, 0, st>>>((const double*)workspace, blocks, out4, N, iou_weight, classify_weight);
   YG_LAUNCH_CHECK("yogo_loss_finalize");
