@@ -2447,7 +2447,11 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   bool two_d = two_d1, cta2 = false;
   // (stride-2 dgrad as pairs - four parity classes in class-per-round order, option bit 15 - is implemented and correct but
   //  slower: 0.64 vs 0.47 ms on base L5; its tiles carry 8-32 MMAs each and the pair's barrier round trips dominate)
-  if (!two_d && (g_tc_options & 16384) && !s2f && (stride == 1 || (g_tc_options & 32768)) && Cin == BN && BN % 32 == 0 &&
+  // pairs also where the weights WOULD fit one CTA when N = 64 (unfolded): an M = 128, N = 64 MMA is bound by its
+  // shared-memory operand fetch (4 KB of A + 2 KB of B for 32 cycles of math); in a pair each CTA fetches half of B.
+  // base L4 dgrad 0.49 -> 0.44 ms; the W-folded 16-channel layer does not gain (0.42 -> 0.43).  Option bit 18 turns it off.
+  const bool force_pair = !(g_tc_options & (1 << 18)) && two_d && stride == 1 && BN == 64 && fg == 1;
+  if ((!two_d || force_pair) && (g_tc_options & 16384) && !s2f && (stride == 1 || (g_tc_options & 32768)) && Cin == BN && BN % 32 == 0 &&
       pick_kc(Cout) == 64 &&
       two_d_fits(Cout, BN / 2, 1, 9, stride == 1 ? (T2_TH + 2) * (T2_TW + 2) : (T2_TH + 1) * (T2_TW + 1), 1, &kc2))
     two_d = cta2 = true;   // CTA pair, see conv_fwd_tc
