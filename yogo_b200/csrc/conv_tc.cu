@@ -305,6 +305,16 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
+// 32-byte global store (sm_100: STG.256): a pixel row's 64 bytes of an epilogue iteration leave as two full sectors
+// instead of four 16-byte pieces of them
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
 // 1 / (1 + 2^(-x log2 e)) on the SFU: one ex2.approx and one rcp.approx (x -> -inf gives 1 / inf = 0, x -> +inf gives 1)
 __device__ __forceinline__ float fast_sigmoid(float x) {
   float e, r;
@@ -897,9 +907,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             else mbits3 |= bits << sh;
           }
           if (valid && !(e_dbg & 1)) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+            st_global_256(orow + j * 16, ob32);
+            st_global_256(orow + j * 16 + 16, ob32 + 8);
           }
         }
       } else if (MODE == 1 && fast_bwd) {
@@ -932,9 +941,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
           }
           if (valid && !(e_dbg & 1)) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+            st_global_256(orow + j * 16, ob32);
+            st_global_256(orow + j * 16 + 16, ob32 + 8);
           }
         }
       } else if (MODE == 0 && fast_fwd_silu) {
@@ -964,9 +972,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             v[2 * i] = f2.x; v[2 * i + 1] = f2.y;
           }
           if (valid && !(e_dbg & 1)) {
-            uint4* dst = reinterpret_cast<uint4*>(prow + j * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(pb32)[i];
+            st_global_256(prow + j * 16, pb32);
+            st_global_256(prow + j * 16 + 16, pb32 + 8);
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= fast_sigmoid(v[i]);
@@ -982,9 +989,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
           }
           if (valid && !(e_dbg & 1)) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+            st_global_256(orow + j * 16, ob32);
+            st_global_256(orow + j * 16 + 16, ob32 + 8);
           }
         }
       } else if (MODE == 1 && fast_bwd_silu) {
@@ -993,7 +999,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // the saved row of the next chunk pair is requested one iteration ahead (it sits in L2: prefetched two tiles ago)
         uint4 nx[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) nx[i] = (valid && jb < j_end) ? __ldg(reinterpret_cast<const uint4*>(srow + jb * 16) + i) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 4; ++i) nx[i] = make_uint4(0, 0, 0, 0);
+        if (valid && jb < j_end) { ld_global_nc_256(srow + jb * 16, nx[0], nx[1]); ld_global_nc_256(srow + jb * 16 + 16, nx[2], nx[3]); }
         for (int j = jb; j < j_end; j += 2) {
           uint32_t ra[16], rb[16];
           tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
@@ -1002,10 +1009,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           uint4 cu[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) cu[i] = nx[i];
-          if (j + 2 < j_end && valid) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) nx[i] = __ldg(reinterpret_cast<const uint4*>(srow + (j + 2) * 16) + i);
-          }
+          if (j + 2 < j_end && valid) { ld_global_nc_256(srow + (j + 2) * 16, nx[0], nx[1]); ld_global_nc_256(srow + (j + 2) * 16 + 16, nx[2], nx[3]); }
           float pre[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -1043,9 +1047,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             ob32[8 + i] = *reinterpret_cast<const uint32_t*>(&pb);
           }
           if (valid && !(e_dbg & 1)) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + j * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(ob32)[i];
+            st_global_256(orow + j * 16, ob32);
+            st_global_256(orow + j * 16 + 16, ob32 + 8);
           }
         }
       } else {
@@ -1072,9 +1075,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         __align__(16) bf16 sv[16];
         if (MODE == 1) {
           if (e_saved && valid && !use_mask) {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e_saved) + pix * e_OC + c0);
-            reinterpret_cast<uint4*>(sv)[0] = __ldg(src);
-            reinterpret_cast<uint4*>(sv)[1] = __ldg(src + 1);
+            ld_global_nc_256(reinterpret_cast<const bf16*>(e_saved) + pix * e_OC + c0, reinterpret_cast<uint4*>(sv)[0],
+                             reinterpret_cast<uint4*>(sv)[1]);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
@@ -1205,14 +1207,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           if (eprof) { const long long t = clock64(); ec_math += t - eprev; eprev = t; }
           if (valid && !(e_dbg & 1)) {
             if (out) {
-              uint4* dst = reinterpret_cast<uint4*>(out + pix * e_OC + c0);
-              dst[0] = reinterpret_cast<uint4*>(ob)[0];
-              dst[1] = reinterpret_cast<uint4*>(ob)[1];
+              st_global_256(out + pix * e_OC + c0, reinterpret_cast<const uint32_t*>(ob));
             }
             if (e_preact) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e_preact) + pix * e_OC + c0);
-              dst[0] = reinterpret_cast<uint4*>(pb)[0];
-              dst[1] = reinterpret_cast<uint4*>(pb)[1];
+              st_global_256(reinterpret_cast<bf16*>(e_preact) + pix * e_OC + c0, reinterpret_cast<const uint32_t*>(pb));
             }
           }
           if (eprof) { const long long t = clock64(); ec_store += t - eprev; eprev = t; }
@@ -1299,9 +1297,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
           const bool second_sum = has_bn;   // sum(g * xhat) only exists for BatchNorm layers; sum(g) alone = d(bias)
           if (valid && !(e_dbg & 1)) {
-            uint4* dst = reinterpret_cast<uint4*>(out + pix * e_OC + c0);
-            dst[0] = reinterpret_cast<uint4*>(ob)[0];
-            dst[1] = reinterpret_cast<uint4*>(ob)[1];
+            st_global_256(out + pix * e_OC + c0, reinterpret_cast<const uint32_t*>(ob));
           }
           if (e_bn_sums) {
             const float t1 = lane_transpose_reduce16(s1, lane);

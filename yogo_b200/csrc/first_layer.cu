@@ -641,7 +641,10 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : (NM == 2 ? 5 : 4)
           load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
           const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)cur.p * CO);
 #pragma unroll
-          for (int i = 0; i < 2 * NM; ++i) d[i] = __ldg(gp + i);
+          for (int m = 0; m < NM; ++m)
+            asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(d[2 * m].x), "=r"(d[2 * m].y), "=r"(d[2 * m].z), "=r"(d[2 * m].w), "=r"(d[2 * m + 1].x),
+                           "=r"(d[2 * m + 1].y), "=r"(d[2 * m + 1].z), "=r"(d[2 * m + 1].w) : "l"(gp + 2 * m));
         } else {
 #pragma unroll
           for (int t = 0; t < 9; ++t) v[t] = 0.f;
@@ -829,8 +832,11 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 6) first_fwd_mma_
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
           const unsigned char* yt = tiles[warp][1 + m];
-          dst[2 * m] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((0 ^ sw) << 4));
-          dst[2 * m + 1] = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((1 ^ sw) << 4));
+          const uint4 lo = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((0 ^ sw) << 4));
+          const uint4 hi = *reinterpret_cast<const uint4*>(yt + lane * 32 + ((1 ^ sw) << 4));
+          // the 16 channels of this M tile leave as one 32-byte store (a full sector) instead of two halves
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 2 * m), "r"(lo.x), "r"(lo.y),
+                       "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
         }
       }
     }
