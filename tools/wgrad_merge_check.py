@@ -1,16 +1,18 @@
-"""wgrad with the three filter rows merged into one N = 192 MMA (default; option bit 19 disables it) against the per-row path."""
+"""tcgen05 wgrad variants against the plain path: merged row taps (one N = 192 MMA; option bit 19 disables) and the dz tile
+shared by both parity groups of a stride-2 tile (option bit 20 disables)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from yogo_b200 import _lib as L
 lib = L.lib(); dev = "cuda:0"
 BASE = 25 + 8192 + 16384
-for (N, H, W, Cin, Cout, s) in [(2, 9, 11, 64, 128, 1), (1, 8, 16, 64, 64, 1), (3, 21, 37, 64, 128, 1), (64, 193, 258, 64, 128, 1)]:
+for (N, H, W, Cin, Cout, s) in [(2, 9, 11, 64, 128, 1), (3, 21, 37, 64, 128, 1), (64, 193, 258, 64, 128, 1), (3, 26, 35, 32, 64, 2),
+                               (2, 20, 28, 128, 128, 2), (2, 21, 37, 64, 128, 2), (64, 386, 516, 32, 64, 2), (64, 193, 258, 128, 128, 2)]:
     g = torch.Generator().manual_seed(N + H)
     x = torch.randn(N, H, W, Cin, generator=g).to(dev).bfloat16()
-    dz = torch.randn(N, H, W, Cout, generator=g).to(dev).bfloat16()
+    dz = torch.randn(N, (H - 1) // s + 1, (W - 1) // s + 1, Cout, generator=g).to(dev).bfloat16()
     res = {}
-    for name, opt in (("rows", BASE + (1 << 19)), ("merged", BASE)):
+    for name, opt in (("rows", BASE + (1 << 19) + (1 << 20) + (1 << 17)), ("merged", BASE + (1 << 17))):
         lib.yg_set_tc_options(opt)
         dw = torch.zeros(Cout, Cin, 3, 3, device=dev); db = torch.zeros(Cout, device=dev)
         nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, 3, s); ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)

@@ -1539,6 +1539,11 @@ struct TwParams {
   TcSrc asrc;        // dz as seen by the cp.async producer
   TcSrc bsrc[4];     // x (or its parity sub-grids)
   float* partial;
+  int share_a;          // stride 2 (two parity groups per tile): ONE stage per tile holds the dz tile once and both x boxes
+                        // (the dz tile used to be fetched from L2 once per group - the kernel is L2-bandwidth bound)
+  int merge2;           // stride 2, one B block per tap: the two row taps of the odd-parity group (filter rows 0 and 2, adjacent
+                        // rows of the same box) run as ONE N = 2 BNW MMA; they own the adjacent accumulator slots 0 and 1
+  int row_slot[3];      // accumulator slot of filter row r (identity unless merge2)
   int merge3;           // stride 1, one 64-channel B block per tap: the three filter rows of a column run as ONE N = 3 BNW MMA
                         // (the B descriptor's leading-dimension stride = one tile row of the halo box = the next row tap)
   int do_bias;          // also accumulate d(bias)[co] = sum over pixels of dz: one extra N = 16 MMA per K step against
@@ -1622,20 +1627,27 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
           const int tw = t % p.tiles_w; t /= p.tiles_w;
           const int th = t % p.tiles_h;
           const int n = t / p.tiles_h;
+          const bool share = p.share_a != 0;
           for (int gi = 0; gi < ngroups; ++gi) {
             const TwGroup& g = p.g[sg][gi];
-            mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 11);
             unsigned char* sa = smem + (size_t)stage * p.stage_bytes;
-            unsigned char* sb = sa + MBLOCKS * p.a_block_bytes;
-            const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + nbblocks * g.rows * TC_TW * (int)ROWB);
-            mbar_expect_tx_p(&full_bar[stage], bytes, leader);
-            for (int ab = 0; ab < a_blocks; ++ab)
-              tma_load_4d_p(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * KA, tw * TC_TW,
-                            th * TC_TH, n, leader);
+            unsigned char* sb = sa + MBLOCKS * p.a_block_bytes + (share ? (size_t)gi * nbblocks * p.b_block_bytes : 0);
+            if (!share || gi == 0) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 11);
+              int brows = g.rows;
+              if (share) for (int g2 = 1; g2 < ngroups; ++g2) brows += p.g[sg][g2].rows;
+              const uint32_t bytes = (uint32_t)(a_blocks * p.a_block_bytes + nbblocks * brows * TC_TW * (int)ROWB);
+              mbar_expect_tx_p(&full_bar[stage], bytes, leader);
+              for (int ab = 0; ab < a_blocks; ++ab)
+                tma_load_4d_p(sa + (size_t)ab * p.a_block_bytes, &maps.a, &full_bar[stage], mt * 128 + ab * KA, tw * TC_TW,
+                              th * TC_TH, n, leader);
+            }
             for (int bb = 0; bb < nbblocks; ++bb)
               tma_load_4d_p(sb + (size_t)bb * p.b_block_bytes, &maps.b[g.map], &full_bar[stage], nt * BNW + bb * KB,
                             tw * TC_TW + g.dw, th * TC_TH + g.dh, n, leader);
-            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            if (!share || gi == ngroups - 1) {
+              if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -1731,6 +1743,13 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
     uint32_t bias_started = 0;
     const uint32_t leader = elect_one();   // whole warp runs the loop, the elected lane issues
     int bias_it = 0;
+    const bool merge2 = p.merge2 != 0;
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                            ((uint32_t)((2 * BNW) >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t b2_lo0 = (uint32_t)umma_desc_mn(smem_u32(smem) + (uint32_t)MBLOCKS * (uint32_t)p.a_block_bytes,
+                                                   (uint32_t)TC_TW * ROWB, 8 * ROWB, LAYOUT_B);
+    const bool share_a = p.share_a != 0;
+    const uint32_t group_units = (uint32_t)(p.nbblocks * p.b_block_bytes) >> 4;
     // merged row taps: N = 3 BNW, block n of the N dimension = the same 64 channels one tile row (TC_TW pixels) further down
     const bool merge3 = p.merge3 != 0;
     const uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
@@ -1742,10 +1761,12 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
       if (++bias_it == bias_period) bias_it = 0;
       for (int gi = 0; gi < ngroups; ++gi) {
         const TwGroup& g = p.g[sg][gi];
-        mbar_wait(&full_bar[stage], phase, p.error_flag, 13);
-        tc_fence_after();
+        if (!share_a || gi == 0) {
+          mbar_wait(&full_bar[stage], phase, p.error_flag, 13);
+          tc_fence_after();
+        }
         const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units;
-        const uint32_t b_lo_s = b_lo0 + (uint32_t)stage * stage_units;
+        const uint32_t b_lo_s = b_lo0 + (uint32_t)stage * stage_units + (share_a ? (uint32_t)gi * group_units : 0u);
         const int ntaps = g.ntaps;
         if (bias_tile && gi == 0) {
           // d(bias) column: dz^T . ones, once per pixel tile
@@ -1764,6 +1785,16 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
             umma_bf16_lh2_p(tmem_base, a_lo + (uint32_t)k * ROWA, a_hi, b_lo + (uint32_t)k * ROWB, b_hi, idesc3,
                             (k > 0 ? 1u : acc0), leader);
           started |= 7u;
+        } else if (merge2 && ntaps == 2) {
+          const int slot = g.slot[0];   // slots slot, slot + 1 <-> box rows ro[0], ro[0] + 1
+          const uint32_t b_lo = b2_lo0 + (uint32_t)stage * stage_units + (share_a ? (uint32_t)gi * group_units : 0u) +
+                                (((uint32_t)(g.ro[0] * TC_TW) * ROWB) >> 4);
+          const uint32_t acc0 = (started >> slot) & 1u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_lh2_p(tmem_base + (uint32_t)(slot * BNW), a_lo + (uint32_t)k * ROWA, a_hi, b_lo + (uint32_t)k * ROWB, b_hi,
+                            idesc2, (k > 0 ? 1u : acc0), leader);
+          started |= 3u << slot;
         } else
         for (int tp = 0; tp < ntaps; ++tp) {
           const int slot = g.slot[tp];
@@ -1776,8 +1807,10 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
             umma_bf16_lh2_p(d_tmem, a_lo + (uint32_t)k * ROWA, a_hi, b_lo + (uint32_t)k * ROWB, b_hi, idesc, 1u, leader);
           started |= 1u << slot;
         }
-        umma_commit_p(&empty_bar[stage], leader);
-        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+        if (!share_a || gi == ngroups - 1) {
+          umma_commit_p(&empty_bar[stage], leader);
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
     umma_commit_p(&done_bar[0], leader);
@@ -1805,7 +1838,7 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
       for (int j = 0; j < BNW / 16; ++j) {
         uint32_t v[16];
         if (any_tile) {
-          tmem_ld16(tmem_base + (uint32_t)(r * BNW + j * 16) + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld16(tmem_base + (uint32_t)(p.row_slot[r] * BNW + j * 16) + ((uint32_t)(q * 32) << 16), v);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -1952,6 +1985,9 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   const int kb = pick_kc(Cin);
   p.kb = kb; p.nbblocks = p.BNW / kb;
   p.ncols = 3;
+  for (int r = 0; r < 3; ++r) p.row_slot[r] = r;
+  // stride 2 with one B block per tap: filter rows 0 and 2 take the adjacent slots 0 and 1 so that one MMA covers both
+  if (stride == 2 && p.BNW == kb && !(g_tc_options & (1 << 19))) { p.merge2 = 1; p.row_slot[0] = 0; p.row_slot[2] = 1; p.row_slot[1] = 2; }
   // base L4 wgrad 0.50 -> 0.38 ms (1235 TFLOP/s): three N = 64 MMAs (48 cycles each, bound by the shared-memory operand fetch)
   // become one N = 192 MMA (96 cycles of math, 80 of fetch); results are bit-identical.  Option bit 19 turns it off.
   p.merge3 = (stride == 1 && kb == 64 && p.BNW == 64 && !(g_tc_options & (1 << 19))) ? 1 : 0;
@@ -1963,6 +1999,15 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
   p.a_block_bytes = TC_TH * TC_TW * ka * 2;
   p.b_block_bytes = (max_rows * TC_TW * kb * 2 + 1023) & ~1023;
   p.stage_bytes = (128 / ka) * p.a_block_bytes + p.nbblocks * p.b_block_bytes;
+  // stride 2: both parity groups of a tile in one stage, sharing the dz tile (TMA producer only; option bit 20 turns it off)
+  {
+    const int shared_stage = (128 / ka) * p.a_block_bytes + 2 * p.nbblocks * p.b_block_bytes;
+    const bool cp_async_prod = kb <= 32 && (g_tc_options & 2);
+    if (stride == 2 && !cp_async_prod && !(g_tc_options & (1 << 20)) && TC_SMEM_BUDGET / shared_stage >= 2) {
+      p.share_a = 1;
+      p.stage_bytes = shared_stage;
+    }
+  }
   int nst = TC_SMEM_BUDGET / p.stage_bytes;
   if (nst > 6) nst = 6;
   if (nst < 2) { set_error("conv_wgrad_tc: stage of %d bytes does not fit twice", p.stage_bytes); return YG_ERR_INVALID; }
@@ -2016,11 +2061,11 @@ int conv_wgrad_tc(const void* x, const void* dz, float* dw, float* dbias, int N,
       const int pw = (s == 1) ? 0 : 1, dw_ = (s == 0) ? -1 : 0;
       TwGroup& g1 = p.g[s][0];
       g1.map = 2 + pw; g1.dh = -1; g1.dw = dw_; g1.rows = TC_TH + 1; g1.ntaps = 2;
-      g1.ro[0] = 0; g1.slot[0] = 0;
-      g1.ro[1] = 1; g1.slot[1] = 2;
+      g1.ro[0] = 0; g1.slot[0] = p.row_slot[0];
+      g1.ro[1] = 1; g1.slot[1] = p.row_slot[2];
       TwGroup& g0 = p.g[s][1];
       g0.map = pw; g0.dh = 0; g0.dw = dw_; g0.rows = TC_TH; g0.ntaps = 1;
-      g0.ro[0] = 0; g0.slot[0] = 1;
+      g0.ro[0] = 0; g0.slot[0] = p.row_slot[1];
     }
   }
   p.partial = (float*)ws;
@@ -2834,6 +2879,7 @@ int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* 
     wgrad_grid(Cin, DP, &p.nunits, &p.nslices, &grid, &p.BNW, &p.n_mtiles, &p.n_ntiles, 1);
     const int kb = pick_kc(Cin), ka = 32;
     p.kb = kb; p.nbblocks = p.BNW / kb; p.ncols = 1;
+    for (int r = 0; r < 3; ++r) p.row_slot[r] = r;
     p.N = N; p.Cin = Cin; p.Cout = DP;
     p.tiles_h = cdiv(Sy, TC_TH); p.tiles_w = cdiv(Sx, TC_TW);
     p.total_tiles = N * p.tiles_h * p.tiles_w;

@@ -415,9 +415,13 @@ __global__ void __launch_bounds__(256) head_dt_kernel(const float* __restrict__ 
     __align__(16) bf16 ob[HD_DP];
 #pragma unroll
     for (int d = 0; d < HD_DP; ++d) ob[d] = __float2bfloat16_rn(v[d]);
-    uint4* dst = reinterpret_cast<uint4*>(dt + p * HD_DP);
+    // the 64-byte row of this pixel as two 32-byte stores (full sectors)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<uint4*>(ob)[i];
+    for (int i = 0; i < 2; ++i) {
+      const uint4 lo = reinterpret_cast<uint4*>(ob)[2 * i], hi = reinterpret_cast<uint4*>(ob)[2 * i + 1];
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dt + p * HD_DP + 16 * i), "r"(lo.x), "r"(lo.y),
+                   "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    }
 #pragma unroll
     for (int d = 0; d < 16; ++d) { db[d] += v[d]; db_hi[d] += v[16 + d]; }
   }
