@@ -84,7 +84,7 @@ def main():
                 fn()
             e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / args.reps
+            ms = e0.elapsed_time(e1) / max(args.reps, 1)   # --reps 0: one launch per op (ncu captures)
             tf = flops / ms / 1e9
             act_bytes = (N * H * W * Cin + N * Ho * Wo * Cout) * 2
             rec = {"opt": args.tc_options, "layer": li, "op": name, "shape": [N, H, W, Cin, Cout, s], "ms": round(ms, 4), "TFLOPs": round(tf, 1),
