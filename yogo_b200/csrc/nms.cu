@@ -49,8 +49,11 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
   // torchvision/csrc/ops/cpu/nms_kernel.cpp semantics
   const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
   const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
-  const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float w = __fsub_rn(xx2, xx1);
+  const float h = __fsub_rn(yy2, yy1);
+  // disjoint boxes (or NaN coordinates): the clamped intersection is 0 and 0 / x > thr is false for the thr > 0 NMS runs
+  // with (0 / 0 = NaN never suppresses either) - most pairs of a sparse image end here, before the IEEE division
+  if (!(w > 0.f && h > 0.f)) return false;
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
   return (double)ovr > thr;
