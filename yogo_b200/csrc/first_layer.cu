@@ -561,7 +561,7 @@ constexpr int FM_WARPS = 4;
 
 // NM = number of 16-channel M tiles (Cout = 16 NM): the X tile and its two B fragments are shared by all of them
 template <int NM>
-__global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : (NM == 2 ? 5 : 4)) first_bwd_mma_kernel(
+__global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 5 : (NM == 2 ? 4 : 3)) first_bwd_mma_kernel(
     const uint8_t* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ da, int H, int W, int Ho, int Wo,
     int stride, BwdEpi be, const float* __restrict__ fwd_shift, float* __restrict__ partial, int chunk, int cpi, int ntasks) {
   constexpr int CO = 16 * NM;
@@ -630,25 +630,38 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : (NM == 2 ? 5 : 4)
     const bf16* dim = da + (long long)n * npix * CO;
     PixCursor cur;
     cur.init(p0 + warp * 32 + lane, Wo);
-    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
+    // software pipeline: the taps and the gradient row of the NEXT 32 pixels are requested before this iteration's tile is
+    // staged and multiplied, so their HBM latency overlaps the ldmatrix / mma chain instead of heading it
+    float vn[9];
+    uint4 dn[2 * NM];
+    auto fetch = [&](const PixCursor& c) {
+#pragma unroll
+      for (int i = 0; i < 2 * NM; ++i) dn[i] = make_uint4(0, 0, 0, 0);
+      if (c.p < p1) {
+        load_taps1<uint8_t>(xim, H, W, stride, c.ho, c.wo, vn);
+        const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)c.p * CO);
+#pragma unroll
+        for (int m = 0; m < NM; ++m)
+          asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(dn[2 * m].x), "=r"(dn[2 * m].y), "=r"(dn[2 * m].z), "=r"(dn[2 * m].w), "=r"(dn[2 * m + 1].x),
+                         "=r"(dn[2 * m + 1].y), "=r"(dn[2 * m + 1].z), "=r"(dn[2 * m + 1].w) : "l"(gp + 2 * m));
+      } else {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) vn[t] = 0.f;
+      }
+    };
+    if (p0 + warp * 32 < p1) fetch(cur);
+    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32) {
       // ---- stage the 32 pixels of this warp: thread = pixel
       {
         float v[9];
         uint4 d[2 * NM];
 #pragma unroll
-        for (int i = 0; i < 2 * NM; ++i) d[i] = make_uint4(0, 0, 0, 0);
-        if (cur.p < p1) {
-          load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
-          const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)cur.p * CO);
+        for (int t = 0; t < 9; ++t) v[t] = vn[t];
 #pragma unroll
-          for (int m = 0; m < NM; ++m)
-            asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(d[2 * m].x), "=r"(d[2 * m].y), "=r"(d[2 * m].z), "=r"(d[2 * m].w), "=r"(d[2 * m + 1].x),
-                           "=r"(d[2 * m + 1].y), "=r"(d[2 * m + 1].z), "=r"(d[2 * m + 1].w) : "l"(gp + 2 * m));
-        } else {
-#pragma unroll
-          for (int t = 0; t < 9; ++t) v[t] = 0.f;
-        }
+        for (int i = 0; i < 2 * NM; ++i) d[i] = dn[i];
+        cur.advance(FM_WARPS * 32, Wo);
+        if (pb + FM_WARPS * 32 < p1) fetch(cur);
         const uint4 x0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         const uint4 x1 = make_uint4(pack_bf16(v[8], 1.f), 0u, 0u, 0u);   // tap 8, the ones column, zero padding
         const int sw = (lane >> 2) & 1;
