@@ -122,6 +122,8 @@ int yg_conv_first_bwd_finalize(const float* P, const float* Sg, const double* gr
                                int batch_stats, float clip, int Cout, float* dw, float* dbias, float* dgamma,
                                float* dbeta, void* stream);
 
+/* Alignment: activation tensors handed to the convolution entry points should be 32-byte aligned (torch allocations are
+ * 256-byte aligned); tensors that are only 16-byte aligned run on the generic SIMT path. */
 /* ---- generic convolution (3x3 pad 1 or 1x1 pad 0, stride 1 or 2), NHWC -------------
  * replaces nn.Conv2d fprop / dgrad / wgrad (cuDNN) at model_defns.py:34-67 and the
  * elementwise BatchNorm/LeakyReLU/SiLU/Dropout2d kernels that follow each conv. */

@@ -536,6 +536,33 @@ def test_first_layer_tensor_core_kernels_vs_torch(Cout, act):
     assert _rel(dw2.cpu(), dw_ref) < 3e-3 and _rel(dsh2.cpu(), ds_ref) < 3e-3
 
 
+def test_tensors_that_are_only_16_byte_aligned_take_the_generic_path():
+    """The tensor-core epilogues use 32-byte stores; a 16-byte aligned view must not fault and must give the same result."""
+    import ctypes as C
+    N, H, W, Cin, Cout = 2, 12, 20, 64, 128
+    g = torch.Generator().manual_seed(9)
+    lib = L.lib()
+    x = torch.randn(N, H, W, Cin, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / 24).to(DEV)
+    b = torch.zeros(Cout, device=DEV)
+    y = torch.empty(N, H, W, Cout, device=DEV, dtype=torch.bfloat16)
+    ep = L.FwdEpilogue(None, b.data_ptr(), L.ACT_LRELU, None, None, None)
+    L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, 1, C.byref(ep), L.stream()))
+    buf = torch.empty(y.numel() + 8, device=DEV, dtype=torch.bfloat16)
+    y2 = buf[8:].view(N, H, W, Cout)
+    assert y2.data_ptr() % 32 == 16
+    L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y2.data_ptr(), 1, N, H, W, Cin, Cout, 3, 1, C.byref(ep), L.stream()))
+    torch.cuda.synchronize()
+    assert _rel(y2.float().cpu(), y.float().cpu()) < 6e-3
+    dx = torch.empty_like(x)
+    dxb = torch.empty(x.numel() + 8, device=DEV, dtype=torch.bfloat16)
+    dx2 = dxb[8:].view(N, H, W, Cin)
+    L.check(lib.yg_conv_dgrad(y.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, 1, None, L.stream()))
+    L.check(lib.yg_conv_dgrad(y.data_ptr(), w.data_ptr(), dx2.data_ptr(), 1, N, H, W, Cin, Cout, 3, 1, None, L.stream()))
+    torch.cuda.synchronize()
+    assert _rel(dx2.float().cpu(), dx.float().cpu()) < 6e-3
+
+
 # ----------------------------------------------------------------------------- whole model vs golden
 def _build_from_golden(z, name, sdprefix="sd.", dtype=torch.float32, inference=False):
     sd = {k[len(sdprefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(sdprefix)}

@@ -72,6 +72,8 @@ static int yg_get_tc_options_raw() { return get_tc_options(); }
 extern "C" int yg_set_tc_options(int v) { return set_tc_options(v); }
 extern "C" int yg_tc_debug_read(unsigned long long* out, int n) { return tc_debug_read(out, n); }
 
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
 template <typename T>
 __global__ void actmask_from_output_kernel(const T* __restrict__ y, uint32_t* __restrict__ mask, long long nwords) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,9 +90,11 @@ extern "C" int yg_conv_fwd(const void* x, const float* w, void* y, int dtype, in
   YG_CHECK_ARG(x && w, "conv_fwd: null pointer");
   if (N == 0) return YG_OK;
   FwdEpi ep = make_fwd_epi(epp);
-  const bool tc_ok = tc_fwd_supported(dtype, W, Cin, Cout, ks, stride);
+  // the tensor-core epilogues move pixel rows with 32-byte accesses: tensors that are not 32-byte aligned (never the case for
+  // torch allocations) take the generic path
+  const bool tc_ok = tc_fwd_supported(dtype, W, Cin, Cout, ks, stride) && aligned32(x) && aligned32(y) && aligned32(ep.preact);
   if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
-    set_error("conv_fwd: tcgen05 path forced but shape unsupported (dtype %d Cin %d Cout %d k %d s %d)", dtype, Cin, Cout, ks, stride);
+    set_error("conv_fwd: tcgen05 path forced but shape or alignment unsupported (dtype %d Cin %d Cout %d k %d s %d)", dtype, Cin, Cout, ks, stride);
     return YG_ERR_INVALID;
   }
   if (ep.actmask) YG_CHECK_ARG(Cout % 32 == 0 && y, "conv_fwd: actmask needs Cout % 32 == 0 and an output tensor");
@@ -117,9 +121,9 @@ extern "C" int yg_conv_dgrad(const void* dz, const float* w, void* dx, int dtype
   YG_CHECK_ARG(dz && w && dx, "conv_dgrad: null pointer");
   if (N == 0) return YG_OK;
   BwdEpi be = make_bwd_epi(bep);
-  const bool tc_ok = tc_dgrad_supported(dtype, W, Cin, Cout, ks, stride);
+  const bool tc_ok = tc_dgrad_supported(dtype, W, Cin, Cout, ks, stride) && aligned32(dz) && aligned32(dx) && aligned32(be.saved);
   if (g_conv_impl == YG_IMPL_TCGEN05 && !tc_ok) {
-    set_error("conv_dgrad: tcgen05 path forced but shape unsupported");
+    set_error("conv_dgrad: tcgen05 path forced but shape or alignment unsupported");
     return YG_ERR_INVALID;
   }
   if (tc_ok && g_conv_impl != YG_IMPL_SIMT)

@@ -938,7 +938,8 @@ extern "C" int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, voi
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1 && (Cout == 16 || Cout == 32 || Cout == 48) && dtype == YG_BF16 && !ep.preact && (long long)Ho * Wo < (1LL << 30) &&
-      (long long)H * W < (1LL << 31) && x_dtype == YG_U8 && !ep.stats && y && yg_get_conv_impl() != YG_IMPL_SIMT) {
+      (long long)H * W < (1LL << 31) && x_dtype == YG_U8 && !ep.stats && y && (reinterpret_cast<uintptr_t>(y) & 31u) == 0 &&
+      yg_get_conv_impl() != YG_IMPL_SIMT) {
     // warp-level tensor cores, one M tile per 16 output channels (base 16, double_filters 32, triple_filters 48)
     const int chunkm = 16 * FM_WARPS * 32, cpim = cdiv((long long)Ho * Wo, chunkm), ntasksm = N * cpim;
     const int per_sm = Cout == 16 ? 8 : 6;
@@ -999,7 +1000,8 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
     }
   }
   if (mode == 1 && Cin == 1 && (Cout == 16 || Cout == 32 || Cout == 48) && dtype == YG_BF16 && x_dtype == YG_U8 && !bn_dy_mean &&
-      Wo >= 32 && (long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31) && yg_get_conv_impl() != YG_IMPL_SIMT) {
+      Wo >= 32 && (long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31) && (reinterpret_cast<uintptr_t>(da) & 31u) == 0 &&
+      yg_get_conv_impl() != YG_IMPL_SIMT) {
     // raw P / Sg pass on the tensor cores (first_bwd_mma_kernel), one M tile per 16 output channels
     const int chunk = 64 * FM_WARPS * 32, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
     const int grid1 = ntasks < FL_BWD_BLOCKS ? ntasks : FL_BWD_BLOCKS;
