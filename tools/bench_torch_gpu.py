@@ -57,6 +57,34 @@ def main():
         ms = e0.elapsed_time(e1) / args.steps
         res[name + "_ms"] = round(ms, 3)
         res[name + "_img_s"] = round(args.batch / ms * 1e3, 1)
+    # post-processing as the reference does it (utils/prediction_formatting.py:23-93, infer.py:60-87) with torch / torchvision
+    # ops on the GPU: one Python iteration per image - mask gather, box_convert, ops.nms (CUDA), fancy index, argmax counts
+    import torchvision.ops as ops
+    preds = S.synth_sparse_preds(args.batch, K=300).to(dev)
+
+    def post():
+        tot = torch.zeros(7, dtype=torch.long, device=dev)
+        for pred in preds:
+            p = pred.view(pred.shape[0], -1).T
+            c = p[p[:, 4] > 0.5]
+            keep = ops.nms(ops.box_convert(c[:, :4], "cxcywh", "xyxy"), c[:, 5:].max(dim=1).values * c[:, 4], 0.5)
+            rows = c[keep]
+            vals, idx = rows[:, 5:].max(dim=1)
+            tot += torch.nn.functional.one_hot(idx[vals > 0], num_classes=7).sum(dim=0)
+        return tot
+
+    for _ in range(3):
+        post()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        post()
+    e1.record()
+    torch.cuda.synchronize()
+    res["torch_postproc_sparse_ms"] = round(e0.elapsed_time(e1) / 5, 3)
+    rows, kc, _, counts = yogo_b200.format_preds_batch(preds)
+    assert torch.equal(counts.cpu(), post().cpu())   # same per-class counts
     print(json.dumps(res), flush=True)
 
 
