@@ -1883,10 +1883,13 @@ __global__ void wgrad_bias_reduce_kernel(const float* __restrict__ part, float* 
 // s = g*(s'-1) + pi - q + 1 (g = 1: the identity).
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
                                        int g, int BNW, int n_mtiles, int nunits, int nslices, float clip) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over real [co][ci][r][s]
-  if (i >= (long long)Cout * Cin * 9) return;
-  const int s = (int)(i % 3), r = (int)((i / 3) % 3);
-  const int ci = (int)((i / 9) % Cin), co = (int)(i / (9LL * Cin));
+  // thread order [co][r][s][ci] (ci fastest): a warp reads consecutive floats of a partial row; the OIHW store is strided but tiny.
+  // The per-element summation order (fold position, then slice) is fixed, so the result does not depend on this mapping.
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (long long)Cout * Cin * 9) return;
+  const int ci = (int)(j % Cin), s = (int)((j / Cin) % 3), r = (int)((j / (3LL * Cin)) % 3);
+  const int co = (int)(j / (9LL * Cin));
+  const long long i = (((long long)co * Cin + ci) * 3 + r) * 3 + s;
   float acc = 0.f;
   for (int sp = 0; sp < 3; ++sp)
     for (int q = 0; q < g; ++q) {
@@ -1895,9 +1898,10 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
       const int cof = q * Cout + co, cif = pi * Cin + ci;
       const int mt = cof / 128, nt = cif / BNW;
       const int unit = sp + 3 * (mt + n_mtiles * nt);
-      for (int sl = 0; sl < nslices; ++sl) {
+#pragma unroll 8
+      for (int sl = 0; sl < nslices; ++sl) {   // independent loads, adds in slice order
         const size_t cta = (size_t)unit + (size_t)nunits * sl;
-        acc += partial[((cta * 3 + r) * 128 + (cof % 128)) * BNW + (cif % BNW)];
+        acc += __ldg(&partial[((cta * 3 + r) * 128 + (cof % 128)) * BNW + (cif % BNW)]);
       }
     }
   dw[i] = clampf(acc, clip);
