@@ -346,6 +346,14 @@ SHAPES = [
     (1, 10, 14, 128, 128, 3, 1),
     (2, 10, 14, 48, 96, 3, 1),
     (2, 10, 14, 24, 12, 1, 1),
+    # double_filters / triple_filters widths (model_defns.py:130-227): N = 256 MMAs, non-resident weights
+    (2, 9, 11, 128, 256, 3, 1),
+    (1, 10, 14, 256, 256, 3, 1),
+    (2, 20, 28, 256, 256, 3, 2),
+    (2, 11, 14, 96, 192, 3, 2),
+    (1, 10, 14, 192, 384, 3, 1),
+    (1, 9, 13, 384, 384, 3, 2),
+    (2, 10, 14, 256, 12, 1, 1),
 ]
 
 
@@ -718,6 +726,135 @@ def test_full_size_train_step_vs_oracle_fp32():
         assert _rel(g.numpy(), r.numpy()) < 3e-3, (key, _rel(g.numpy(), r.numpy()))
 
 
+# ----------------------------------------------------------------------------- every definition, RGB, BASELINE geometry
+from _zoo_cases import ZOO_CASES, zoo_inputs  # noqa: E402
+
+FULL_CASES = ["full_base_model", "full_silu_model", "full_double_filters"]
+
+
+def _zoo_step(z, case, dtype, impl="auto"):
+    name, net, img, lab, ostride = zoo_inputs(z, case)
+    prefix = case + ".train."
+    net = net.to(DEV)
+    net.compute_dtype = dtype
+    net.train()
+    net._get_runner().drop_keep_override = {
+        int(k.split(".")[-1]): torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix + "keep.")}
+    out = net((img.float() / 255.0).to(DEV))
+    loss, comps = yogo_b200.YOGOLoss().to(DEV)(out, lab.to(DEV))
+    loss.backward()
+    o = out.detach().cpu().numpy()[:, :, ::ostride, ::ostride]
+    # a conv bias in front of BatchNorm has a mathematically zero gradient (the batch mean removes it): what is left is
+    # rounding noise of a cancelling sum, compared against the scale of the BatchNorm bias gradient of the same block
+    zero_keys = {f"model.{i}.0.bias": f"model.{i}.1.bias" for i, blk in enumerate(net.model)
+                 if isinstance(blk, torch.nn.Sequential) and len(blk) > 1 and isinstance(blk[1], torch.nn.BatchNorm2d)
+                 and blk[0].bias is not None}
+    errs = {}
+    for k, p in net.named_parameters():
+        g = p.grad.detach().cpu().numpy().reshape(-1)
+        exp = z[prefix + "grad." + k]
+        g = g[:: max(1, -(-g.size // 4096))]
+        scale = float(np.linalg.norm(exp))
+        if k in zero_keys:
+            scale = max(scale, float(z[prefix + "gradnorm." + zero_keys[k]][0]))
+        errs[k] = float(np.linalg.norm(g - exp)) / max(scale, 1e-3)
+    return net, o, loss, comps, errs
+
+
+@pytest.mark.parametrize("case", ZOO_CASES)
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_zoo_train_step_fp32_matches_reference_golden(golden_dir, case, impl):
+    """double/triple/half_filters, depth_ver_1..4 (model_defns.py:130-277, 358-529) and RGB input (:32): one fp32
+    train step vs the real reference, 1e-3 relative."""
+    z = _load(golden_dir, "model_zoo.npz")
+    L.set_conv_impl(impl)
+    try:
+        net, o, loss, comps, errs = _zoo_step(z, case, torch.float32)
+    finally:
+        L.set_conv_impl("auto")
+    prefix = case + ".train."
+    assert _rel(o, z[prefix + "out"]) < 1e-3
+    np.testing.assert_allclose(
+        [loss.item(), comps["iou_loss"], comps["objectness_loss"], comps["classification_loss"]], z[prefix + "loss"], rtol=1e-3)
+    bad = {k: v for k, v in errs.items() if v > 2e-3}
+    assert not bad, bad
+    for k, v in net.state_dict().items():
+        if "running_" in k:
+            np.testing.assert_allclose(v.cpu().numpy(), z[f"{prefix}after.{k}"], rtol=1e-3, atol=1e-6)
+
+
+def _bf16_bounds_ok(z, case, o, loss, errs, factor=2.0):
+    """Yardstick = the reference's OWN bf16-autocast error against its fp32 run on the same inputs, weights and masks,
+    recorded per tensor by make_golden.py.  Measured over the 12 cases x ~20 tensors of
+    model_zoo.npz / model_full.npz, our error / the reference's error has a median of 0.8 (the engine is a little more
+    accurate than autocast), but a single tensor is a single draw of a rounding error: on 7x9 grids the weight gradient of
+    the last 3x3 conv is dominated by the two dozen labelled cells and reaches 1.4 - 2.4 x.  Acceptance: every tensor
+    <= `factor` x the yardstick (floors for near-zero tensors) AND the median ratio over the tensors <= 1.25."""
+    pre = case + "."
+
+    def bound(key, floor):
+        return max(factor * float(z[pre + "bf16err." + key][0]), floor)
+
+    report = {}
+    e = _rel(o, z[pre + "train.out"])
+    if e >= bound("out", 1e-2):
+        report["out"] = (e, bound("out", 1e-2))
+    ref_loss = z[pre + "train.loss"][0]
+    e = abs(loss.item() - ref_loss) / abs(ref_loss)
+    if e >= bound("loss", 1e-3):
+        report["loss"] = (e, bound("loss", 1e-3))
+    for k, v in errs.items():
+        if v >= bound("grad." + k, 2e-2):
+            report[k] = (v, bound("grad." + k, 2e-2))
+    ratios = [v / max(float(z[pre + "bf16err.grad." + k][0]), 1e-2) for k, v in errs.items()]
+    if float(np.median(ratios)) > 1.25:
+        report["median ratio"] = float(np.median(ratios))
+    return report
+
+
+@pytest.mark.parametrize("case", ZOO_CASES)
+def test_zoo_train_step_bf16_within_calibrated_tolerance(golden_dir, case):
+    z = _load(golden_dir, "model_zoo.npz")
+    net, o, loss, comps, errs = _zoo_step(z, case, torch.bfloat16)
+    report = _bf16_bounds_ok(z, case, o, loss, errs, factor=3.0)   # tiny grids: see _bf16_bounds_ok
+    assert not report, report
+
+
+@pytest.mark.parametrize("case", FULL_CASES)
+def test_full_geometry_train_step_bf16_vs_reference_golden(golden_dir, case):
+    """BASELINE configs[1] / configs[3] geometry (772x1032 -> 97x129; many tiles per CTA, TMEM accumulators in rotation,
+    W-fold, CTA pairs, parity classes with 97x129 tails, N = 256 MMAs) on the bf16 tcgen05 path that bench.py times,
+    against the real reference's fp32 step with its own bf16-autocast error as the yardstick."""
+    z = _load(golden_dir, "model_full.npz")
+    net, o, loss, comps, errs = _zoo_step(z, case, torch.bfloat16)
+    report = _bf16_bounds_ok(z, case, o, loss, errs)
+    assert not report, report
+    name, net, img, _, ostride = zoo_inputs(z, case)   # fresh buffers: the golden eval output uses the initial running stats
+    net = net.to(DEV)
+    net.compute_dtype = torch.bfloat16
+    net.eval()
+    with torch.no_grad():
+        ev = net((img.float() / 255.0).to(DEV)).cpu().numpy()[:, :, ::ostride, ::ostride]
+    assert _rel(ev, z[case + ".eval.out"]) < 3e-2
+
+
+@pytest.mark.parametrize("case", ["full_base_model", "full_silu_model"])
+def test_full_geometry_train_step_fp32_vs_reference_golden(golden_dir, case):
+    """fp32 storage path at the BASELINE geometry.  With 1e8 LeakyReLU inputs some always sit within rounding noise of
+    the kink, and taking the other slope there is a legitimate fp32 result: the reference's own fp32 gradients differ from
+    its float64 gradients by up to 1.5e-2 on this fixture (fp32err.*, make_golden.py).  Bound per tensor: max(1e-3 (north
+    star), 3 x that error).  silu_model has no kink: its bounds stay at 1e-3 for every tensor."""
+    z = _load(golden_dir, "model_full.npz")
+    net, o, loss, comps, errs = _zoo_step(z, case, torch.float32)
+    assert _rel(o, z[case + ".train.out"]) < 1e-3
+    assert abs(loss.item() - z[case + ".train.loss"][0]) < 1e-3 * abs(z[case + ".train.loss"][0])
+    bound = {k: max(1e-3, 3.0 * float(z[f"{case}.fp32err.grad.{k}"][0])) for k in errs}
+    if case == "full_silu_model":
+        bound = {k: 1e-3 for k in errs}
+    bad = {k: (v, bound[k]) for k, v in errs.items() if v > bound[k]}
+    assert not bad, bad
+
+
 def test_variable_batch_and_3d_input():
     net = yogo_b200.YOGO((64, 96), 0.05, 0.05, 7).to(DEV)
     net.eval()
@@ -838,6 +975,63 @@ def test_conv_outputs_stay_inside_their_buffers(shape):
     torch.cuda.synchronize()
     assert intact(dxbuf, dx.numel(), 7.0) and intact(dwbuf, dw.numel(), 7.0) and intact(dbbuf, db.numel(), 7.0)
     assert bool(torch.isfinite(dx.float()).all()) and bool(torch.isfinite(dw).all())
+
+
+def test_conv_tensors_larger_than_4GiB():
+    """Index arithmetic beyond 2^32 bytes (double_filters at batch >= 168, base_model at batch 256 x 2 maps): a 32 -> 64
+    stride-1 conv whose bf16 output is 4.4 GB.  Forward and dgrad are compared at sampled pixels (the last image sits
+    above the 4 GiB line) with F.conv2d on the surrounding patches; wgrad by additivity over the batch."""
+    import ctypes as C
+    lib = L.lib()
+    N, H, W, Cin, Cout = 172, 386, 516, 32, 64
+    assert N * H * W * Cout * 2 > (1 << 32) + (1 << 26)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    dt = torch.bfloat16
+    x = torch.randn(N, H, W, Cin, device=DEV, generator=g, dtype=torch.float32).to(dt)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, device=DEV, generator=g) * 0.1
+    y = torch.empty(N, H, W, Cout, device=DEV, dtype=dt)
+    ep = L.FwdEpilogue(None, b.data_ptr(), L.ACT_NONE, None, None, None, None)
+    L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, 1, C.byref(ep), L.stream()))
+    dz = torch.randn(N, H, W, Cout, device=DEV, generator=g, dtype=torch.float32).to(dt)
+    dx = torch.empty(N, H, W, Cin, device=DEV, dtype=dt)
+    L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, 1, None, L.stream()))
+    rs = np.random.RandomState(0)
+    pts = [(n, int(rs.randint(0, H)), int(rs.randint(0, W))) for n in (0, 1, 85, 86, 167, 168, 169, 170, 171) for _ in range(24)]
+    pts += [(171, H - 1, W - 1), (171, 0, 0), (171, H - 1, 0), (168, H - 1, W - 1), (0, 0, 0)]
+    wc, bc = w.cpu(), b.cpu()
+    for (n, h, ww) in pts:
+        h0, h1, w0, w1 = max(h - 1, 0), min(h + 2, H), max(ww - 1, 0), min(ww + 2, W)
+        patch = torch.zeros(1, Cin, 3, 3)
+        patch[0, :, h0 - h + 1:h1 - h + 1, w0 - ww + 1:w1 - ww + 1] = x[n, h0:h1, w0:w1].float().cpu().permute(2, 0, 1)
+        ref = torch.nn.functional.conv2d(patch, wc, bc)[0, :, 0, 0]
+        assert _rel(y[n, h, ww].float().cpu(), ref) < 6e-3, ("fwd", n, h, ww)
+        gp = torch.zeros(1, Cout, 3, 3)
+        gp[0, :, h0 - h + 1:h1 - h + 1, w0 - ww + 1:w1 - ww + 1] = dz[n, h0:h1, w0:w1].float().cpu().permute(2, 0, 1)
+        # dx[ci] = sum_{co,r,s} dz[h+1-r, w+1-s, co] w[co,ci,r,s]  == conv of the dz patch with the flipped, transposed filter
+        refd = torch.nn.functional.conv2d(gp, wc.flip(2, 3).permute(1, 0, 2, 3))[0, :, 0, 0]
+        assert _rel(dx[n, h, ww].float().cpu(), refd) < 6e-3, ("dgrad", n, h, ww)
+    # wgrad is additive over images: whole batch == first 160 + last 12 (the last chunk starts beyond 4 GiB of dz)
+    nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, 3, 1)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
+
+    def wgrad(xs, dzs):
+        n = xs.shape[0]
+        dw = torch.empty_like(w)
+        db = torch.empty_like(b)
+        L.check(lib.yg_conv_wgrad(xs.data_ptr(), dzs.data_ptr(), dw.data_ptr(), db.data_ptr(), 1, n, H, W, Cin, Cout, 3, 1, 0.0,
+                                  ws.data_ptr(), nb, L.stream()))
+        return dw.double().cpu(), db.double().cpu()
+
+    dw_all, db_all = wgrad(x, dz)
+    dw_a, db_a = wgrad(x[:160], dz[:160])
+    dw_b, db_b = wgrad(x[160:], dz[160:])
+    assert _rel(dw_all, dw_a + dw_b) < 1e-4 and _rel(db_all, db_a + db_b) < 1e-4
+    # and the tail chunk against autograd on the CPU
+    xr = x[160:].float().cpu().permute(0, 3, 1, 2)
+    wr = wc.clone().requires_grad_(True)
+    torch.nn.functional.conv2d(xr, wr, None, padding=1).backward(dz[160:].float().cpu().permute(0, 3, 1, 2))
+    assert _rel(dw_b, wr.grad.double()) < 3e-3
 
 
 @pytest.mark.parametrize("shape", [(2, 19, 35, 16, 32, 1), (1, 8, 32, 16, 32, 1), (3, 21, 37, 32, 64, 2), (2, 40, 70, 16, 32, 1)])

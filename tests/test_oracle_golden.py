@@ -185,3 +185,33 @@ def test_model_oracle_eval_and_inference(golden_dir):
             t = O.backbone_forward(x, blocks, train=False)
             out = O.head_transform(t, float(sd["anchor_w"]), float(sd["anchor_h"]), inference=inf)
         np.testing.assert_allclose(out.numpy(), z[key], rtol=2e-4, atol=2e-5)
+
+
+from _zoo_cases import ZOO_CASES, zoo_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ZOO_CASES)
+def test_zoo_oracle_train_step_matches_reference(golden_dir, case):
+    """Every registered definition (model_defns.py:130-529) and RGB input (:32) through the oracle vs the real reference."""
+    z = _load(golden_dir, "model_zoo.npz")
+    name, net, img, lab, _ = zoo_inputs(z, case)
+    prefix = case + ".train."
+    sd = net.state_dict()
+    blocks = O.blocks_from_state_dict(name, sd)
+    for b in blocks:
+        b.weight.requires_grad_(True)
+    keeps = [torch.from_numpy(z[f"{prefix}keep.{i}"]) if f"{prefix}keep.{i}" in z.files else None
+             for i in range(len(blocks))]
+    t = O.backbone_forward(img.float() / 255.0, blocks, train=True, drop_keep=keeps, update_running=True)
+    out = O.head_transform(t, 0.0425, 0.0555)
+    loss, comps, dpred = O.yogo_loss_np(out.detach().numpy(), lab.numpy())
+    out.backward(torch.from_numpy(dpred))
+    np.testing.assert_allclose(out.detach().numpy(), z[prefix + "out"], rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(loss, z[prefix + "loss"][0], rtol=2e-4)
+    for i, b in enumerate(blocks):
+        key = f"model.{i}.weight" if i == len(blocks) - 1 else f"model.{i}.0.weight"
+        g = b.weight.grad.clamp(-1, 1).numpy().reshape(-1)
+        exp = z[prefix + "grad." + key]
+        g = g[:: max(1, -(-g.size // 4096))]
+        scale = max(1e-6, float(np.abs(exp).max()))
+        assert np.abs(g - exp).max() <= 1e-3 * scale + 2e-6, key

@@ -69,3 +69,33 @@ def synth_sparse_preds(B: int, Sy: int = 97, Sx: int = 129, C: int = 7, K: int =
                 p[b, 3, j, i] = ANCHOR_H * (1 + 0.05 * (2 * torch.rand(n, generator=g) - 1))
                 p[b, 4, j, i] = 0.6 + 0.4 * torch.rand(n, generator=g)
     return p
+
+
+def synth_fill_model(net: torch.nn.Module, seed: int = 0, head_scale: float = 0.05) -> None:
+    """Deterministic parameters for parity fixtures without committing the weights: values are integers drawn with
+    numpy's PCG64 scaled by a power-of-two-free constant in fp32 (bit-reproducible on any host).  Same statistics as
+    the reference's Kaiming(fan_out) init (model.py:79-87) for conv weights, head weights scaled by ``head_scale``
+    (SURVEY.md 8d "tame"), conv biases U(-.1,.1), BatchNorm weight U(.5,1.5) / bias U(-.2,.2).  Applies to any module
+    whose ``.model`` is the backbone Sequential (the reference's YOGO and yogo_b200.YOGO alike)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+
+    def u(shape, lo, hi):
+        ints = rng.integers(0, 1 << 16, size=tuple(shape), dtype=np.int64).astype(np.float32)
+        return torch.from_numpy(np.float32(lo) + ints * np.float32((hi - lo) / 65536.0))
+
+    convs = [m for m in net.model.modules() if isinstance(m, torch.nn.Conv2d)]
+    with torch.no_grad():
+        for m in net.model.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                fan_out = m.weight.shape[0] * m.weight.shape[2] * m.weight.shape[3]
+                a = (3.0 * 2.0 / fan_out) ** 0.5
+                if m is convs[-1]:
+                    a *= head_scale
+                m.weight.copy_(u(m.weight.shape, -a, a))
+                if m.bias is not None:
+                    m.bias.copy_(u(m.bias.shape, -0.1, 0.1))
+            elif isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(u(m.weight.shape, 0.5, 1.5))
+                m.bias.copy_(u(m.bias.shape, -0.2, 0.2))

@@ -203,7 +203,30 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def stream() -> int:
+    """The caller's current stream on the CURRENT device; every entry point runs under `on_device` so that the current
+    device is the one the tensors live on."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(pick):
+    """Decorator: run the wrapped entry point with the CUDA device of the tensor `pick(*args, **kwargs)` returns as the
+    current device (kernel launches, cudaMemsetAsync, TMA descriptors and `stream()` all use the current device; ATen
+    does this switch for every op of the reference).  Non-CUDA tensors pass through so that the callee raises its own
+    'no CPU fallback' error."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            t = pick(*args, **kwargs)
+            if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kwargs)
+            return fn(*args, **kwargs)
+
+        return wrapped
+
+    return deco
 
 
 def dtype_code(dt: torch.dtype) -> int:

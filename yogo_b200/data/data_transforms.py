@@ -43,6 +43,7 @@ class ImageTransformLabelIdentity(DualInputModule):
         return self.transform(img_batch), labels
 
 
+@L.on_device(lambda img_batch, *a, **k: img_batch)
 def flip_batch(img_batch: torch.Tensor, label_batch: torch.Tensor, hflip: bool, vflip: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     """Images (N,C,H,W) uint8/fp32 and labels (N,6,Sy,Sx) flipped horizontally and/or vertically with the box coordinates
     mirrored (x1' = 1 - x2, ...), out of place, two launches."""

@@ -167,6 +167,7 @@ class Runner:
         return x.contiguous(), code
 
     # ---------------------------------------------------------------- forward
+    @L.on_device(lambda self, x, want_grad: x)
     def forward(self, x: torch.Tensor, want_grad: bool):
         own = self.owner
         lib = L.lib()
@@ -249,9 +250,12 @@ class Runner:
                                                                       float(N * ho * wo), blk.cout, stats.data_ptr(), st))
                         else:
                             # pass 1: conv (+bias) with the plain epilogue, then one streaming pass for sum / sum of squares
-                            # (cheaper than reducing inside the tensor-core epilogue, and keeps the MMAs at full rate)
-                            conv(_fwd_ep(shift=bias), y_raw)
-                            L.check(lib.yg_bn_stats(y_raw.data_ptr(), dcode, N, ho * wo, blk.cout, stats.data_ptr(), st))
+                            # (cheaper than reducing inside the tensor-core epilogue, and keeps the MMAs at full rate).
+                            # A direct first layer without Gram statistics (RGB input) uses `out` as the scratch copy: the
+                            # stencil is recomputed with the final constants below.
+                            y_stat = y_raw if y_raw is not None else out
+                            conv(_fwd_ep(shift=bias), y_stat)
+                            L.check(lib.yg_bn_stats(y_stat.data_ptr(), dcode, N, ho * wo, blk.cout, stats.data_ptr(), st))
                         L.check(lib.yg_bn_finalize(stats.data_ptr(), float(N * ho * wo), g.data_ptr(), b.data_ptr(),
                                                    bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                                    float(bn.momentum), float(bn.eps), mean.data_ptr(),
@@ -306,6 +310,7 @@ class Runner:
         return outp, (saved if want_grad else None)
 
     # ---------------------------------------------------------------- backward
+    @L.on_device(lambda self, saved, dpred: dpred)
     def backward(self, saved, dpred: torch.Tensor) -> List[Optional[torch.Tensor]]:
         own = self.owner
         lib = L.lib()

@@ -16,6 +16,7 @@ from .. import _lib as L
 BoxFormat = Literal["xyxy", "cxcywh"]
 
 
+@L.on_device(lambda preds, *a, **k: preds)
 def format_preds_batch(
     preds: torch.Tensor,
     obj_thresh: float = 0.5,
@@ -78,6 +79,7 @@ def split_formatted(rows: torch.Tensor, keep_count: torch.Tensor) -> List[torch.
     return [rows[b, :n] for b, n in enumerate(counts)]
 
 
+@L.on_device(lambda labels_xyxy, preds_xyxy: preds_xyxy)
 def box_iou_cost(labels_xyxy: torch.Tensor, preds_xyxy: torch.Tensor) -> torch.Tensor:
     """(N, >=4) label rows and (M, >=4) prediction rows whose first four columns are xyxy -> (N, M) fp32 matrix
     ``1 - torchvision.ops.box_iou(labels, preds)`` (prediction_formatting.py:296-298), one launch, bit-identical."""

@@ -65,6 +65,7 @@ class _LazyFloats(dict):
 
 class _LossFunction(torch.autograd.Function):
     @staticmethod
+    @L.on_device(lambda ctx, pred, *a: pred)
     def forward(ctx, pred, label, weights, out4_holder):
         lib = L.lib()
         N, D, Sy, Sx = pred.shape
