@@ -977,6 +977,72 @@ def test_conv_outputs_stay_inside_their_buffers(shape):
     assert bool(torch.isfinite(dx.float()).all()) and bool(torch.isfinite(dw).all())
 
 
+FULL_LAYERS = [
+    # (N, H, W, Cin, Cout, stride): every 3x3 layer of base_model / double_filters at the 772x1032 geometry
+    (3, 386, 516, 16, 32, 1), (3, 386, 516, 32, 64, 2), (3, 193, 258, 64, 128, 1), (3, 193, 258, 128, 128, 2),
+    (5, 97, 129, 128, 128, 1),
+    (2, 386, 516, 32, 64, 1), (2, 386, 516, 64, 128, 2), (2, 193, 258, 128, 256, 1), (2, 193, 258, 256, 256, 2),
+    (3, 97, 129, 256, 256, 1),
+]
+
+
+@pytest.mark.parametrize("shape", FULL_LAYERS)
+def test_full_geometry_layers_tcgen05_equals_simt(shape):
+    """The tcgen05 kernels at the benchmark geometry (many tiles per CTA, accumulators in rotation, W-fold, CTA pairs,
+    parity classes with 97x129 / 193x258 tails, N = 256) against the straightforward SIMT kernels on the same bf16
+    inputs: both accumulate in fp32, so outputs agree up to the accumulation order (one bf16 ulp on a few elements)."""
+    import ctypes as C
+    N, H, W, Cin, Cout, s = shape
+    lib = L.lib()
+    g = torch.Generator(device=DEV).manual_seed(sum(shape))
+    dt = torch.bfloat16
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+    x = torch.randn(N, H, W, Cin, device=DEV, generator=g).to(dt)
+    # weights representable in bf16: the tcgen05 path packs them to bf16 (as autocast does), the SIMT path reads fp32
+    w = (torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / (Cin * 9) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, device=DEV, generator=g) * 0.1
+    keep = ((torch.rand(N, Cout, device=DEV, generator=g) > 0.15).float() / 0.85).contiguous()
+    keep_in = ((torch.rand(N, Cin, device=DEV, generator=g) > 0.15).float() / 0.85).contiguous()
+    dz = torch.randn(N, Ho, Wo, Cout, device=DEV, generator=g).to(dt)
+    res = {}
+    for impl in ("simt", "auto"):
+        L.set_conv_impl(impl)
+        try:
+            y = torch.empty(N, Ho, Wo, Cout, device=DEV, dtype=dt)
+            mask = torch.zeros(N * Ho * Wo * Cout // 8, dtype=torch.uint8, device=DEV)
+            ep = L.FwdEpilogue(None, b.data_ptr(), L.ACT_LRELU, keep.data_ptr(), None, None, mask.data_ptr())
+            L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(ep), L.stream()))
+            dx = torch.empty(N, H, W, Cin, device=DEV, dtype=dt)
+            be = L.BwdEpilogue(x.data_ptr(), L.ACT_LRELU, keep_in.data_ptr(), None, None, None, None, None, None)
+            L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(be), L.stream()))
+            dw = torch.empty_like(w)
+            db = torch.empty_like(b)
+            nb = lib.yg_conv_wgrad_workspace(N, H, W, Cin, Cout, 3, s)
+            ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
+            L.check(lib.yg_conv_wgrad(x.data_ptr(), dz.data_ptr(), dw.data_ptr(), db.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, 0.0,
+                                      ws.data_ptr(), nb, L.stream()))
+            torch.cuda.synchronize()
+            res[impl] = (y.float(), dx.float(), dw, db, mask)
+        finally:
+            L.set_conv_impl("auto")
+    (y0, dx0, dw0, db0, m0), (y1, dx1, dw1, db1, m1) = res["simt"], res["auto"]
+
+    def close(a, b_, what):
+        # bf16 outputs: every element within one bf16 ulp (2^-7 relative at worst) of the SIMT result - the fp32 accumulation
+        # order and the order of the epilogue's roundings differ - plus the fp32 noise of cancelling sums near zero
+        d = (a - b_).abs()
+        rms = float(b_.pow(2).mean().sqrt())
+        viol = d > (2.0 ** -7) * torch.maximum(a.abs(), b_.abs()) + 1e-5 * rms
+        assert int(viol.sum()) == 0, (what, int(viol.sum()), float(d.max()))
+        assert float(torch.linalg.vector_norm(d) / torch.linalg.vector_norm(b_)) < 2e-3, what
+
+    close(y1, y0, "fwd")
+    close(dx1, dx0, "dgrad")
+    assert float((dw1 - dw0).norm() / dw0.norm()) < 2e-5 and float((db1 - db0).norm() / db0.norm()) < 2e-5
+    # sign masks may differ only where the activation input is within rounding of zero
+    assert float((m0 != m1).float().mean()) < 1e-3
+
+
 def test_conv_tensors_larger_than_4GiB():
     """Index arithmetic beyond 2^32 bytes (double_filters at batch >= 168, base_model at batch 256 x 2 maps): a 32 -> 64
     stride-1 conv whose bf16 output is 4.4 GB.  Forward and dgrad are compared at sampled pixels (the last image sits
