@@ -121,3 +121,43 @@ def test_registry_and_plan_compiler():
         engine.compile_plan(nn.Sequential(nn.Sequential(nn.Conv2d(1, 8, 5, padding=2)), nn.Conv2d(8, 12, 1)))
     with pytest.raises(NotImplementedError):
         engine.compile_plan(nn.Sequential(nn.Sequential(nn.Conv2d(1, 8, 3, padding=1), nn.ReLU()), nn.Conv2d(8, 12, 1)))
+
+
+def test_trainer_optimizer_state_round_trip(tmp_path):
+    """DataParallelTrainer.state_dict / checkpoint: the reference's checkpoint dict (train.py:266-293) with an
+    optimizer_state_dict that torch.optim.AdamW itself accepts; a resumed trainer continues the moments and the schedule."""
+    import yogo_b200
+    from yogo_b200.train import DataParallelTrainer
+
+    torch.manual_seed(0)
+    net = yogo_b200.YOGO((64, 96), 0.05, 0.05, 7)
+    tr = DataParallelTrainer(net, total_steps=100)
+    tr.exp_avg.normal_()
+    tr.exp_avg_sq.uniform_(0, 1)
+    tr.step_count = 7
+    path = tmp_path / "ckpt.pth"
+    tr.checkpoint(path, "base_model", epoch=3, classes=["a"] * 7)
+    ck = torch.load(path, weights_only=False)
+    assert {"epoch", "step", "normalize_images", "classes", "model_name", "model_state_dict", "optimizer_state_dict",
+            "model_version"} <= set(ck)
+    assert ck["step"] == 7 and ck["epoch"] == 3
+    # torch's own optimizer loads it and sees the same moments, parameter by parameter
+    opt = torch.optim.AdamW(net.parameters(), lr=3e-4, weight_decay=5e-2)
+    opt.load_state_dict(ck["optimizer_state_dict"])
+    for p in net.parameters():
+        o, k = tr.offsets[id(p)]
+        assert torch.equal(opt.state[p]["exp_avg"].reshape(-1), tr.exp_avg[o:o + k])
+        assert float(opt.state[p]["step"]) == 7.0
+    assert abs(opt.param_groups[0]["lr"] - tr.lr_at(7)) < 1e-12
+    # and the other direction: a state dict produced by torch.optim.AdamW resumes a fresh trainer
+    net2, _ = yogo_b200.YOGO.from_pth(path)
+    tr2 = DataParallelTrainer(net2, total_steps=100)
+    tr2.load_optimizer_state_dict(opt.state_dict())
+    assert tr2.step_count == 7
+    for p, p2 in zip(net.parameters(), net2.parameters()):
+        (o, k), (o2, k2) = tr.offsets[id(p)], tr2.offsets[id(p2)]
+        assert torch.equal(tr.exp_avg_sq[o:o + k], tr2.exp_avg_sq[o2:o2 + k2])
+    # parameters that stop aliasing the flat buffer are detected
+    net2.model[0][0].weight.data = net2.model[0][0].weight.data.clone()
+    with pytest.raises(RuntimeError, match="no longer aliases"):
+        tr2._check_views()

@@ -1128,3 +1128,17 @@ def test_small_channel_wgrad_on_mma_sync_matches_autograd(shape):
         assert _rel(dw.cpu(), wr.grad) < 1e-4 and _rel(db.cpu(), br.grad) < 1e-4
     finally:
         lib.yg_set_tc_options(25 + 8192 + 16384)
+
+
+def test_multi_rank_equivalence(tmp_path):
+    """tests/ddp_gpu_check.py under torchrun on 2 GPUs (skipped on single-GPU boxes; its log from a 2-GPU gpurun is kept
+    under profiles/)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "ddp_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ddp_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

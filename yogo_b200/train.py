@@ -56,6 +56,7 @@ class DataParallelTrainer:
         self.overlap = overlap
         self.step_count = 0
         self._graph = None
+        self._graphs, self._graph_losses, self._static = [], [], []
 
         runner = net._get_runner()
         params = [p for p in runner.plan.params if p.requires_grad]
@@ -142,8 +143,6 @@ class DataParallelTrainer:
                 dist.broadcast(b, src, group=self.pg)
 
     def _on_grad_ready(self, p) -> None:
-        if getattr(self, "_defer_allreduce", False):
-            return   # CUDA-graph mode with several ranks: one all-reduce of the whole flat buffer after the replay
         bi = self.bucket_of.get(id(p))
         if bi is None:
             return
@@ -152,9 +151,12 @@ class DataParallelTrainer:
             self._launch_bucket(bi)
 
     def _launch_bucket(self, bi: int) -> None:
+        """All-reduce one complete bucket on the side stream while the remaining dgrad / wgrad kernels run on the main
+        stream.  Only stream/event dependencies are used, so the same code runs eagerly and under CUDA-graph capture
+        (the side stream joins the capture through the event wait; NCCL collectives are capturable)."""
         s, e = self.buckets[bi]
-        cur = torch.cuda.current_stream() if self.comm_stream is not None else None
         if self.overlap and self.comm_stream is not None:
+            cur = torch.cuda.current_stream()
             ev = torch.cuda.Event()
             ev.record(cur)
             self.comm_stream.wait_event(ev)
@@ -187,8 +189,23 @@ class DataParallelTrainer:
                 cur.wait_event(ev)
         return loss
 
+    def _check_views(self) -> None:
+        """`net.to()`, `.half()` or `load_state_dict(assign=True)` after construction re-allocate parameters; AdamW would
+        then update a buffer the model no longer reads.  Cheap (one pointer compare per tensor), checked every step."""
+        base = self.flat_p.data_ptr()
+        for p in self.params:
+            o, _ = self.offsets[id(p)]
+            if p.data_ptr() != base + 4 * o:
+                raise RuntimeError("DataParallelTrainer: a parameter no longer aliases the flat parameter buffer (the model "
+                                   "was moved / cast / re-assigned after the trainer was built); build a new trainer")
+
     def optimizer_step(self) -> None:
         self.step_count += 1
+        b1, b2 = self.betas
+        with torch.cuda.device(self.flat_p.device):
+            self._adamw_host()
+
+    def _adamw_host(self) -> None:
         b1, b2 = self.betas
         L.check(L.lib().yg_adamw_flat(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
                                       self.exp_avg_sq.data_ptr(), self.numel, self.lr_at(self.step_count - 1),
@@ -196,8 +213,10 @@ class DataParallelTrainer:
 
     def step(self, imgs: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """zero_grad is implicit: every gradient view is overwritten by its kernel each step."""
-        if self._graph is not None:
+        self._check_views()
+        if self._graph is not None and imgs.shape == self._static_imgs.shape and labels.shape == self._static_labels.shape:
             return self._graph_step(imgs, labels)
+        # eager path (also the ragged last batch of an epoch when a graph of the full batch shape is active)
         loss = self.forward_backward(imgs, labels)
         self.optimizer_step()
         return loss
@@ -208,31 +227,29 @@ class DataParallelTrainer:
         return torch.tensor([self.lr_at(step_count - 1), b1, b2, self.eps, self.wd, 1.0 - b1 ** step_count,
                              math.sqrt(1.0 - b2 ** step_count), 1.0 / self.world], dtype=torch.float32)
 
-    def enable_cuda_graph(self, imgs: torch.Tensor, labels: torch.Tensor, warmup: int = 2) -> None:
-        """Capture forward + loss + backward (+ all-reduce) + AdamW for this input shape into one CUDA graph;
+    def enable_cuda_graph(self, imgs: torch.Tensor, labels: torch.Tensor, warmup: int = 2, slots: int = 1) -> None:
+        """Capture forward + loss + backward (+ bucketed all-reduces) + AdamW for this input shape into one CUDA graph;
         afterwards `step` copies the batch into static buffers and replays it (launch-bound inner loop:
-        ~350 kernel launches and their host-side argument marshalling collapse into one graph launch)."""
+        ~350 kernel launches and their host-side argument marshalling collapse into one graph launch).
+
+        `slots` > 1 captures one graph per static input buffer set (sharing one memory pool, they never run
+        concurrently): `steps_from_host` then copies host batch i+1 straight into the idle slot while the graph of the
+        other slot runs, so no device-to-device staging copy is needed."""
         dev = imgs.device
-        self._static_imgs = imgs.clone()
-        self._static_labels = labels.clone()
+        self._static = [(imgs.clone(), labels.clone()) for _ in range(max(1, slots))]
+        self._static_imgs, self._static_labels = self._static[0]
         self._hyper = torch.zeros(8, dtype=torch.float32, device=dev)
 
-        # several ranks: the graph holds forward + loss + backward only; the gradient all-reduce (one NCCL call on the whole
-        # 2 MB flat buffer, a few tens of microseconds over NVLink) and the fused AdamW follow the replay on the same stream,
-        # so no collective is ever captured
-        self._graph_has_optimizer = self.world == 1
-        self._defer_allreduce = self.world > 1
-
-        def body():
-            loss = self.forward_backward(self._static_imgs, self._static_labels)
-            if self._graph_has_optimizer:
-                self._adamw_dev()
+        def body(slot=0):
+            loss = self.forward_backward(*self._static[slot])
+            self._adamw_dev()
             return loss
 
-        # warm-up on a side stream (allocator pools, library caches), with a learning rate of zero so that the
-        # parameters and optimizer state are not disturbed ... they are: so snapshot and restore instead
+        # warm-up on a side stream (allocator pools, NCCL communicator and channel setup, library caches); parameters,
+        # optimizer state, module buffers and the CUDA RNG stream (Dropout2d masks) are restored afterwards
         snap = (self.flat_p.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
-                [b.clone() for b in self.net.buffers()])
+                [b.clone() for b in self.net.buffers()], self.flat_g.clone())
+        rng = torch.cuda.get_rng_state(dev)
         self._hyper.copy_(self._hyper_host(1))
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream())
@@ -241,31 +258,161 @@ class DataParallelTrainer:
                 body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        n0 = L.load().yg_launch_count()
-        with torch.cuda.graph(graph):
-            self._graph_loss = body()
-        self.graph_launches = int(L.load().yg_launch_count() - n0)  # our kernels inside one replay
-        self.flat_p.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2])
+        # several ranks: the per-bucket NCCL all-reduces are captured on the side stream (fork / join through events), so
+        # one replay runs backward with the communication overlapped and the fused AdamW behind it.  NCCL's watchdog
+        # thread polls events of earlier collectives, which a capture in "global" mode would reject: thread-local mode.
+        mode = "thread_local" if self.world > 1 else "global"
+        self._graphs, self._graph_losses, pool = [], [], None
+        for slot in range(len(self._static)):
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.load().yg_launch_count()
+            with torch.cuda.graph(graph, pool=pool, capture_error_mode=mode):
+                loss = body(slot)
+            self.graph_launches = int(L.load().yg_launch_count() - n0)  # our kernels inside one replay
+            pool = graph.pool()
+            self._graphs.append(graph)
+            self._graph_losses.append(loss)
+        self.flat_p.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2]); self.flat_g.copy_(snap[4])
         for b, v in zip(self.net.buffers(), snap[3]):
             b.copy_(v)
+        torch.cuda.set_rng_state(rng, dev)
         torch.cuda.synchronize()
-        self._graph = graph
+        self._graph = self._graphs[0]
+
+    def disable_cuda_graph(self) -> None:
+        """Drop the captured graphs (before `destroy_process_group`: they hold captured NCCL work)."""
+        self._graph = None
+        self._graphs, self._graph_losses = [], []
+        torch.cuda.synchronize()
 
     def _adamw_dev(self) -> None:
+        # current stream has already joined the side stream (forward_backward waits on the bucket events)
         L.check(L.lib().yg_adamw_flat_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), self.numel, self._hyper.data_ptr(), L.stream()))
 
     def _graph_step(self, imgs: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        self.step_count += 1
-        self._hyper.copy_(self._hyper_host(self.step_count))  # 32 bytes from pageable memory: staged, race-free
         self._static_imgs.copy_(imgs, non_blocking=True)
         self._static_labels.copy_(labels, non_blocking=True)
-        self._graph.replay()
-        if not self._graph_has_optimizer:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-            self._adamw_dev()
-        return self._graph_loss
+        return self.step_static(0)
+
+    def step_static(self, slot: int = 0) -> torch.Tensor:
+        """Replay the graph of `slot` on whatever its static input buffers (`static_inputs(slot)`) hold."""
+        self.step_count += 1
+        self._hyper.copy_(self._hyper_host(self.step_count))  # 32 bytes from pageable memory: staged, race-free
+        self._graphs[slot].replay()
+        return self._graph_losses[slot].clone()   # callers may keep losses across steps; the graph's tensor is overwritten
+
+    def static_inputs(self, slot: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._static[slot]
+
+    def steps_from_host(self, batches):
+        """Generator: one training step per pinned host batch `(images, labels)`, yielding the loss tensor.  In graph mode
+        batch i+1 is copied host->device straight into the idle static slot on a copy stream while step i replays (the
+        reference's `pin_memory` + `non_blocking` loader pattern, train.py:288-291, without a staging copy); otherwise it
+        falls back to `DevicePrefetcher` + `step`."""
+        if self._graph is None:
+            for x, y in DevicePrefetcher(batches, self.flat_p.device):
+                yield self.step(x, y)
+            return
+        dev = self.flat_p.device
+        nslot = len(self._static)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy = self._copy_stream
+        cur = torch.cuda.current_stream(dev)
+        free_ev = [None] * nslot
+        ready_ev = [None] * nslot
+
+        def issue(slot, batch):
+            with torch.cuda.stream(copy):
+                if free_ev[slot] is not None:
+                    copy.wait_event(free_ev[slot])      # the replay that last read this slot has finished
+                self._static[slot][0].copy_(batch[0], non_blocking=True)
+                self._static[slot][1].copy_(batch[1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                ready_ev[slot] = ev
+
+        it = iter(batches)
+        nxt = next(it, None)
+        slot = 0
+        if nxt is not None:
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+            free_ev = [ev0] * nslot                     # earlier work on the main stream may still read the slots
+            issue(0, nxt)
+        while nxt is not None:
+            nxt2 = next(it, None)
+            if nxt2 is not None and nslot > 1:
+                issue((slot + 1) % nslot, nxt2)         # overlaps with the replay below
+            cur.wait_event(ready_ev[slot])
+            loss = self.step_static(slot)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            free_ev[slot] = ev
+            if nxt2 is not None and nslot == 1:
+                issue(0, nxt2)
+            yield loss
+            nxt = nxt2
+            slot = (slot + 1) % nslot
+
+    # ------------------------------------------------------------------ checkpoint state (train.py:262-293)
+    def optimizer_state_dict(self) -> Dict:
+        """`torch.optim.AdamW.state_dict()` layout (what the reference stores under "optimizer_state_dict"): per-parameter
+        `step` / `exp_avg` / `exp_avg_sq` in `net.parameters()` order, one param group with the current learning rate."""
+        params = list(self.net.parameters())
+        state = {}
+        for i, p in enumerate(params):
+            if id(p) not in self.offsets:
+                continue
+            o, k = self.offsets[id(p)]
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[o:o + k].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + k].view_as(p).clone()}
+        group = {"lr": self.lr_at(self.step_count), "betas": self.betas, "eps": self.eps, "weight_decay": self.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "initial_lr": self.lr0, "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: Dict) -> None:
+        params = list(self.net.parameters())
+        steps = set()
+        with torch.no_grad():
+            for i, st in sd["state"].items():
+                p = params[int(i)]
+                if id(p) not in self.offsets:
+                    continue
+                o, k = self.offsets[id(p)]
+                self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}); the fused AdamW keeps one")
+        if steps:
+            self.step_count = steps.pop()   # drives the bias correction and the cosine schedule
+
+    def state_dict(self) -> Dict:
+        return {"step": self.step_count, "total_steps": self.total_steps,
+                "optimizer_state_dict": self.optimizer_state_dict()}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.load_optimizer_state_dict(sd["optimizer_state_dict"])
+        if "step" in sd:
+            self.step_count = int(sd["step"])
+
+    def checkpoint(self, filename, model_name: str, epoch: int = 0, normalize_images: bool = False, classes=None,
+                   **kwargs) -> None:
+        """The reference's checkpoint dict (train.py:266-293), loadable by `YOGO.from_pth` of either implementation and by
+        `torch.optim.AdamW.load_state_dict`.  BN running statistics of rank 0 are broadcast first (the per-step buffer
+        broadcast of DDP, done on demand)."""
+        self.sync_bn_buffers()
+        if self.world > 1 and dist.get_rank(self.pg) != 0:
+            return
+        torch.save({"epoch": epoch, "step": self.step_count, "normalize_images": normalize_images, "classes": classes,
+                    "model_name": model_name,
+                    "model_state_dict": {k: v.detach().clone() for k, v in self.net.state_dict().items()},
+                    "optimizer_state_dict": self.optimizer_state_dict(),
+                    "model_version": getattr(self.net, "model_version", None), **kwargs}, str(filename))
 
 
 class DevicePrefetcher:
