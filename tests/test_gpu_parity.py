@@ -114,6 +114,47 @@ def test_format_preds_reference_known_answers():
     assert yogo_b200.format_preds(two).shape[0] == 2
 
 
+@pytest.mark.parametrize("thr", [0.5, 1.0 / 3.0, 0.3, 0.25])
+def test_nms_pairs_sitting_on_the_iou_threshold(thr):
+    """The suppression masks decide most pairs without the IEEE division (two fp32 products against thresholds a hair
+    below / above); pairs inside that sliver take the exact quotient path.  Boxes on a lattice - equal sizes, shifts of
+    1/3, 1/2, 3/5 of the width - put hundreds of pairs at IoU = 1/2, 1/3, 1/4 up to rounding noise, where the fp32 quotient
+    lands on either side of the threshold: results must still equal the oracle (torchvision CPU semantics) bit for bit."""
+    g = torch.Generator().manual_seed(int(thr * 1000))
+    B, C, Sy, Sx = 3, 7, 24, 32
+    p = torch.zeros(B, 5 + C, Sy, Sx)
+    jj, ii = torch.meshgrid(torch.arange(Sy), torch.arange(Sx), indexing="ij")
+    w = 0.06
+    for b in range(B):
+        frac = [1.0 / 3.0, 0.5, 0.6][b]
+        # neighbouring cells hold the same box shifted by `frac` of its width: IoU = (1 - frac) / (1 + frac) = 1/2, 1/3, 1/4
+        p[b, 0] = 0.1 + (ii.float() * frac * w) % 0.8
+        p[b, 1] = 0.1 + 0.03 * (jj % 3).float() + 0.2 * (jj // 3).float() / 8
+        p[b, 2] = w
+        p[b, 3] = 0.05
+        p[b, 4] = 0.55 + 0.4 * torch.rand(Sy, Sx, generator=g)
+        p[b, 5:] = torch.softmax(3 * torch.randn(C, Sy, Sx, generator=g), dim=0)
+    import torchvision.ops as ops
+    rows, kc, kidx, counts = yogo_b200.format_preds_batch(p.to(DEV), 0.5, thr)
+    tot = np.zeros(C, np.int64)
+    near = 0
+    for b in range(B):
+        exp = O.format_preds_np(p[b].numpy(), 0.5, thr)
+        assert int(kc[b]) == exp.shape[0], (b, int(kc[b]), exp.shape[0])
+        assert np.array_equal(rows[b, : exp.shape[0]].cpu().numpy().view(np.uint32), exp.view(np.uint32))
+        tot += O.count_cells_np(exp[:, 5:])
+        # the installed torchvision CPU kernel itself, on the same candidates
+        pb = p[b].reshape(5 + C, -1).T
+        m = pb[:, 4] > 0.5
+        c = pb[m]
+        boxes = ops.box_convert(c[:, :4], "cxcywh", "xyxy")
+        keep = ops.nms(boxes, c[:, 5:].max(1).values * c[:, 4], thr)
+        assert np.array_equal(kidx[b, : int(kc[b])].cpu().numpy(), torch.nonzero(m)[:, 0][keep].numpy())
+        near += int(((ops.box_iou(boxes, boxes) - thr).abs() < 1e-6).sum())
+    assert np.array_equal(counts.cpu().numpy(), tot)
+    assert near > 100 or thr == 0.3   # the fixture really has pairs on the threshold (1/2, 1/3, 1/4)
+
+
 @pytest.mark.parametrize("K,B", [(50, 8), (300, 8), (1000, 4)])
 def test_format_preds_full_size_sparse_vs_oracle(K, B):
     p = O.synth_sparse_preds(B, K=K, seed=100 + K)
@@ -1142,3 +1183,25 @@ def test_multi_rank_equivalence(tmp_path):
                         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "ddp_gpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ddp_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_graphed_inference_equals_eager():
+    """yogo_b200.infer.GraphedInference: forward + threshold + NMS + counts replayed from one CUDA graph gives exactly
+    the eager results, for successive different batches."""
+    from yogo_b200.infer import GraphedInference
+    torch.manual_seed(0)
+    net = yogo_b200.YOGO((196, 260), O.ANCHOR_W, O.ANCHOR_H, 7, inference=True).to(DEV)
+    with torch.no_grad():
+        net.model[-1].weight.mul_(0.3)
+    net.eval()
+    gi = GraphedInference(net, (3, 1, 196, 260))
+    for seed in (1, 2, 3):
+        img = O.synth_images(3, 196, 260, seed=seed).to(DEV)
+        pred, rows, kc, kidx, counts = gi(img)
+        with torch.no_grad():
+            ref = net(img)
+        r2, kc2, kidx2, counts2 = yogo_b200.format_preds_batch(ref)
+        assert torch.equal(pred, ref) and torch.equal(kc, kc2) and torch.equal(counts, counts2)
+        for b in range(3):
+            n = int(kc[b])
+            assert torch.equal(rows[b, :n], r2[b, :n]) and torch.equal(kidx[b, :n], kidx2[b, :n])
