@@ -559,8 +559,71 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 constexpr int FM_WARPS = 4;
 
+// Row segments: a warp works on 32 consecutive output pixels of ONE output row (lane = pixel), so the input row
+// pointers and the row-validity tests are warp-uniform, and with stride 2 and an even image width each lane fetches its
+// centre / right tap of a row as one aligned 16-bit load (a fully coalesced 64-byte warp request) and takes the left tap
+// from its neighbour's register: 3 loads + 3 shuffles per pixel instead of 9 predicated byte loads with per-lane
+// address arithmetic (ncu: the byte-load version issued 175-270 instructions per 32 pixels and was issue-bound).
+struct SegCursor {
+  int ho, sg;   // output row, segment inside the row
+  __device__ __forceinline__ void init(int s, int spr) { ho = s / spr; sg = s - ho * spr; }
+  __device__ __forceinline__ void advance(int step, int spr) {
+    sg += step;
+    while (sg >= spr) { sg -= spr; ++ho; }
+  }
+};
+
+// Raw taps of one pixel as they come from memory: requested one iteration ahead (fetch), turned into the nine floats
+// only when the pixel is processed (unpack) - the shuffles of the fast path would otherwise wait for the loads at once.
+template <bool FAST> struct TapRaw;
+template <> struct TapRaw<true> { unsigned cr[3], lf[3]; };   // per input row: centre | right << 8; left tap of lane 0
+template <> struct TapRaw<false> { float v[9]; };
+
+__device__ __forceinline__ void fetch_taps(TapRaw<true>& t, const uint8_t* __restrict__ xim, int H, int W, int stride, int ho,
+                                           int wo, bool pv, int lane) {
+  (void)stride;
+  // one address per pixel (row 2 ho - 1, column 2 wo), the other two rows are W and 2 W bytes further; the row tests are
+  // warp-uniform, the left tap of lane 0 sits one byte before its centre tap
+  const int ih0 = 2 * ho - 1;
+  const uint8_t* p = xim + ((long long)ih0 * W + 2 * wo);
+  const bool lf = lane == 0 && wo > 0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const bool ok = pv && (unsigned)(ih0 + r) < (unsigned)H;
+    t.cr[r] = 0u;                                          // (W even: column 2 wo + 1 exists whenever wo < Wo)
+    t.lf[r] = 0u;
+    if (ok) t.cr[r] = __ldg(reinterpret_cast<const unsigned short*>(p));
+    if (ok && lf) t.lf[r] = __ldg(p - 1);
+    p += W;
+  }
+}
+__device__ __forceinline__ void fetch_taps(TapRaw<false>& t, const uint8_t* __restrict__ xim, int H, int W, int stride, int ho,
+                                           int wo, bool pv, int lane) {
+  (void)lane;
+  if (pv) load_taps1<uint8_t>(xim, H, W, stride, ho, wo, t.v);
+  else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t.v[i] = 0.f;
+  }
+}
+__device__ __forceinline__ void unpack_taps(const TapRaw<true>& t, bool pv, int lane, float (&v)[9]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    unsigned left = __shfl_up_sync(0xffffffffu, t.cr[r] >> 8, 1);
+    if (lane == 0) left = t.lf[r];
+    v[3 * r] = pv ? (float)left : 0.f;   // (an invalid lane next to a valid one would inherit its neighbour's byte)
+    v[3 * r + 1] = (float)(t.cr[r] & 0xFFu);
+    v[3 * r + 2] = (float)(t.cr[r] >> 8);
+  }
+}
+__device__ __forceinline__ void unpack_taps(const TapRaw<false>& t, bool pv, int lane, float (&v)[9]) {
+  (void)pv; (void)lane;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) v[i] = t.v[i];
+}
+
 // NM = number of 16-channel M tiles (Cout = 16 NM): the X tile and its two B fragments are shared by all of them
-template <int NM>
+template <int NM, bool FAST>
 __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 5 : (NM == 2 ? 4 : 3)) first_bwd_mma_kernel(
     const uint8_t* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ da, int H, int W, int Ho, int Wo,
     int stride, BwdEpi be, const float* __restrict__ fwd_shift, float* __restrict__ partial, int chunk, int cpi, int ntasks) {
@@ -616,9 +679,10 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 5 : (NM == 2 ? 4 : 3)
   auto row_addr = [](uint32_t base, int px, int half) { return base + (uint32_t)(px * 32 + ((half ^ ((px >> 2) & 1)) << 4)); };
   __syncthreads();
   const int npix = Ho * Wo;
+  const int spr = (Wo + 31) >> 5, nseg = Ho * spr;   // 32-pixel segments per output row / per image
   for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
-    const int p1 = min(p0 + chunk, npix);
+    const int n = task / cpi, s0 = (task - n * cpi) * chunk;
+    const int s1 = min(s0 + chunk, nseg);
     if (be.dropscale) {
 #pragma unroll
       for (int m = 0; m < NM; ++m) {
@@ -628,40 +692,42 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 5 : (NM == 2 ? 4 : 3)
     }
     const uint8_t* xim = x + (long long)n * H * W;
     const bf16* dim = da + (long long)n * npix * CO;
-    PixCursor cur;
-    cur.init(p0 + warp * 32 + lane, Wo);
+    SegCursor cur;
+    cur.init(s0 + warp, spr);
     // software pipeline: the taps and the gradient row of the NEXT 32 pixels are requested before this iteration's tile is
     // staged and multiplied, so their HBM latency overlaps the ldmatrix / mma chain instead of heading it
-    float vn[9];
+    TapRaw<FAST> tn;
+    bool pvn = false;
     uint4 dn[2 * NM];
-    auto fetch = [&](const PixCursor& c) {
+    auto fetch = [&](const SegCursor& c) {
+      const int wo = c.sg * 32 + lane;
+      const bool pv = wo < Wo;
+      pvn = pv;
+      fetch_taps(tn, xim, H, W, stride, c.ho, wo, pv, lane);
 #pragma unroll
       for (int i = 0; i < 2 * NM; ++i) dn[i] = make_uint4(0, 0, 0, 0);
-      if (c.p < p1) {
-        load_taps1<uint8_t>(xim, H, W, stride, c.ho, c.wo, vn);
-        const uint4* gp = reinterpret_cast<const uint4*>(dim + (long long)c.p * CO);
+      if (pv) {
+        const uint4* gp = reinterpret_cast<const uint4*>(dim + ((long long)c.ho * Wo + wo) * CO);
 #pragma unroll
         for (int m = 0; m < NM; ++m)
           asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                        : "=r"(dn[2 * m].x), "=r"(dn[2 * m].y), "=r"(dn[2 * m].z), "=r"(dn[2 * m].w), "=r"(dn[2 * m + 1].x),
                          "=r"(dn[2 * m + 1].y), "=r"(dn[2 * m + 1].z), "=r"(dn[2 * m + 1].w) : "l"(gp + 2 * m));
-      } else {
-#pragma unroll
-        for (int t = 0; t < 9; ++t) vn[t] = 0.f;
       }
     };
-    if (p0 + warp * 32 < p1) fetch(cur);
-    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32) {
+    if (s0 + warp < s1) fetch(cur);
+    for (int sb = s0 + warp; sb < s1; sb += FM_WARPS) {
       // ---- stage the 32 pixels of this warp: thread = pixel
       {
         float v[9];
         uint4 d[2 * NM];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) v[t] = vn[t];
+        const TapRaw<FAST> tc = tn;
+        const bool pvc = pvn;
 #pragma unroll
         for (int i = 0; i < 2 * NM; ++i) d[i] = dn[i];
-        cur.advance(FM_WARPS * 32, Wo);
-        if (pb + FM_WARPS * 32 < p1) fetch(cur);
+        cur.advance(FM_WARPS, spr);
+        if (sb + FM_WARPS < s1) fetch(cur);
+        unpack_taps(tc, pvc, lane, v);
         const uint4 x0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         const uint4 x1 = make_uint4(pack_bf16(v[8], 1.f), 0u, 0u, 0u);   // tap 8, the ones column, zero padding
         const int sw = (lane >> 2) & 1;
@@ -752,7 +818,7 @@ __device__ __forceinline__ void stage_taps_tile(unsigned char* xt, int lane, con
   *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ sw) << 4)) = x1;
 }
 
-template <int NM>
+template <int NM, bool FAST>
 __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 6) first_fwd_mma_kernel(
     const uint8_t* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int H, int W, int Ho, int Wo,
     int stride, FwdEpi ep, int chunk, int cpi, int ntasks) {
@@ -791,9 +857,10 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 6) first_fwd_mma_
   const int lm = lane >> 3, lr = lane & 7;
   auto row_addr = [](uint32_t base, int px, int half) { return base + (uint32_t)(px * 32 + ((half ^ ((px >> 2) & 1)) << 4)); };
   const int npix = Ho * Wo;
+  const int spr = (Wo + 31) >> 5, nseg = Ho * spr;
   for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
-    const int p1 = min(p0 + chunk, npix);
+    const int n = task / cpi, s0 = (task - n * cpi) * chunk;
+    const int s1 = min(s0 + chunk, nseg);
     if (ep.dropscale) {
 #pragma unroll
       for (int m = 0; m < NM; ++m) {
@@ -803,15 +870,20 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 6) first_fwd_mma_
     }
     const uint8_t* xim = x + (long long)n * H * W;
     bf16* yim = y + (long long)n * npix * CO;
-    PixCursor cur;
-    cur.init(p0 + warp * 32 + lane, Wo);
-    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
+    SegCursor cur, nxt;
+    cur.init(s0 + warp, spr);
+    nxt = cur;
+    TapRaw<FAST> tn;
+    if (s0 + warp < s1) fetch_taps(tn, xim, H, W, stride, cur.ho, cur.sg * 32 + lane, cur.sg * 32 + lane < Wo, lane);
+    for (int sb = s0 + warp; sb < s1; sb += FM_WARPS, cur = nxt) {
+      const int wo = cur.sg * 32 + lane;
+      const bool pv = wo < Wo;
+      const TapRaw<FAST> tc = tn;
+      nxt.advance(FM_WARPS, spr);
+      if (sb + FM_WARPS < s1)   // the next segment's taps are in flight while this one is multiplied and stored
+        fetch_taps(tn, xim, H, W, stride, nxt.ho, nxt.sg * 32 + lane, nxt.sg * 32 + lane < Wo, lane);
       float v[9];
-      if (cur.p < p1) load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
-      else {
-#pragma unroll
-        for (int t = 0; t < 9; ++t) v[t] = 0.f;
-      }
+      unpack_taps(tc, pv, lane, v);
       __syncwarp();
       stage_taps_tile(xt, lane, v);
       __syncwarp();
@@ -839,9 +911,9 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 6) first_fwd_mma_
         }
       }
       __syncwarp();
-      if (cur.p < p1) {
+      if (pv) {
         const int sw = (lane >> 2) & 1;
-        uint4* dst = reinterpret_cast<uint4*>(yim + (long long)cur.p * CO);
+        uint4* dst = reinterpret_cast<uint4*>(yim + ((long long)cur.ho * Wo + wo) * CO);
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
           const unsigned char* yt = tiles[warp][1 + m];
@@ -856,6 +928,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, NM == 1 ? 8 : 6) first_fwd_mma_
   }
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_gram_mma_kernel(const uint8_t* __restrict__ x, int H, int W, int Ho,
                                                                           int Wo, int stride, double* __restrict__ gram,
                                                                           int chunk, int cpi, int ntasks) {
@@ -883,24 +956,29 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_gram_mma_kernel(const 
       D0[e] = 0.f; D1[e] = 0.f;
     }
   };
-  const int npix = Ho * Wo;
+  const int spr = (Wo + 31) >> 5, nseg = Ho * spr;
   int since_flush = 0;
   for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    const int n = task / cpi, p0 = (task - n * cpi) * chunk;
-    const int p1 = min(p0 + chunk, npix);
+    const int n = task / cpi, s0 = (task - n * cpi) * chunk;
+    const int s1 = min(s0 + chunk, nseg);
     const uint8_t* xim = x + (long long)n * H * W;
-    PixCursor cur;
-    cur.init(p0 + warp * 32 + lane, Wo);
-    for (int pb = p0 + warp * 32; pb < p1; pb += FM_WARPS * 32, cur.advance(FM_WARPS * 32, Wo)) {
+    SegCursor cur, nxt;
+    cur.init(s0 + warp, spr);
+    nxt = cur;
+    TapRaw<FAST> tn;
+    if (s0 + warp < s1) fetch_taps(tn, xim, H, W, stride, cur.ho, cur.sg * 32 + lane, cur.sg * 32 + lane < Wo, lane);
+    for (int sb = s0 + warp; sb < s1; sb += FM_WARPS, cur = nxt) {
+      const int wo = cur.sg * 32 + lane;
+      const bool pv = wo < Wo;
+      const TapRaw<FAST> tc = tn;
+      nxt.advance(FM_WARPS, spr);
+      if (sb + FM_WARPS < s1)
+        fetch_taps(tn, xim, H, W, stride, nxt.ho, nxt.sg * 32 + lane, nxt.sg * 32 + lane < Wo, lane);
       float v[9];
-      if (cur.p < p1) load_taps1<uint8_t>(xim, H, W, stride, cur.ho, cur.wo, v);
-      else {
-#pragma unroll
-        for (int t = 0; t < 9; ++t) v[t] = 0.f;
-      }
+      unpack_taps(tc, pv, lane, v);
       __syncwarp();
       stage_taps_tile(xt, lane, v);
-      if (cur.p >= p1) *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ ((lane >> 2) & 1)) << 4)) = make_uint4(0, 0, 0, 0);   // no ones
+      if (!pv) *reinterpret_cast<uint4*>(xt + lane * 32 + ((1 ^ ((lane >> 2) & 1)) << 4)) = make_uint4(0, 0, 0, 0);   // no ones
       __syncwarp();
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
@@ -920,6 +998,11 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_gram_mma_kernel(const 
 }
 
 constexpr int FL_BWD_BLOCKS = 592;
+
+// aligned 16-bit tap loads: stride 2, even width (every row starts on an even offset) and an even base address
+static bool first_fast_taps(const void* x, int W, int stride) {
+  return stride == 2 && (W & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 1u) == 0;
+}
 
 }  // namespace yg
 
@@ -941,10 +1024,13 @@ extern "C" int yg_conv_first_fwd(const void* x, int x_dtype, const float* w, voi
       (long long)H * W < (1LL << 31) && x_dtype == YG_U8 && !ep.stats && y && (reinterpret_cast<uintptr_t>(y) & 31u) == 0 &&
       yg_get_conv_impl() != YG_IMPL_SIMT) {
     // warp-level tensor cores, one M tile per 16 output channels (base 16, double_filters 32, triple_filters 48)
-    const int chunkm = 16 * FM_WARPS * 32, cpim = cdiv((long long)Ho * Wo, chunkm), ntasksm = N * cpim;
+    // tasks of 16 row segments (32 pixels of one output row) per warp
+    const int chunkm = 16 * FM_WARPS, cpim = cdiv((long long)Ho * cdiv(Wo, 32), chunkm), ntasksm = N * cpim;
     const int per_sm = Cout == 16 ? 8 : 6;
     const int gridm = ntasksm < 148 * per_sm ? ntasksm : 148 * per_sm;
-#define LAUNCHM(NM) first_fwd_mma_kernel<NM><<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunkm, cpim, ntasksm)
+    const bool fast = first_fast_taps(x, W, stride);
+#define LAUNCHM(NM) do { if (fast) first_fwd_mma_kernel<NM, true><<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunkm, cpim, ntasksm); \
+                         else first_fwd_mma_kernel<NM, false><<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (bf16*)y, H, W, Ho, Wo, stride, ep, chunkm, cpim, ntasksm); } while (0)
     if (Cout == 16) LAUNCHM(1); else if (Cout == 32) LAUNCHM(2); else LAUNCHM(3);
 #undef LAUNCHM
     YG_LAUNCH_CHECK("conv_first_fwd_mma");
@@ -1003,9 +1089,11 @@ extern "C" int yg_conv_first_bwd(const void* x, int x_dtype, const float* w, con
       Wo >= 32 && (long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31) && (reinterpret_cast<uintptr_t>(da) & 31u) == 0 &&
       yg_get_conv_impl() != YG_IMPL_SIMT) {
     // raw P / Sg pass on the tensor cores (first_bwd_mma_kernel), one M tile per 16 output channels
-    const int chunk = 64 * FM_WARPS * 32, cpi = cdiv((long long)Ho * Wo, chunk), ntasks = N * cpi;
+    const int chunk = 64 * FM_WARPS, cpi = cdiv((long long)Ho * cdiv(Wo, 32), chunk), ntasks = N * cpi;
     const int grid1 = ntasks < FL_BWD_BLOCKS ? ntasks : FL_BWD_BLOCKS;
-#define LAUNCHM(NM) first_bwd_mma_kernel<NM><<<grid1, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be, fwd_shift, (float*)workspace, chunk, cpi, ntasks)
+    const bool fast = first_fast_taps(x, W, stride);
+#define LAUNCHM(NM) do { if (fast) first_bwd_mma_kernel<NM, true><<<grid1, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be, fwd_shift, (float*)workspace, chunk, cpi, ntasks); \
+                         else first_bwd_mma_kernel<NM, false><<<grid1, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, w, (const bf16*)da, H, W, Ho, Wo, stride, be, fwd_shift, (float*)workspace, chunk, cpi, ntasks); } while (0)
     if (Cout == 16) LAUNCHM(1); else if (Cout == 32) LAUNCHM(2); else LAUNCHM(3);
 #undef LAUNCHM
     YG_LAUNCH_CHECK("conv_first_bwd_mma");
@@ -1176,9 +1264,12 @@ extern "C" int yg_conv_first_gram(const void* x, int x_dtype, int N, int H, int 
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   YG_CHECK_ARG((long long)Ho * Wo < (1LL << 30) && (long long)H * W < (1LL << 31), "conv_first_gram: image too large");
   if (x_dtype == YG_U8 && yg_get_conv_impl() != YG_IMPL_SIMT) {
-    const int chunkm = 32 * FM_WARPS * 32, cpim = cdiv((long long)Ho * Wo, chunkm), ntasksm = N * cpim;
+    const int chunkm = 32 * FM_WARPS, cpim = cdiv((long long)Ho * cdiv(Wo, 32), chunkm), ntasksm = N * cpim;
     const int gridm = ntasksm < 148 * 8 ? ntasksm : 148 * 8;
-    first_gram_mma_kernel<<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, H, W, Ho, Wo, stride, gram, chunkm, cpim, ntasksm);
+    if (first_fast_taps(x, W, stride))
+      first_gram_mma_kernel<true><<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, H, W, Ho, Wo, stride, gram, chunkm, cpim, ntasksm);
+    else
+      first_gram_mma_kernel<false><<<gridm, FM_WARPS * 32, 0, st>>>((const uint8_t*)x, H, W, Ho, Wo, stride, gram, chunkm, cpim, ntasksm);
     YG_LAUNCH_CHECK("first_gram_mma");
     return YG_OK;
   }
