@@ -19,7 +19,6 @@ import argparse
 import json
 import os
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 import statistics
 import sys
 import threading
@@ -410,7 +409,7 @@ def run_ours(args):
     net.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     net.train()
     loss_fn = yogo_b200.YOGOLoss().to(dev)
-    trainer = DataParallelTrainer(net, loss_fn, total_steps=10000)
+    trainer = DataParallelTrainer(net, loss_fn, total_steps=10000, overlap=bool(args.overlap))
     trainer.broadcast_state()
     use_graph = bool(args.graph)
 
@@ -523,7 +522,8 @@ def run_ours(args):
                 "l2_policy": "inputs+activations per step (>3 GB) far exceed the 126 MB L2; batches alternate",
                 "conv_impl": L.get_conv_impl(), "cuda_graph": bool(use_graph),
                 "allreduce": "none (1 rank)" if world == 1 else
-                             f"{len(trainer.buckets)} NCCL bucket(s) on a side stream, overlapped with backward, captured in the step graph",
+                             (f"{len(trainer.buckets)} NCCL bucket(s) on a side stream, overlapped with backward, captured in the step graph"
+                              if args.overlap else f"{len(trainer.buckets)} NCCL bucket(s) on the main stream (no overlap), captured in the step graph"),
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
@@ -535,11 +535,19 @@ def run_ours(args):
             "final_loss": final_loss,
             "kernel_breakdown_ms": breakdown,
         }
+    if world > 1:
+        # several ranks: nothing else to measure.  The step graphs hold captured NCCL work; tearing them (or the process
+        # group) down can block in NCCL's cleanup, so the ranks leave through os._exit once the line is out.
+        dist.barrier()
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        dist.barrier()
+        os._exit(0)
     # free the training state before the single-GPU extras
     if use_graph:
         trainer.disable_cuda_graph()
-    if world > 1:
-        dist.barrier()
     if rank == 0 and world == 1:
         del trainer, net
         torch.cuda.empty_cache()
@@ -562,9 +570,6 @@ def run_ours(args):
                                     "sample": f"8 images/step of the same workload, fp32, {what}, 3 timed steps"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(0)   # nothing left to do; skip interpreter teardown of CUDA / NCCL state
@@ -696,6 +701,7 @@ def main():
     ap.add_argument("--no-infer", action="store_true", help="skip the inference sweep record (N = 1)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-GPU comparator (N = 1)")
     ap.add_argument("--graph", type=int, default=1, help="replay the whole step from a CUDA graph")
+    ap.add_argument("--overlap", type=int, default=1, help="N > 1: all-reduce gradient buckets on a side stream while backward continues")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

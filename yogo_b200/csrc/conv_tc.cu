@@ -855,61 +855,68 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       unsigned long long mbits0 = 0ull, mbits1 = 0ull, mbits2 = 0ull, mbits3 = 0ull;   // forward: sign bits of this thread's chunks
       // ---- straight-line fast paths for the common epilogue flavours: 32 columns per iteration, no branches inside,
       // so the compiler can interleave 32 independent element chains (the generic loop below issues at IPC ~0.25)
-      if (MODE == 0 && fast_fwd) {
+      if (MODE == 0 && fast_fwd && ((j_end - jb) & 3) == 0) {
+        // 64 columns per iteration of the runtime loop, as two unrolled 32-column halves: the sign-mask word of the group
+        // leaves as one 8-byte store, no per-chunk bookkeeping (ncu: the previous form spent ~100 of its 350 instructions
+        // per 32 columns on loop / select overhead, and the epilogue's issue slots are what bounds the forward layers)
         bf16* orow = out + pix * e_OC + nt * BN;
-        for (int j = jb; j < j_end; j += 2) {
-          uint32_t ra[16], rb[16];
-          tmem_ld16(taddr0 + (uint32_t)(j * 16), ra);
-          tmem_ld16(taddr0 + (uint32_t)(j * 16 + 16), rb);
-          const int c0 = nt * BN + j * 16;
-          float v[32], k[32];
-          {
-            const float4* k4 = reinterpret_cast<const float4*>(s_k1 + c0);
+        unsigned long long* mrow = e_mask_out ? reinterpret_cast<unsigned long long*>(
+            reinterpret_cast<unsigned char*>(e_mask_out) + ((pix * e_OC + nt * BN) >> 3)) : nullptr;
+        for (int j = jb; j < j_end; j += 4) {
+          unsigned long long mb64 = 0ull;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; k[4*i] = t4.x; k[4*i+1] = t4.y; k[4*i+2] = t4.z; k[4*i+3] = t4.w; }
-          }
-          tmem_ld_wait32(ra, rb);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int jq = j + 2 * hh;
+            uint32_t ra[16], rb[16];
+            tmem_ld16(taddr0 + (uint32_t)(jq * 16), ra);
+            tmem_ld16(taddr0 + (uint32_t)(jq * 16 + 16), rb);
+            const int c0 = nt * BN + jq * 16;
+            float v[32], k[32];
+            {
+              const float4* k4 = reinterpret_cast<const float4*>(s_k1 + c0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(ra[i]) + k[i]; v[16 + i] = __uint_as_float(rb[i]) + k[16 + i]; }
-          if (e_act == YG_ACT_LRELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
-          }
-          if (e_dropscale) {
-            const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
-          }
-          __align__(16) uint32_t ob32[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
-          }
-          if (e_mask_out) {
-            // sign bits from the packed outputs: bf16 > 0 <=> its bit pattern, read as int16, is > 0; sign(y) = sign(v)
-            // wherever the Dropout2d scale is non-zero (and a dropped channel's gradient is zero whatever the bit says)
-            // word i holds elements 2i (low half) and 2i+1 (high half): select bit 2i of the low and bit 2i+1 of the high
-            // compare mask and OR everything together - one compare and one three-input logic op per word
-            uint32_t acc0 = 0, acc1 = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t sel = (1u << (2 * i)) | (1u << (2 * i + 17));
-              acc0 |= __vcmpgts2(ob32[i], 0u) & sel;
-              acc1 |= __vcmpgts2(ob32[8 + i], 0u) & sel;
+              for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; k[4*i] = t4.x; k[4*i+1] = t4.y; k[4*i+2] = t4.z; k[4*i+3] = t4.w; }
             }
-            const unsigned long long bits =
-                (unsigned long long)(((acc0 & 0xFFFFu) | (acc0 >> 16)) | ((((acc1 & 0xFFFFu) | (acc1 >> 16))) << 16));
-            const int jj = j - jb, mb = jj >> 2, sh = 16 * (jj & 3);
-            if (mb == 0) mbits0 |= bits << sh;
-            else if (mb == 1) mbits1 |= bits << sh;
-            else if (mb == 2) mbits2 |= bits << sh;
-            else mbits3 |= bits << sh;
+            tmem_ld_wait32(ra, rb);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(ra[i]) + k[i]; v[16 + i] = __uint_as_float(rb[i]) + k[16 + i]; }
+            if (e_act == YG_ACT_LRELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
+            }
+            if (e_dropscale) {
+              const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
+            }
+            __align__(16) uint32_t ob32[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
+            }
+            if (e_mask_out) {
+              // sign bits from the packed outputs: bf16 > 0 <=> its bit pattern, read as int16, is > 0; sign(y) = sign(v)
+              // wherever the Dropout2d scale is non-zero (and a dropped channel's gradient is zero whatever the bit says)
+              // word i holds elements 2i (low half) and 2i+1 (high half): select bit 2i of the low and bit 2i+1 of the high
+              // compare mask and OR everything together - one compare and one three-input logic op per word
+              uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t sel = (1u << (2 * i)) | (1u << (2 * i + 17));
+                acc0 |= __vcmpgts2(ob32[i], 0u) & sel;
+                acc1 |= __vcmpgts2(ob32[8 + i], 0u) & sel;
+              }
+              const unsigned long long bits =
+                  (unsigned long long)(((acc0 & 0xFFFFu) | (acc0 >> 16)) | ((((acc1 & 0xFFFFu) | (acc1 >> 16))) << 16));
+              mb64 |= bits << (32 * hh);
+            }
+            if (valid && !(e_dbg & 1)) {
+              st_global_256(orow + jq * 16, ob32);
+              st_global_256(orow + jq * 16 + 16, ob32 + 8);
+            }
           }
-          if (valid && !(e_dbg & 1)) {
-            st_global_256(orow + j * 16, ob32);
-            st_global_256(orow + j * 16 + 16, ob32 + 8);
-          }
+          if (mrow && valid) mrow[j >> 2] = mb64;
         }
       } else if (MODE == 1 && fast_bwd) {
         bf16* orow = out + pix * e_OC + nt * BN;
@@ -1310,7 +1317,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
       }   // generic chunk loop
-      if (MODE == 0 && e_mask_out && valid && j_end > jb) {
+      if (MODE == 0 && e_mask_out && valid && j_end > jb && !(fast_fwd && ((j_end - jb) & 3) == 0)) {
         // one store per thread and tile: 2 bytes per chunk, contiguous because the chunks are
         unsigned char* mp = reinterpret_cast<unsigned char*>(e_mask_out) + ((pix * e_OC + nt * BN) >> 3) + jb * 2;
         const int nmine = j_end - jb;

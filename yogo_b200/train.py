@@ -280,7 +280,8 @@ class DataParallelTrainer:
         self._graph = self._graphs[0]
 
     def disable_cuda_graph(self) -> None:
-        """Drop the captured graphs (before `destroy_process_group`: they hold captured NCCL work)."""
+        """Drop the captured graphs and the memory pool they pin.  With several ranks the graphs hold captured NCCL work and
+        destroying them has been seen to block inside NCCL's cleanup: keep them until the process exits instead."""
         self._graph = None
         self._graphs, self._graph_losses = [], []
         torch.cuda.synchronize()
