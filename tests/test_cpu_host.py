@@ -161,3 +161,14 @@ def test_trainer_optimizer_state_round_trip(tmp_path):
     net2.model[0][0].weight.data = net2.model[0][0].weight.data.clone()
     with pytest.raises(RuntimeError, match="no longer aliases"):
         tr2._check_views()
+
+
+def test_collate_batch_robust_cpu():
+    """yogo/data/utils.py:49-63 without a device: pure stacking, identity transforms."""
+    from yogo_b200.data import collate_batch_robust
+    a = (torch.zeros(1, 4, 4, dtype=torch.uint8), torch.zeros(6, 2, 2))
+    b = (torch.ones(1, 4, 4, dtype=torch.uint8), torch.ones(6, 2, 2))
+    x, y = collate_batch_robust([a, None, b])
+    assert tuple(x.shape) == (2, 1, 4, 4) and tuple(y.shape) == (2, 6, 2, 2) and int(x[1].sum()) == 16
+    with pytest.raises(ValueError):
+        collate_batch_robust([None])

@@ -1205,3 +1205,69 @@ def test_graphed_inference_equals_eager():
         for b in range(3):
             n = int(kc[b])
             assert torch.equal(rows[b, :n], r2[b, :n]) and torch.equal(kidx[b, :n], kidx2[b, :n])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_input_normalisation_equals_divide_by_255(golden_dir, dtype):
+    """N3 (yogo_dataset.py:280-283, image_path_dataset.py:71-73): uint8 images with the /255 folded into the first layer
+    give the same train step as feeding `x.float() / 255` - outputs, loss, every gradient (incl. the clamped first-layer
+    weight gradient) and the BatchNorm running statistics - and therefore match the reference golden as well."""
+    z = _load(golden_dir, "model_base.npz")
+    prefix = "base_train."
+    keeps = {int(k.split(".")[-1]): torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix + "keep.")}
+    img = torch.from_numpy(z["img"])
+    res = []
+    for fused in (False, True):
+        net, _ = _build_from_golden(z, "base_model", dtype=dtype)
+        net.train()
+        net._get_runner().drop_keep_override = keeps
+        if fused:
+            net.set_fused_input_scale(1.0 / 255.0)
+            x = img.to(DEV)
+            assert x.dtype == torch.uint8
+        else:
+            x = (img.float() / 255.0).to(DEV)
+        out = net(x)
+        loss, _ = yogo_b200.YOGOLoss().to(DEV)(out, torch.from_numpy(z["label"]).to(DEV))
+        loss.backward()
+        res.append((out.detach(), loss.detach(), {k: p.grad.clone() for k, p in net.named_parameters()},
+                    {k: v.clone() for k, v in net.state_dict().items() if "running_" in k}))
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert _rel(res[1][0].cpu().numpy(), res[0][0].cpu().numpy()) < tol
+    assert abs(float(res[1][1]) - float(res[0][1])) < tol * abs(float(res[0][1]))
+    for k in res[0][2]:
+        a, b = res[1][2][k].cpu().numpy(), res[0][2][k].cpu().numpy()
+        # (floor 1e-2: the conv bias in front of BatchNorm has a ~0 gradient that is pure rounding noise)
+        assert np.linalg.norm(a - b) <= (2e-3 if dtype == torch.float32 else 0.35) * max(np.linalg.norm(b), 1e-2), k
+        assert np.abs(a).max() <= 1.0 + 1e-6   # clamp(+-clip_value) still holds after the rescaling
+    for k in res[0][3]:
+        torch.testing.assert_close(res[1][3][k], res[0][3][k], rtol=1e-3 if dtype == torch.float32 else 2e-2, atol=1e-5)
+    if dtype == torch.float32:
+        assert _rel(res[1][0].cpu().numpy(), z[prefix + "out"]) < 1e-3
+
+
+def test_nan_gradient_propagates_like_torch_clamp():
+    """The reference's gradient hook is torch.clamp (model.py:76-77), which keeps NaN; the fused reduce kernels must not turn
+    a NaN gradient into a finite -clip."""
+    net = yogo_b200.YOGO((64, 96), O.ANCHOR_W, O.ANCHOR_H, 7).to(DEV)
+    net.train()
+    x = torch.rand(2, 1, 64, 96, device=DEV)
+    out = net(x)
+    g = torch.zeros_like(out)
+    g[0, 5, 3, 3] = float("nan")
+    out.backward(g)
+    assert torch.isnan(net.model[-1].weight.grad).any() and torch.isnan(net.model[-1].bias.grad).any()
+    assert torch.isnan(net.model[3][0].weight.grad).any()
+
+
+def test_collate_batch_robust_on_device():
+    """yogo/data/utils.py:49-63: None items are dropped, the rest stacked, batch transforms applied (here on the GPU)."""
+    from yogo_b200.data import MultiArgSequential, RandomHorizontalFlipWithBBs, collate_batch_robust
+    imgs = O.synth_images(3, 32, 48)
+    labs = O.synth_labels(3, 4, 6, 7, 5)
+    batch = [(imgs[0], labs[0]), None, (imgs[1], labs[1]), (imgs[2], labs[2]), None]
+    a, b = collate_batch_robust(batch, MultiArgSequential(RandomHorizontalFlipWithBBs(1.0)), device=DEV)
+    ea, eb = O.flip_batch_np(imgs.numpy(), labs.numpy(), True, False)
+    assert a.is_cuda and np.array_equal(a.cpu().numpy(), ea) and np.array_equal(b.cpu().numpy().view(np.uint32), eb.view(np.uint32))
+    with pytest.raises(ValueError):
+        collate_batch_robust([None, None])

@@ -78,8 +78,10 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// torch.clamp(grad, -c, c) of the reference's parameter hook (model.py:76-77) propagates NaN; fminf / fmaxf would
+// return the finite operand and turn a NaN gradient into a silent -c
 __device__ __forceinline__ float clampf(float v, float c) {
-  return c > 0.f ? fminf(fmaxf(v, -c), c) : v;
+  return (c > 0.f && v == v) ? fminf(fmaxf(v, -c), c) : v;
 }
 
 // The shared backward epilogue (yg_bwd_epilogue semantics): g = d(loss)/d(layer output)

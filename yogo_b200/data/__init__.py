@@ -9,3 +9,4 @@ from .data_transforms import (  # noqa: F401
     flip_batch,
 )
 from .yogo_dataset import LABEL_TENSOR_PRED_DIM_SIZE, format_labels_batch, format_labels_tensor  # noqa: F401
+from .utils import collate_batch_robust  # noqa: F401

@@ -139,6 +139,9 @@ class Runner:
         # straight into views of a flat bucket, and a callback fires as each one is enqueued
         self.grad_views: Optional[Dict[int, torch.Tensor]] = None
         self.on_grad_ready = None
+        # uint8 input normalisation fused into the first layer: the network sees x * input_scale (1/255 = the `/ 255` of
+        # the reference's datasets, yogo_dataset.py:280-283, image_path_dataset.py:71-73) without an fp32 copy of the image
+        self.input_scale: Optional[float] = None
 
     # ---------------------------------------------------------------- helpers
     def _dropscale(self, i: int, blk: ConvBlock, N: int, device, training: bool) -> Optional[torch.Tensor]:
@@ -193,9 +196,16 @@ class Runner:
             rec = {"in": cur, "h": h, "w": w, "ho": ho, "wo": wo, "dropscale": ds, "bn_train": bn_train}
             first_direct = i == 0 and blk.ksize == 3 and blk.cin <= 3
             rec["first_direct"] = first_direct
+            in_scale = self.input_scale if (i == 0 and x_code == L.YG_U8 and self.input_scale not in (None, 1.0)) else None
+            if in_scale is not None:
+                # conv(x * s, W) = conv(x, W * s): the first layer runs on the raw bytes with scaled weights (144 floats)
+                wt = wt * in_scale
+                rec["in_scale"], rec["wt_eff"] = in_scale, wt
             if i == 0 and not first_direct:
                 cur = x.permute(0, 2, 3, 1).contiguous().to(dt)  # plumbing: NCHW image -> NHWC
                 rec["in"] = cur
+                if in_scale is not None:
+                    raise _unsupported("input_scale with a first block that is not a 3x3 conv on 1-3 input channels")
             out = torch.empty((N, ho, wo, blk.cout), dtype=dt, device=dev)
 
             def conv(ep: L.FwdEpilogue, y: Optional[torch.Tensor]):
@@ -386,7 +396,16 @@ class Runner:
         for i in range(last, -1, -1):
             blk, rec = plan.blocks[i], recs[i]
             h, w, ho, wo = rec["h"], rec["w"], rec["ho"], rec["wo"]
-            wt = _f32(blk.conv.weight)
+            wt = rec.get("wt_eff") if rec.get("wt_eff") is not None else _f32(blk.conv.weight)
+            in_scale = rec.get("in_scale")
+            # W_eff = W * s: dL/dW = s * dL/dW_eff, and clamp(s * g, c) = s * clamp(g, c / s)
+            clip_w = clip / in_scale if (in_scale and clip > 0) else clip
+
+            def reclamp(*ts):   # the kernels clamp every output of a call with one bound: restore the true one for the others
+                if in_scale and clip > 0:
+                    for t in ts:
+                        if t is not None:
+                            t.clamp_(-clip, clip)
             dw = gbuf(blk.conv.weight)
             db = gbuf(blk.conv.bias) if blk.conv.bias is not None else None
             if rec["first_direct"]:
@@ -409,8 +428,11 @@ class Runner:
                                                            wt.data_ptr(), L.ptr(rec.get("fwd_shift")),
                                                            rec["gamma"].data_ptr(), rec["mean"].data_ptr(),
                                                            rec["invstd"].data_ptr(), float(N * ho * wo),
-                                                           1 if rec["bn_train"] else 0, clip, blk.cout, dw.data_ptr(),
+                                                           1 if rec["bn_train"] else 0, clip_w, blk.cout, dw.data_ptr(),
                                                            L.ptr(db), dgam.data_ptr(), dbet.data_ptr(), st))
+                    if in_scale:
+                        dw.mul_(in_scale)
+                        reclamp(db, dgam, dbet)
                     grads[id(blk.bn.weight)] = dgam
                     grads[id(blk.bn.bias)] = dbet
                     grads[id(blk.conv.weight)] = dw
@@ -447,7 +469,10 @@ class Runner:
                     ep2 = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), None, None, None, None, None)
                 L.check(lib.yg_conv_first_bwd(x.data_ptr(), x_code, wt.data_ptr(), g.data_ptr(), dcode, N, h, w,
                                               blk.cin, blk.cout, blk.stride, C.byref(ep2), L.ptr(rec.get("fwd_shift") if blk.bn is not None else (_f32(blk.conv.bias) if blk.conv.bias is not None else None)),
-                                              L.ptr(m1), L.ptr(m2), dw.data_ptr(), L.ptr(db), clip, ws.data_ptr(), nb, st))
+                                              L.ptr(m1), L.ptr(m2), dw.data_ptr(), L.ptr(db), clip_w, ws.data_ptr(), nb, st))
+                if in_scale:
+                    dw.mul_(in_scale)
+                    reclamp(db)
                 grads[id(blk.conv.weight)] = dw
                 if db is not None:
                     grads[id(blk.conv.bias)] = db

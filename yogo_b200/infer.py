@@ -224,6 +224,8 @@ def predict(
 
         pbar = tqdm(unit="images", total=n_images)
     normalize = bool(model.normalize_images)
+    if normalize:
+        model.set_fused_input_scale(1.0 / 255.0)   # uint8 batches: the /255 happens inside the first-layer kernel
     for i, lo in enumerate(range(0, n_images, batch_size)):
         hi = min(lo + batch_size, n_images)
         try:
@@ -232,7 +234,7 @@ def predict(
             warnings.warn(f"got error {e}; continuing")
             continue
         x = img_batch.to(dev, non_blocking=True)
-        if normalize:
+        if normalize and x.dtype != torch.uint8:
             x = x.float() / 255.0
         res = model(x)
         if results is None and return_full_predictions:

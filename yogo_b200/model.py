@@ -237,6 +237,13 @@ class YOGO(nn.Module):
             self._runner = engine.Runner(self)
         return self._runner
 
+    def set_fused_input_scale(self, scale: Optional[float]) -> None:
+        """uint8 images are consumed as `x * scale` by the first-layer kernels (scale = 1/255 reproduces the `/ 255` that
+        the reference's datasets apply when `normalize_images` is set, yogo_dataset.py:280-283) - no fp32 copy of the
+        image is made.  `None` restores the reference's forward (`x.float()`, model.py:272-273).  Float inputs are never
+        scaled."""
+        self._get_runner().input_scale = scale
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """model.py:267-313.  Returns (N, 5+C, Sy, Sx) fp32: [xc, yc, w, h, objectness, classes...]."""
         from . import engine
