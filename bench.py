@@ -407,6 +407,8 @@ def run_ours(args):
     net = yogo_b200.YOGO((H, W), O.ANCHOR_W, O.ANCHOR_H, NUM_CLASSES,
                          model_func=yogo_b200.get_model_func(args.model)).to(dev)
     net.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    if args.dtype == "fp32" and args.fp32_x3:
+        yogo_b200.set_fp32_tensor_cores(True)   # split-bf16 convolutions of fp32 tensors on the tensor cores (csrc/x3.cu)
     net.train()
     loss_fn = yogo_b200.YOGOLoss().to(dev)
     trainer = DataParallelTrainer(net, loss_fn, total_steps=10000, overlap=bool(args.overlap))
@@ -520,7 +522,7 @@ def run_ours(args):
                                "(parity / sweep configuration)"),
                 "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                 "l2_policy": "inputs+activations per step (>3 GB) far exceed the 126 MB L2; batches alternate",
-                "conv_impl": L.get_conv_impl(), "cuda_graph": bool(use_graph),
+                "conv_impl": L.get_conv_impl() + (" + fp32 x3" if yogo_b200.get_fp32_tensor_cores() else ""), "cuda_graph": bool(use_graph),
                 "allreduce": "none (1 rank)" if world == 1 else
                              (f"{len(trainer.buckets)} NCCL bucket(s) on a side stream, overlapped with backward, captured in the step graph"
                               if args.overlap else f"{len(trainer.buckets)} NCCL bucket(s) on the main stream (no overlap), captured in the step graph"),
@@ -701,6 +703,7 @@ def main():
     ap.add_argument("--no-infer", action="store_true", help="skip the inference sweep record (N = 1)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-GPU comparator (N = 1)")
     ap.add_argument("--graph", type=int, default=1, help="replay the whole step from a CUDA graph")
+    ap.add_argument("--fp32-x3", type=int, default=1, help="--dtype fp32: run the convolutions as split-bf16 x3 on the tensor cores")
     ap.add_argument("--overlap", type=int, default=1, help="N > 1: all-reduce gradient buckets on a side stream while backward continues")
     args = ap.parse_args()
     if args.impl == "reference":

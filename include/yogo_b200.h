@@ -52,8 +52,10 @@ int yg_get_conv_impl(void);
  * bit 15 = CTA pairs for stride-2 dgrad (slower), bit 16 = mma.sync wgrad also for 32->64 stride 2 (slower),
  * bit 17 = no mma.sync wgrad at all, bit 18 = no CTA pairs for N = 64 stride-1 dgrad,
  * bit 19 = no merged row taps (one N = 192 MMA) in the 64-input-channel wgrad, bit 20 = stride-2 wgrad fetches the dz tile once
- * per parity group instead of once per tile. */
+ * per parity group instead of once per tile, bit 21 = fp32 tensors as split-bf16 "x3" convolutions on the tensor cores
+ * (csrc/x3.cu; off by default: the exact SIMT kernels are the fp32 parity path). */
 int yg_set_tc_options(int options);
+int yg_get_tc_options(void);
 /* profiling hook: copies n (<= 2048) cycle counters written by the engine's MMA warps (8 per CTA) to host memory. */
 int yg_tc_debug_read(unsigned long long* out, int n);
 /* number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */

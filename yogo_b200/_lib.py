@@ -62,6 +62,7 @@ _PROTOS = {
     "yg_set_conv_impl": (c_int, [c_int]),
     "yg_get_conv_impl": (c_int, []),
     "yg_set_tc_options": (c_int, [c_int]),
+    "yg_get_tc_options": (c_int, []),
     "yg_tc_debug_read": (c_int, [c_void_p, c_int]),
     "yg_launch_count": (C.c_ulonglong, []),
     "yg_conv_first_fwd": (
@@ -271,3 +272,21 @@ def set_conv_impl(impl: str) -> None:
 
 def get_conv_impl() -> str:
     return {IMPL_AUTO: "auto", IMPL_SIMT: "simt", IMPL_TCGEN05: "tcgen05"}[load().yg_get_conv_impl()]
+
+
+FP32_X3_BIT = 1 << 21
+
+
+def set_fp32_tensor_cores(on: bool) -> None:
+    """fp32 tensors (`compute_dtype = torch.float32`) on the bf16 tensor cores through the split-bf16 "x3" convolutions of
+    csrc/x3.cu (error ~2^-16 per product, ~13x faster than the exact SIMT kernels).  Off by default: the exact kernels are
+    the fp32 parity path - LeakyReLU networks amplify any rounding difference wherever a pre-activation sits within that
+    difference of the kink, so gradients of the x3 path agree with the reference to ~1e-2, not 1e-3 (its forward does, and so
+    do the gradients of SiLU networks)."""
+    lib_ = load()
+    cur = lib_.yg_get_tc_options()
+    check(lib_.yg_set_tc_options((cur | FP32_X3_BIT) if on else (cur & ~FP32_X3_BIT)))
+
+
+def get_fp32_tensor_cores() -> bool:
+    return bool(load().yg_get_tc_options() & FP32_X3_BIT)

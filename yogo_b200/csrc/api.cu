@@ -28,6 +28,14 @@ int conv_fwd_tc(const void*, const float*, void*, int, int, int, int, int, int, 
 int conv_dgrad_tc(const void*, const float*, void*, int, int, int, int, int, int, int, const BwdEpi&, cudaStream_t);
 int conv_wgrad_tc(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace(int, int, int, int, int, int, int);
+// fp32 tensors on the bf16 tensor cores (x3.cu)
+bool x3_fwd_supported(int W, int Cin, int Cout, int ks, int stride);
+bool x3_dgrad_supported(int W, int Cin, int Cout, int ks, int stride);
+bool x3_wgrad_supported(int W, int Cin, int Cout, int ks, int stride);
+size_t x3_wgrad_workspace(int, int, int, int, int, int, int);
+int conv_fwd_x3(const float*, const float*, float*, int, int, int, int, int, int, int, FwdEpi, cudaStream_t);
+int conv_dgrad_x3(const float*, const float*, float*, int, int, int, int, int, int, int, BwdEpi, cudaStream_t);
+int conv_wgrad_x3(const float*, const float*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
 bool wgrad_hmma_supported(int dtype, int W, int Cin, int Cout, int ks, int stride);
 size_t wgrad_hmma_workspace(int Cin, int Cout);
 int conv_wgrad_hmma(const void*, const void*, float*, float*, int, int, int, int, int, int, int, float, void*, size_t, cudaStream_t);
@@ -70,6 +78,7 @@ extern "C" int yg_set_conv_impl(int impl) {
 extern "C" int yg_get_conv_impl(void) { return g_conv_impl; }
 static int yg_get_tc_options_raw() { return get_tc_options(); }
 extern "C" int yg_set_tc_options(int v) { return set_tc_options(v); }
+extern "C" int yg_get_tc_options(void) { return get_tc_options(); }
 extern "C" int yg_tc_debug_read(unsigned long long* out, int n) { return tc_debug_read(out, n); }
 
 static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
@@ -100,6 +109,10 @@ extern "C" int yg_conv_fwd(const void* x, const float* w, void* y, int dtype, in
   if (ep.actmask) YG_CHECK_ARG(Cout % 32 == 0 && y, "conv_fwd: actmask needs Cout % 32 == 0 and an output tensor");
   if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
     return conv_fwd_tc(x, w, y, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
+  // fp32 tensors: split-bf16 convolution on the tensor cores (opt-in, option bit 21: yogo_b200.set_fp32_tensor_cores)
+  if (dtype == YG_F32 && g_conv_impl != YG_IMPL_SIMT && (yg_get_tc_options_raw() & 2097152) && y && !ep.actmask &&
+      x3_fwd_supported(W, Cin, Cout, ks, stride) && aligned32(x) && aligned32(y) && aligned32(ep.preact))
+    return conv_fwd_x3((const float*)x, w, (float*)y, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
   rc = conv_fwd_simt(x, w, y, dtype, N, H, W, Cin, Cout, ks, stride, ep, (cudaStream_t)stream);
   if (rc == YG_OK && ep.actmask) {
     // generic path: derive the sign bits from the stored output (sign(y) == sign(v) wherever dropscale != 0)
@@ -128,12 +141,16 @@ extern "C" int yg_conv_dgrad(const void* dz, const float* w, void* dx, int dtype
   }
   if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
     return conv_dgrad_tc(dz, w, dx, N, H, W, Cin, Cout, ks, stride, be, (cudaStream_t)stream);
+  if (dtype == YG_F32 && g_conv_impl != YG_IMPL_SIMT && (yg_get_tc_options_raw() & 2097152) && !be.actmask &&
+      x3_dgrad_supported(W, Cin, Cout, ks, stride) && aligned32(dz) && aligned32(dx) && aligned32(be.saved))
+    return conv_dgrad_x3((const float*)dz, w, (float*)dx, N, H, W, Cin, Cout, ks, stride, be, (cudaStream_t)stream);
   return conv_dgrad_simt(dz, w, dx, dtype, N, H, W, Cin, Cout, ks, stride, be, (cudaStream_t)stream);
 }
 
 extern "C" size_t yg_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ks, int stride) {
   size_t a = simt_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
   size_t b = tc_wgrad_workspace(N, H, W, Cin, Cout, ks, stride);
+  { const size_t c = x3_wgrad_workspace(N, H, W, Cin, Cout, ks, stride); if (c > b) b = c; }
   if (wgrad_hmma_supported(YG_BF16, W, Cin, Cout, ks, stride)) { const size_t c = wgrad_hmma_workspace(Cin, Cout); if (c > b) b = c; }
   return a > b ? a : b;
 }
@@ -157,5 +174,10 @@ extern "C" int yg_conv_wgrad(const void* x, const void* dz, float* dw, float* db
     return conv_wgrad_hmma(x, dz, dw, dbias, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);
   if (tc_ok && g_conv_impl != YG_IMPL_SIMT)
     return conv_wgrad_tc(x, dz, dw, dbias, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (dtype == YG_F32 && g_conv_impl != YG_IMPL_SIMT && (yg_get_tc_options_raw() & 2097152) &&
+      x3_wgrad_supported(W, Cin, Cout, ks, stride) && aligned32(x) && aligned32(dz) &&
+      workspace_bytes >= x3_wgrad_workspace(N, H, W, Cin, Cout, ks, stride))
+    return conv_wgrad_x3((const float*)x, (const float*)dz, dw, dbias, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
   return conv_wgrad_simt(x, dz, dw, dbias, dtype, N, H, W, Cin, Cout, ks, stride, clip, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -97,6 +97,7 @@ struct BwdEpi {
   const float* bn_invstd;
   double* bn_sums;
   const void* actmask;
+  int io_f32;   // internal: `saved` is read and the output written as fp32 (x3.cu)
 };
 inline BwdEpi make_bwd_epi(const yg_bwd_epilogue* be) {
   BwdEpi e{};
@@ -132,6 +133,7 @@ struct FwdEpi {
   double* stats;
   void* preact;
   void* actmask;
+  int io_f32;   // internal: the output / pre-activation copy are written as fp32 (x3.cu)
 };
 inline FwdEpi make_fwd_epi(const yg_fwd_epilogue* ep) {
   FwdEpi e{};

@@ -98,6 +98,7 @@ struct TcParams {
   uint32_t tab_a[27], tab_b[27], tab_km[27], tab_hi[27];   // tab_hi: high descriptor word of A (SBO = box row pitch)
   int ebeg[TC_MAX_GROUPS + 1];
   int shift_exp[TC_MAX_GROUPS];   // experiment (option bit 12): extra A start offset in bytes per group
+  int io_f32;  // the epilogue reads `saved` and writes `out` / `preact` as fp32 (split-bf16 "x3" convolutions of fp32 tensors, see x3.cu)
   int debug;   // profiling knobs (tools/bench_conv.py): 1 = no global stores, 2 = no MMA issue, 4 = epilogue skips TMEM loads and math, 8 = no TMA loads, 16 = MMA-warp cycle counters -> g_tc_dbg
 };
 
@@ -676,7 +677,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           for (int e = p.ebeg[g0]; e < e1; ++e) {
             // descriptors advance by 32 bytes (2 units of 16 B) per K step
             const uint32_t ad0 = ast + p.tab_a[e], bd0 = bst + p.tab_b[e], a_hi = p.tab_hi[e];
-            const unsigned km = (p.tab_km[e] >> (kc * KSTEPS)) & ((1u << KSTEPS) - 1u);
+            // (all ones = no structural zeros: also for K > 512 channels, whose K steps do not fit the 32-bit mask)
+            const unsigned kmr = p.tab_km[e];
+            const unsigned km = kmr == 0xFFFFFFFFu ? ((1u << KSTEPS) - 1u) : ((kmr >> (kc * KSTEPS)) & ((1u << KSTEPS) - 1u));
             if (p.debug & 2) continue;
             if (km == (1u << KSTEPS) - 1u) {
 #pragma unroll
@@ -782,16 +785,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool ds_smem = e_dropscale != nullptr && alt && e_OC <= 256;   // else the scales are read through L1 per chunk
     const bool eprof = (p.debug & 16) != 0 && warp == PW + 1;
     long long ec_tfull = 0, ec_ld = 0, ec_pre = 0, ec_math = 0, ec_store = 0, ec_rest = 0, ec_tiles = 0, eprev = clock64();
-    const bool use_mask = MODE == 1 && p.actmask_in && e_act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (e_OC % 32) == 0;
+    const bool io_f32 = p.io_f32 != 0;
+    const bool use_mask = MODE == 1 && p.actmask_in && e_act == YG_ACT_LRELU && !has_bn && (BN % 32) == 0 && (e_OC % 32) == 0 && !io_f32;
     // (dgrad fast path: the multiplication order differs from the generic path only by commuting g*ds*slope)
-    const bool fast_fwd = MODE == 0 && !e_head_out && !e_has_scale && !e_stats && !e_preact && (BN % 64) == 0 &&
+    const bool fast_fwd = MODE == 0 && !io_f32 && !e_head_out && !e_has_scale && !e_stats && !e_preact && (BN % 64) == 0 &&
                           (e_act == YG_ACT_LRELU || e_act == YG_ACT_NONE) && !(p.debug & 4) && out != nullptr;
     const bool fast_bwd = MODE == 1 && use_mask && !e_bn_sums && (BN % 64) == 0 && !(p.debug & 4);
     // SiLU flavours (silu_model): forward = bias + SiLU (+ Dropout2d) with the bf16 pre-activation saved for backward,
     // backward = SiLU'(saved pre-activation, or saved raw output through the BatchNorm affine) without the BN sums
-    const bool fast_fwd_silu = MODE == 0 && !e_head_out && !e_has_scale && !e_stats && e_preact && e_act == YG_ACT_SILU &&
+    const bool fast_fwd_silu = MODE == 0 && !io_f32 && !e_head_out && !e_has_scale && !e_stats && e_preact && e_act == YG_ACT_SILU &&
                                alt && (BN % 32) == 0 && !(p.debug & 4) && out != nullptr && !e_mask_out;
-    const bool fast_bwd_silu = MODE == 1 && !use_mask && e_saved && e_act == YG_ACT_SILU && !e_bn_sums && alt &&
+    const bool fast_bwd_silu = MODE == 1 && !io_f32 && !use_mask && e_saved && e_act == YG_ACT_SILU && !e_bn_sums && alt &&
                                (BN % 32) == 0 && !(p.debug & 4);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = acc_it;
@@ -827,9 +831,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const int a2 = th2 * e_TH + hl, b2 = tw2 * e_TW + wl;
           const int oh2 = a2 * e_osh + C2.oh0, ow2 = b2 * e_osw + C2.ow0;
           if (a2 < C2.TSH && b2 < C2.TSW && oh2 < e_OH && ow2 < e_OW) {
+            const int esz = io_f32 ? 2 : 1;   // in units of bf16 elements
             const bf16* row = reinterpret_cast<const bf16*>(e_saved) +
-                              (((long long)n2 * e_OH + oh2) * e_OW + ow2) * e_OC + nt2 * BN;
-            for (int c = 0; c < BN; c += 64)
+                              ((((long long)n2 * e_OH + oh2) * e_OW + ow2) * e_OC + nt2 * BN) * esz;
+            for (int c = 0; c < BN * esz; c += 64)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c));
           }
         }
@@ -1080,13 +1085,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           for (int i = 0; i < 16; ++i) ds[i] = 1.f;
         }
         __align__(16) bf16 sv[16];
+        __align__(16) float svf[16];
         if (MODE == 1) {
-          if (e_saved && valid && !use_mask) {
+          if (e_saved && valid && !use_mask && io_f32) {
+            const float* sp = reinterpret_cast<const float*>(e_saved) + pix * e_OC + c0;
+            ld_global_nc_256(sp, reinterpret_cast<uint4*>(svf)[0], reinterpret_cast<uint4*>(svf)[1]);
+            ld_global_nc_256(sp + 8, reinterpret_cast<uint4*>(svf)[2], reinterpret_cast<uint4*>(svf)[3]);
+          } else if (e_saved && valid && !use_mask) {
             ld_global_nc_256(reinterpret_cast<const bf16*>(e_saved) + pix * e_OC + c0, reinterpret_cast<uint4*>(sv)[0],
                              reinterpret_cast<uint4*>(sv)[1]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sv[i] = __float2bfloat16_rn(0.f);
+            for (int i = 0; i < 16; ++i) { sv[i] = __float2bfloat16_rn(0.f); svf[i] = 0.f; }
           }
         }
         long long ec0 = 0;
@@ -1144,7 +1154,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         } else if (MODE == 0) {
           __align__(16) bf16 pb[16];
-          const bool rnd = e_stats || e_preact;
+          const bool rnd = (e_stats || e_preact) && !io_f32;
           {
             // per-channel constants: 128-bit broadcast loads from smem
             const float4* sh4 = reinterpret_cast<const float4*>(s_k1 + c0);
@@ -1174,12 +1184,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               const float2 f2 = __bfloat1622float2(pk);
               r[2*i] = __float_as_uint(f2.x); r[2*i+1] = __float_as_uint(f2.y);
             }
+          }
+          if (rnd || (io_f32 && e_stats)) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float x = __uint_as_float(r[i]);
               s1[i] = valid ? x : 0.f;
               s2[i] = valid ? x * x : 0.f;
             }
+          }
+          if (io_f32 && e_preact && valid && !(e_dbg & 1)) {   // fp32 pre-activation copy (before the activation below)
+            float* pp = reinterpret_cast<float*>(e_preact) + pix * e_OC + c0;
+            st_global_256(pp, r);
+            st_global_256(pp + 8, r + 8);
           }
           if (e_mask_out && valid) {
             uint32_t bits = 0;
@@ -1213,10 +1230,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             reinterpret_cast<__nv_bfloat162*>(ob)[i] = __floats2bfloat162_rn(__uint_as_float(r[2*i]), __uint_as_float(r[2*i+1]));
           if (eprof) { const long long t = clock64(); ec_math += t - eprev; eprev = t; }
           if (valid && !(e_dbg & 1)) {
-            if (out) {
+            if (out && io_f32) {
+              float* op = reinterpret_cast<float*>(p.out) + pix * e_OC + c0;
+              st_global_256(op, r);
+              st_global_256(op + 8, r + 8);
+            } else if (out) {
               st_global_256(out + pix * e_OC + c0, reinterpret_cast<const uint32_t*>(ob));
             }
-            if (e_preact) {
+            if (e_preact && !io_f32) {
               st_global_256(reinterpret_cast<bf16*>(e_preact) + pix * e_OC + c0, reinterpret_cast<const uint32_t*>(pb));
             }
           }
@@ -1232,10 +1253,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         } else {
           float pre[16];
           // saved activations: packed bf16x2 -> float2
+          if (io_f32) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 f2 = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sv)[i]);
-            pre[2*i] = f2.x; pre[2*i+1] = f2.y;
+            for (int i = 0; i < 16; ++i) pre[i] = svf[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f2 = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sv)[i]);
+              pre[2*i] = f2.x; pre[2*i+1] = f2.y;
+            }
           }
           if (has_bn) {
             const float4* k0 = reinterpret_cast<const float4*>(s_k0 + c0);
@@ -1285,13 +1311,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               }
             }
           }
+          if (io_f32) {
+            if (valid && !(e_dbg & 1)) {
+              float* op = reinterpret_cast<float*>(p.out) + pix * e_OC + c0;
+              uint32_t sb[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 pk = __floats2bfloat162_rn(s1[2*i], s1[2*i+1]);
-            reinterpret_cast<__nv_bfloat162*>(ob)[i] = pk;
-            if (e_bn_sums) {
-              const float2 f2 = __bfloat1622float2(pk);
-              s1[2*i] = f2.x; s1[2*i+1] = f2.y;
+              for (int i = 0; i < 16; ++i) sb[i] = __float_as_uint(s1[i]);
+              st_global_256(op, sb);
+              st_global_256(op + 8, sb + 8);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(s1[2*i], s1[2*i+1]);
+              reinterpret_cast<__nv_bfloat162*>(ob)[i] = pk;
+              if (e_bn_sums) {
+                const float2 f2 = __bfloat1622float2(pk);
+                s1[2*i] = f2.x; s1[2*i+1] = f2.y;
+              }
             }
           }
           if (e_bn_sums) {
@@ -1303,7 +1340,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
           }
           const bool second_sum = has_bn;   // sum(g * xhat) only exists for BatchNorm layers; sum(g) alone = d(bias)
-          if (valid && !(e_dbg & 1)) {
+          if (valid && !(e_dbg & 1) && !io_f32) {
             st_global_256(out + pix * e_OC + c0, reinterpret_cast<const uint32_t*>(ob));
           }
           if (e_bn_sums) {
@@ -2497,6 +2534,7 @@ int conv_fwd_tc(const void* x, const float* w, void* y, int N, int H, int W, int
   p.out = y;
   p.scale = ep.scale; p.shift = ep.shift; p.act = ep.act; p.dropscale = ep.dropscale; p.stats = ep.stats;
   p.preact = ep.preact;
+  p.io_f32 = ep.io_f32;
   p.actmask_out = ep.actmask;
   rc = launch_engine(maps, p, KCc, 0, max_rows, st);
   return rc;
@@ -2692,6 +2730,7 @@ int conv_dgrad_tc(const void* dz, const float* w, void* dx, int N, int H, int W,
   p.BN = BN; p.kchunks = Cout / KCc;
   p.out = dx;
   p.saved = be.saved; p.act = be.act; p.dropscale = be.dropscale; p.bn_scale = be.bn_scale; p.bn_shift = be.bn_shift;
+  p.io_f32 = be.io_f32;
   p.bn_mean = be.bn_mean; p.bn_invstd = be.bn_invstd; p.bn_sums = be.bn_sums;
   p.actmask_in = be.actmask;
   return launch_engine(maps, p, KCc, 1, max_rows, st);
