@@ -172,3 +172,15 @@ def test_collate_batch_robust_cpu():
     assert tuple(x.shape) == (2, 1, 4, 4) and tuple(y.shape) == (2, 6, 2, 2) and int(x[1].sum()) == 16
     with pytest.raises(ValueError):
         collate_batch_robust([None])
+
+
+def test_gradient_clamp_keeps_the_constructor_clip_value(tmp_path):
+    """model.py:76-77: the reference's hook closes over the constructor argument; loading a checkpoint whose `clip_value`
+    buffer differs (from_pth builds with the default 1.0) must not change the clamp the kernels apply."""
+    import yogo_b200
+    net = yogo_b200.YOGO((64, 96), 0.05, 0.05, 7, clip_value=0.25)
+    assert net._clip_value_f == 0.25
+    path = tmp_path / "c.pth"
+    torch.save({"model_state_dict": net.state_dict(), "model_version": "base_model"}, path)
+    loaded, _ = yogo_b200.YOGO.from_pth(path)
+    assert float(loaded.clip_value) == 0.25 and loaded._clip_value_f == 1.0

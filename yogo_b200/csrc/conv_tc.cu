@@ -2374,6 +2374,15 @@ struct PackKey {
 };
 static std::map<PackKey, std::pair<void*, size_t>> g_pack_cache;
 static std::mutex g_pack_mutex;
+// Keys are raw weight pointers: models that come and go (or temporaries handed in as weights) would otherwise leave their
+// packed copies behind for ever.  Beyond 256 entries everything is released (after a device synchronisation - kernels in
+// flight may still read the buffers) and rebuilt on demand; a training run of one model never gets there.
+static void pack_cache_trim_locked() {
+  if (g_pack_cache.size() < 256) return;
+  cudaDeviceSynchronize();
+  for (auto& kv : g_pack_cache) cudaFree(kv.second.first);
+  g_pack_cache.clear();
+}
 
 static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int transpose, int g, cudaStream_t st) {
   // transpose == 2: stride-2 dgrad with folded column pairs (6 slices of [2 Cin][Cout])
@@ -2383,6 +2392,7 @@ static int pack_weights(const float* w, bf16** out, int Cout, int Cin, int trans
     int dev = 0;
     cudaGetDevice(&dev);
     PackKey key{w, transpose, dev};
+    if (g_pack_cache.find(key) == g_pack_cache.end()) pack_cache_trim_locked();
     auto it = g_pack_cache.find(key);
     if (it == g_pack_cache.end() || it->second.second < (size_t)total * sizeof(bf16)) {
       void* buf = nullptr;

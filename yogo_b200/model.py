@@ -86,7 +86,8 @@ class YOGO(nn.Module):
             "width_multiplier": float(self.width_multiplier) if hasattr(self, "width_multiplier") else 1.0,
             "height_multiplier": float(self.height_multiplier) if hasattr(self, "height_multiplier") else 1.0,
         }
-        self._clip_value_f = float(self.clip_value)
+        # (the gradient clamp keeps the CONSTRUCTOR's clip_value, like the reference, whose hook closes over the argument
+        # (model.py:76-77): a `clip_value` buffer loaded from a checkpoint does not change it)
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         out = super().load_state_dict(state_dict, *args, **kwargs)
