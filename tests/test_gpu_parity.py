@@ -1327,3 +1327,131 @@ def test_collate_batch_robust_on_device():
     assert a.is_cuda and np.array_equal(a.cpu().numpy(), ea) and np.array_equal(b.cpu().numpy().view(np.uint32), eb.view(np.uint32))
     with pytest.raises(ValueError):
         collate_batch_robust([None, None])
+
+
+def test_model_on_second_gpu_while_first_is_current():
+    """Every entry point switches to the device of its tensors (ATen does this for every op of the reference): a model, loss
+    and post-processing on cuda:1 while cuda:0 is current give the same results as on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    torch.manual_seed(0)
+    net0 = yogo_b200.YOGO((96, 128), O.ANCHOR_W, O.ANCHOR_H, 7)
+    sd = {k: v.clone() for k, v in net0.state_dict().items()}
+    img, lab = O.synth_images(2, 96, 128), O.synth_labels(2, 12, 16, 7, 10)
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        assert torch.cuda.current_device() == 0
+        net = yogo_b200.YOGO((96, 128), O.ANCHOR_W, O.ANCHOR_H, 7)
+        net.load_state_dict(sd)
+        net = net.to(dev)
+        net.train()
+        for m in net.model.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = 0.0
+        out = net(img.to(dev))
+        loss, _ = yogo_b200.YOGOLoss().to(dev)(out, lab.to(dev))
+        loss.backward()
+        rows, kc, _, counts = yogo_b200.format_preds_batch(out.detach())
+        torch.cuda.synchronize(dev)
+        res.append((out.detach().cpu(), float(loss), net.model[-1].weight.grad.cpu(), kc.cpu(), counts.cpu()))
+    assert torch.cuda.current_device() == 0
+    torch.testing.assert_close(res[1][0], res[0][0], rtol=1e-3, atol=1e-4)
+    assert abs(res[1][1] - res[0][1]) < 1e-3 * abs(res[0][1])
+    torch.testing.assert_close(res[1][2], res[0][2], rtol=2e-2, atol=1e-3)
+
+
+def test_outputs_of_the_other_kernels_stay_inside_their_buffers():
+    """Guard regions around the outputs of the first-layer, BatchNorm, head, loss and NMS kernels (the convolution engine has
+    its own test): nothing outside the tensors may be written, at sizes with ragged tails."""
+    import ctypes as C
+    lib = L.lib()
+    GUARD = 4096
+
+    def guarded(shape, dtype, fill):
+        numel = int(np.prod(shape))
+        buf = torch.full((numel + 2 * GUARD,), fill, dtype=dtype, device=DEV)
+        return buf, buf[GUARD:GUARD + numel].view(*shape)
+
+    def intact(buf, view, fill):
+        n = view.numel()
+        return bool((buf[:GUARD] == fill).all()) and bool((buf[GUARD + n:] == fill).all())
+
+    g = torch.Generator().manual_seed(4)
+    N, H, W, C1 = 3, 70, 90, 16
+    Ho, Wo = 35, 45
+    img = torch.randint(0, 256, (N, 1, H, W), dtype=torch.uint8, generator=g).to(DEV)
+    w1 = (torch.randn(C1, 1, 3, 3, generator=g) / 300).to(DEV)
+    sc, sh = (torch.rand(C1, generator=g) + 0.5).to(DEV), (torch.randn(C1, generator=g) * 0.1).to(DEV)
+    # first layer forward (tensor-core and generic kernels)
+    for impl in ("auto", "simt"):
+        L.set_conv_impl(impl)
+        try:
+            ybuf, y = guarded((N, Ho, Wo, C1), torch.bfloat16, 7.0)
+            ep = L.FwdEpilogue(sc.data_ptr(), sh.data_ptr(), L.ACT_LRELU, None, None, None, None)
+            L.check(lib.yg_conv_first_fwd(img.data_ptr(), L.YG_U8, w1.data_ptr(), y.data_ptr(), 1, N, H, W, 1, C1, 2, C.byref(ep), L.stream()))
+            torch.cuda.synchronize()
+            assert intact(ybuf, y, 7.0) and bool(torch.isfinite(y.float()).all()) and float(y.float().abs().sum()) > 0
+        finally:
+            L.set_conv_impl("auto")
+    # BatchNorm apply (+ sign mask) and backward apply, ragged pixel count
+    Cb, HW = 128, 97 * 13 + 5
+    yraw = torch.randn(N, HW, Cb, generator=g).to(DEV).bfloat16()
+    bsc, bsh = (torch.rand(Cb, generator=g) + 0.5).to(DEV), torch.randn(Cb, generator=g).to(DEV)
+    abuf, a = guarded((N, HW, Cb), torch.bfloat16, 7.0)
+    mbuf, m = guarded((N * HW * Cb // 8,), torch.uint8, 0xA5)
+    L.check(lib.yg_bn_act_apply(yraw.data_ptr(), a.data_ptr(), 1, N, HW, Cb, bsc.data_ptr(), bsh.data_ptr(), L.ACT_LRELU, None,
+                                m.data_ptr(), L.stream()))
+    gbuf, gg = guarded((N, HW, Cb), torch.bfloat16, 7.0)
+    gg.copy_(torch.randn(N, HW, Cb, generator=g).to(DEV).bfloat16())
+    sums = torch.zeros(2 * Cb, dtype=torch.float64, device=DEV)
+    mean, istd = torch.zeros(Cb, device=DEV), torch.ones(Cb, device=DEV)
+    L.check(lib.yg_bn_bwd_sums(gg.data_ptr(), yraw.data_ptr(), 1, N, HW, Cb, mean.data_ptr(), istd.data_ptr(), sums.data_ptr(), L.stream()))
+    dgb, dg = guarded((Cb,), torch.float32, 7.0)
+    dbb, db = guarded((Cb,), torch.float32, 7.0)
+    L.check(lib.yg_bn_bwd_apply(gg.data_ptr(), yraw.data_ptr(), 1, N, HW, Cb, sums.data_ptr(), bsc.data_ptr(), mean.data_ptr(),
+                                istd.data_ptr(), dg.data_ptr(), db.data_ptr(), 1.0, 1, L.stream()))
+    torch.cuda.synchronize()
+    assert intact(abuf, a, 7.0) and intact(mbuf, m, 0xA5) and intact(gbuf, gg, 7.0) and intact(dgb, dg, 7.0) and intact(dbb, db, 7.0)
+    # head forward + backward on an odd grid
+    Sy, Sx, Cl, nc = 13, 17, 128, 7
+    D = 5 + nc
+    xh = torch.randn(N, Sy, Sx, Cl, generator=g).to(DEV).bfloat16()
+    wh, bh = (torch.randn(D, Cl, 1, 1, generator=g) * 0.05).to(DEV), torch.zeros(D, device=DEV)
+    obuf, o = guarded((N, D, Sy, Sx), torch.float32, 7.0)
+    tbuf, t = guarded((N, Sy, Sx, D), torch.float32, 7.0)
+    L.check(lib.yg_head_fwd(xh.data_ptr(), 1, wh.data_ptr(), bh.data_ptr(), o.data_ptr(), t.data_ptr(), N, Sy, Sx, Cl, nc,
+                            0.04, 0.05, 1.0, 1.0, 0, None, None, L.stream()))
+    dpred = torch.randn(N, D, Sy, Sx, generator=g).to(DEV)
+    dxbuf, dx = guarded((N, Sy, Sx, Cl), torch.bfloat16, 7.0)
+    dwbuf, dw = guarded((D, Cl, 1, 1), torch.float32, 7.0)
+    dbbuf, dbh = guarded((D,), torch.float32, 7.0)
+    nb = lib.yg_head_bwd_workspace(N, Sy, Sx, Cl, nc)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
+    L.check(lib.yg_head_bwd(dpred.data_ptr(), t.data_ptr(), xh.data_ptr(), wh.data_ptr(), dx.data_ptr(), 1, dw.data_ptr(), dbh.data_ptr(),
+                            N, Sy, Sx, Cl, nc, 0.04, 0.05, 1.0, 1.0, None, 1.0, ws.data_ptr(), nb, L.stream()))
+    torch.cuda.synchronize()
+    assert intact(obuf, o, 7.0) and intact(tbuf, t, 7.0) and intact(dxbuf, dx, 7.0) and intact(dwbuf, dw, 7.0) and intact(dbbuf, dbh, 7.0)
+    # loss
+    lab = O.synth_labels(N, Sy, Sx, nc, 20).to(DEV)
+    pbuf, dp = guarded((N, D, Sy, Sx), torch.float32, 7.0)
+    o4buf, o4 = guarded((4,), torch.float32, 7.0)
+    nbl = lib.yg_yogo_loss_workspace(N, Sy, Sx)
+    wsl = torch.empty(max(nbl, 16), dtype=torch.uint8, device=DEV)
+    L.check(lib.yg_yogo_loss_fwd_bwd(o.data_ptr(), lab.data_ptr(), o4.data_ptr(), dp.data_ptr(), N, nc, Sy, Sx, 0.5, 5.0, 1.0, 0.01,
+                                     wsl.data_ptr(), nbl, L.stream()))
+    torch.cuda.synchronize()
+    assert intact(pbuf, dp, 7.0) and intact(o4buf, o4, 7.0) and bool(torch.isfinite(o4).all())
+    # threshold + NMS + counts
+    p = O.synth_sparse_preds(N, Sy, Sx, nc, 30).to(DEV)
+    cells = Sy * Sx
+    rbuf, rows = guarded((N, cells, D), torch.float32, 7.0)
+    kbuf, kc = guarded((N,), torch.int32, 77)
+    ibuf, ki = guarded((N, cells), torch.int32, 77)
+    cbuf, cnt = guarded((nc,), torch.int64, 77)
+    nbn = lib.yg_format_preds_workspace(N, nc, Sy, Sx)
+    wsn = torch.empty(max(nbn, 16), dtype=torch.uint8, device=DEV)
+    L.check(lib.yg_format_preds_batch(p.data_ptr(), N, nc, Sy, Sx, 0.5, 0.5, 0, 0.0, kc.data_ptr(), rows.data_ptr(), ki.data_ptr(),
+                                      cnt.data_ptr(), wsn.data_ptr(), nbn, L.stream()))
+    torch.cuda.synchronize()
+    assert intact(rbuf, rows, 7.0) and intact(kbuf, kc, 77) and intact(ibuf, ki, 77) and intact(cbuf, cnt, 77)
+    assert int(cnt.sum()) == int(kc.sum()) > 0
