@@ -428,7 +428,10 @@ extern "C" int yg_format_preds_batch(const float* preds, int B, int num_classes,
   int P = 1;
   while (P < cells) P <<= 1;
   const size_t smem = (size_t)P * sizeof(unsigned long long);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // the attribute is per device
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
     YG_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NMS_MAX_CELLS * sizeof(unsigned long long))));
     YG_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NMS_SCAN_SMEM_WORDS * sizeof(unsigned long long))));
