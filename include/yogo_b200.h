@@ -247,6 +247,14 @@ int yg_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_av
 int yg_adamw_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                       const float* hyper_dev, void* stream);
 
+/* ---- Dropout2d keep-scales of every block of a step + BatchNorm step counters, one launch -------------------------
+ * replaces nn.Dropout2d's mask draw (model_defns.py:44-57) and `num_batches_tracked += 1`.  out: `total` floats, the
+ * blocks' (N, C) scale matrices back to back; table (device): nblocks x int4 (offset, count, p as float bits, 0);
+ * state (device, 3 x uint64): [seed, call counter, 0] - the kernel advances the counter, so CUDA-graph replays draw
+ * fresh masks; counters (device): ncounters pointers to int64 `num_batches_tracked` buffers, each incremented by one. */
+int yg_dropout_scales(float* out, const void* table, int nblocks, int total, void* state, const void* counters,
+                      int ncounters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1455,3 +1455,42 @@ def test_outputs_of_the_other_kernels_stay_inside_their_buffers():
     torch.cuda.synchronize()
     assert intact(rbuf, rows, 7.0) and intact(kbuf, kc, 77) and intact(ibuf, ki, 77) and intact(cbuf, cnt, 77)
     assert int(cnt.sum()) == int(kc.sum()) > 0
+
+
+def test_dropout_scales_kernel_statistics_and_counters():
+    """yg_dropout_scales: Bernoulli(1 - p) keep decisions per (n, c) plane scaled by 1 / (1 - p) (nn.Dropout2d), fresh on every
+    call (also when replayed from a CUDA graph), and `num_batches_tracked += 1` for every training-mode BatchNorm."""
+    torch.manual_seed(0)
+    net = yogo_b200.YOGO((96, 128), O.ANCHOR_W, O.ANCHOR_H, 7).to(DEV)
+    net.train()
+    r = net._get_runner()
+    N = 512
+    a = {i: t.clone() for i, t in r._step_randoms(N, torch.device(DEV), True).items()}
+    b = {i: t.clone() for i, t in r._step_randoms(N, torch.device(DEV), True).items()}
+    ps = {i: blk.p_drop for i, blk in enumerate(r.plan.blocks) if blk.p_drop > 0}
+    assert set(a) == set(ps) == {1, 2, 3}
+    for i, p in ps.items():
+        assert tuple(a[i].shape) == (N, r.plan.blocks[i].cout)
+        vals = torch.unique(a[i])
+        assert len(vals) == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1.0 / (1.0 - p)) < 1e-6
+        frac = float((a[i] == 0).float().mean())
+        assert abs(frac - p) < 4 * (p * (1 - p) / a[i].numel()) ** 0.5 + 1e-3, (i, frac, p)
+        assert not torch.equal(a[i], b[i])                          # a new draw per call
+    assert int(net.model[0][1].num_batches_tracked) == 2 and int(net.model[4][1].num_batches_tracked) == 2
+    # graph replay: masks change between replays, counters advance
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        r._step_randoms(N, torch.device(DEV), True)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        out = r._step_randoms(N, torch.device(DEV), True)
+    g.replay(); torch.cuda.synchronize(); m1 = out[2].clone()
+    g.replay(); torch.cuda.synchronize(); m2 = out[2].clone()
+    assert not torch.equal(m1, m2)
+    assert int(net.model[0][1].num_batches_tracked) == 5
+    # eval mode: nothing is drawn or counted
+    net.eval()
+    assert r._step_randoms(4, torch.device(DEV), False) == {}
+    assert int(net.model[0][1].num_batches_tracked) == 5

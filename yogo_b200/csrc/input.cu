@@ -152,3 +152,69 @@ extern "C" int yg_format_labels_batch(const float* labels, const int* offsets, i
   YG_LAUNCH_CHECK("format_labels fill");
   return YG_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Dropout2d keep-scales of ALL blocks of a step in one launch (nn.Dropout2d(p), model_defns.py:44-57: whole (n, c)
+// planes are zeroed with probability p, the rest scaled by 1 / (1 - p)), plus the `num_batches_tracked += 1` of the
+// BatchNorm layers.  Replaces ~5 torch elementwise launches per block (rand, >=, float, div, contiguous) and one per counter.
+// Philox4x32-10 keyed by (seed, call counter, element): the counter lives in device memory and is advanced by the kernel
+// itself, so that a CUDA-graph replay draws fresh masks.  state = [seed, counter, ticket].
+// ------------------------------------------------------------------------------------------------
+namespace yg {
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+  const unsigned long long p = (unsigned long long)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    const uint32_t lo0 = mulhilo32(0xD2511F53u, ctr.x, &hi0), lo1 = mulhilo32(0xCD9E8D57u, ctr.z, &hi1);
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// table: per block (offset, count, p as float bits, unused), nblk <= 16
+__global__ void dropout_scales_kernel(float* __restrict__ out, const int4* __restrict__ table, int nblk, int total,
+                                      unsigned long long* __restrict__ state, long long* const* __restrict__ counters, int ncounters) {
+  const unsigned long long seed = state[0], call = state[1];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    float p = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+      const int4 t = table[b];
+      if (i >= t.x && i < t.x + t.y) p = __int_as_float(t.z);
+    }
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)i, 0u, (uint32_t)call, (uint32_t)(call >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);     // uniform in [0, 1)
+    out[i] = (u >= p) ? 1.f / (1.f - p) : 0.f;
+  }
+  // the last block to finish advances the call counter and the BatchNorm counters (every block has read `call` by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long done = atomicAdd(&state[2], 1ull);
+    if (done == gridDim.x - 1) {
+      state[2] = 0ull;
+      state[1] = call + 1ull;
+      for (int c = 0; c < ncounters; ++c) *counters[c] += 1;
+    }
+  }
+}
+}  // namespace yg
+
+extern "C" int yg_dropout_scales(float* out, const void* table, int nblocks, int total, void* state, const void* counters,
+                                 int ncounters, void* stream) {
+  YG_CHECK_ARG(state && nblocks >= 0 && nblocks <= 16 && total >= 0 && ncounters >= 0, "dropout_scales: bad arguments");
+  YG_CHECK_ARG(total == 0 || (out && table), "dropout_scales: null pointer");
+  const int grid = total > 0 ? yg::cdiv(total, 256) : 1;
+  yg::dropout_scales_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, (const int4*)table, nblocks, total,
+                                                                    (unsigned long long*)state, (long long* const*)counters, ncounters);
+  YG_LAUNCH_CHECK("dropout_scales");
+  return YG_OK;
+}

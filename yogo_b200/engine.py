@@ -144,16 +144,51 @@ class Runner:
         self.input_scale: Optional[float] = None
 
     # ---------------------------------------------------------------- helpers
+    def _step_randoms(self, N: int, device, want_grad: bool) -> Dict[int, torch.Tensor]:
+        """Dropout2d keep-scales of every training-mode Dropout2d block and the `num_batches_tracked += 1` of every
+        training-mode BatchNorm, in ONE launch (csrc/input.cu: Philox keyed by a seed drawn once from torch's generator and a
+        device-side call counter, so CUDA-graph replays draw fresh masks).  The mask values cannot match the reference's
+        draw; the distribution does."""
+        lib = L.lib()
+        blocks = [(i, b) for i, b in enumerate(self.plan.blocks) if b.p_drop > 0 and b.drop is not None and b.drop.training
+                  and not (self.drop_keep_override is not None and i in self.drop_keep_override)]
+        bns = [b.bn for b in self.plan.blocks if b.bn is not None and b.bn.training and b.bn.num_batches_tracked is not None
+               and b.bn.num_batches_tracked.is_cuda]
+        key = (N, str(device), tuple(i for i, _ in blocks), tuple(float(b.p_drop) for _, b in blocks),
+               tuple(b.num_batches_tracked.data_ptr() for b in bns))
+        st = getattr(self, "_rand_state", None)
+        if st is None or st["key"] != key:
+            import struct
+            offs, rows, off = {}, [], 0
+            for i, b in blocks:
+                cnt = N * b.cout
+                offs[i] = (off, cnt, b.cout)
+                rows.append([off, cnt, struct.unpack("i", struct.pack("f", float(b.p_drop)))[0], 0])
+                off += cnt
+            table = torch.tensor(rows if rows else [[0, 0, 0, 0]], dtype=torch.int32).to(device)
+            # derived from torch's seed without consuming its generator (reproducible under torch.manual_seed; runners differ)
+            Runner._seed_counter = getattr(Runner, "_seed_counter", 0) + 1
+            seed = ((torch.initial_seed() * 6364136223846793005 + 1442695040888963407 * Runner._seed_counter) % (2 ** 62)) \
+                if (st is None) else st["seed"]
+            state = st["state"] if (st is not None and st["state"].device == torch.device(device)) else \
+                torch.tensor([seed, 0, 0], dtype=torch.int64).to(device)
+            ptrs = torch.tensor([b.num_batches_tracked.data_ptr() for b in bns] or [0], dtype=torch.int64).to(device)
+            st = {"key": key, "offs": offs, "table": table, "total": off, "seed": seed, "state": state, "ptrs": ptrs, "nbn": len(bns)}
+            self._rand_state = st
+        out = torch.empty(max(st["total"], 1), dtype=torch.float32, device=device)
+        if st["total"] > 0 or st["nbn"] > 0:
+            L.check(lib.yg_dropout_scales(out.data_ptr(), st["table"].data_ptr(), len(st["offs"]), st["total"],
+                                          st["state"].data_ptr(), st["ptrs"].data_ptr(), st["nbn"], L.stream()))
+        self._bn_counted = {id(b) for b in bns}
+        return {i: out[o:o + c].view(N, co) for i, (o, c, co) in st["offs"].items()}
+
     def _dropscale(self, i: int, blk: ConvBlock, N: int, device, training: bool) -> Optional[torch.Tensor]:
         if blk.p_drop <= 0 or not training:
             return None
         if self.drop_keep_override is not None and i in self.drop_keep_override:
             keep = self.drop_keep_override[i].to(device=device, dtype=torch.float32)
-        else:
-            # Dropout2d: Bernoulli(1-p) per (n, c) plane (torch's Philox stream; the mask values
-            # cannot match the reference's draw, the distribution does)
-            keep = (torch.rand(N, blk.cout, device=device) >= blk.p_drop).float()
-        return (keep / (1.0 - blk.p_drop)).contiguous()
+            return (keep / (1.0 - blk.p_drop)).contiguous()
+        return self._scales[i]
 
     def _prep_input(self, x: torch.Tensor) -> Tuple[torch.Tensor, int]:
         if x.ndim == 3:
@@ -184,6 +219,7 @@ class Runner:
         if plan.blocks[0].cin != Cx:
             raise RuntimeError(f"expected input with {plan.blocks[0].cin} channels, got {Cx}")
         saved = {"x": x, "x_code": x_code, "blocks": [], "N": N, "dtype": dt}
+        self._scales = self._step_randoms(N, dev, want_grad)
         cur: Optional[torch.Tensor] = None  # NHWC activation
         h, w = H, W
         for i, blk in enumerate(plan.blocks):
@@ -271,7 +307,8 @@ class Runner:
                                                    float(bn.momentum), float(bn.eps), mean.data_ptr(),
                                                    invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                                    blk.cout, st))
-                        bn.num_batches_tracked += 1
+                        if id(bn) not in self._bn_counted:   # (counted by yg_dropout_scales when the buffer is on the GPU)
+                            bn.num_batches_tracked += 1
                     else:
                         # BN in eval mode inside a training graph (tuning=True, model.py:69-70)
                         L.check(lib.yg_bn_fold_eval(g.data_ptr(), b.data_ptr(), bn.running_mean.data_ptr(),
