@@ -108,6 +108,31 @@ class GraphedInference:
         return self.out
 
 
+class GraphedForward:
+    """Eval forward of one fixed batch shape as a CUDA-graph replay (the forward alone; `predict` applies whatever
+    post-processing its flags ask for to the static output, which is valid until the next call)."""
+
+    def __init__(self, model, batch_shape, dtype=torch.uint8, warmup: int = 2):
+        dev = next(model.parameters()).device
+        self.static_in = torch.zeros(tuple(batch_shape), dtype=dtype, device=dev)
+        with torch.cuda.device(dev):
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(max(1, warmup)):
+                    model(self.static_in)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.out = model(self.static_in)
+
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        self.static_in.copy_(images, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def _list_images(path_to_images: Path) -> List[Path]:
     p = Path(path_to_images)
     if p.is_file():
@@ -223,6 +248,7 @@ def predict(
         from tqdm import tqdm
 
         pbar = tqdm(unit="images", total=n_images)
+    graphed: dict = {}
     normalize = bool(model.normalize_images)
     if normalize:
         model.set_fused_input_scale(1.0 / 255.0)   # uint8 batches: the /255 happens inside the first-layer kernel
@@ -236,7 +262,15 @@ def predict(
         x = img_batch.to(dev, non_blocking=True)
         if normalize and x.dtype != torch.uint8:
             x = x.float() / 255.0
-        res = model(x)
+        # full batches replay the forward from a CUDA graph (a batch of one 772x1032 image is ~60 us of GPU work behind
+        # ~250 us of launches); the ragged last batch runs eagerly
+        if dev.type == "cuda" and tuple(x.shape) == (batch_size,) + tuple(x.shape[1:]) and n_images >= 2 * batch_size:
+            key = (tuple(x.shape), x.dtype)
+            if graphed.get("key") != key:
+                graphed["key"], graphed["fwd"] = key, GraphedForward(model, x.shape, x.dtype)
+            res = graphed["fwd"](x)
+        else:
+            res = model(x)
         if results is None and return_full_predictions:
             results = torch.zeros((n_images, res.shape[1], res.shape[2], res.shape[3]))
         if save_preds:
