@@ -905,12 +905,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               // wherever the Dropout2d scale is non-zero (and a dropped channel's gradient is zero whatever the bit says)
               // word i holds elements 2i (low half) and 2i+1 (high half): select bit 2i of the low and bit 2i+1 of the high
               // compare mask and OR everything together - one compare and one three-input logic op per word
+              // (one packed bf16x2 compare per word - HSET2 - instead of the four-instruction integer emulation of
+              // __vcmpgts2; bf16 > 0 is false for -0 / +0 exactly like the signed integer compare)
               uint32_t acc0 = 0, acc1 = 0;
+              const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const uint32_t sel = (1u << (2 * i)) | (1u << (2 * i + 17));
-                acc0 |= __vcmpgts2(ob32[i], 0u) & sel;
-                acc1 |= __vcmpgts2(ob32[8 + i], 0u) & sel;
+                acc0 |= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&ob32[i]), zero2) & sel;
+                acc1 |= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&ob32[8 + i]), zero2) & sel;
               }
               const unsigned long long bits =
                   (unsigned long long)(((acc0 & 0xFFFFu) | (acc0 >> 16)) | ((((acc1 & 0xFFFFu) | (acc1 >> 16))) << 16));
