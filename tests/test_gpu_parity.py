@@ -587,12 +587,14 @@ def test_silu_epilogues_vs_torch(shape, with_bn, impl):
 
 @pytest.mark.parametrize("Cout", [16, 32, 48])
 @pytest.mark.parametrize("act", [1, 2])
-def test_first_layer_tensor_core_kernels_vs_torch(Cout, act):
+@pytest.mark.parametrize("HW", [(70, 90), (71, 91), (64, 129)])
+def test_first_layer_tensor_core_kernels_vs_torch(Cout, act, HW):
     """1 -> 16 / 32 / 48 channels, stride 2, uint8 image (base / double_filters / triple_filters, model_defns.py:39, 139, 189):
     forward = conv * scale + shift -> activation -> Dropout2d scale; backward = raw sums P[c][t] = sum g x_t and sum g with
     g = da * act'(pre) * dropscale, both on mma.sync with split-bf16 weights (first_layer.cu)."""
     import ctypes as C
-    N, H, W = 3, 70, 90
+    # (even widths take the aligned 16-bit tap loads, odd widths the per-lane byte loads; 129 leaves a one-pixel row segment)
+    N, (H, W) = 3, HW
     g = torch.Generator().manual_seed(Cout + act)
     lib = L.lib()
     img = torch.randint(0, 256, (N, 1, H, W), dtype=torch.uint8, generator=g)
@@ -622,8 +624,8 @@ def test_first_layer_tensor_core_kernels_vs_torch(Cout, act):
     L.check(lib.yg_conv_first_bwd(xd.data_ptr(), L.YG_U8, wd.data_ptr(), da.data_ptr(), 1, N, H, W, 1, Cout, 2, C.byref(be),
                                   None, None, None, dw.data_ptr(), dsh.data_ptr(), 0.0, ws.data_ptr(), nb, L.stream()))
     # g is rounded to bf16 before the P = g . X product (2^-9 relative per term, random sign)
-    assert _rel(dw.cpu(), dw_ref) < 3e-3, _rel(dw.cpu(), dw_ref)
-    assert _rel(dsh.cpu(), ds_ref) < 3e-3
+    assert _rel(dw.cpu(), dw_ref) < 4e-3, _rel(dw.cpu(), dw_ref)
+    assert _rel(dsh.cpu(), ds_ref) < 4e-3
     # the SIMT kernels (any channel count) agree
     L.set_conv_impl("simt")
     try:
@@ -636,7 +638,7 @@ def test_first_layer_tensor_core_kernels_vs_torch(Cout, act):
     finally:
         L.set_conv_impl("auto")
     assert _rel(y2.float().cpu(), y.float().cpu()) < 4e-3
-    assert _rel(dw2.cpu(), dw_ref) < 3e-3 and _rel(dsh2.cpu(), ds_ref) < 3e-3
+    assert _rel(dw2.cpu(), dw_ref) < 4e-3 and _rel(dsh2.cpu(), ds_ref) < 4e-3
 
 
 def test_tensors_that_are_only_16_byte_aligned_take_the_generic_path():
