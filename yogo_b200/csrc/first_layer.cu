@@ -944,16 +944,27 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_gram_mma_kernel(const 
   auto row_addr = [](uint32_t base, int px, int half) { return base + (uint32_t)(px * 32 + ((half ^ ((px >> 2) & 1)) << 4)); };
   float D0[4] = {0.f, 0.f, 0.f, 0.f}, D1[4] = {0.f, 0.f, 0.f, 0.f};
   // D0: (a = g | g+8, b = 2j, 2j+1);  D1: (a, b = 8 + 2j, 9 + 2j): b = 8 and the ones column b = 9 (= S[a]) for j == 0
+  // The fp32 fragments hold exact integers < 2^24; every 7 iterations they move into 64-bit integer registers (8 conversions
+  // and adds per lane instead of shared-memory fp64 atomics), which are reduced once
+  // at the end.
+  unsigned long long I0[4] = {0ull, 0ull, 0ull, 0ull}, I1[4] = {0ull, 0ull, 0ull, 0ull};
   auto flush = [&]() {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int a = g + (e >> 1) * 8, b = 2 * j + (e & 1);
-      if (a <= 8 && a <= b) atomicAdd(&red[9 + a * 9 - a * (a - 1) / 2 + (b - a)], (double)D0[e]);
-      if (a <= 8 && j == 0) {
-        if ((e & 1) == 0) atomicAdd(&red[9 + a * 9 - a * (a - 1) / 2 + (8 - a)], (double)D1[e]);   // G[a][8]
-        else atomicAdd(&red[a], (double)D1[e]);                                                         // S[a]
-      }
+      I0[e] += (unsigned long long)__float2uint_rn(D0[e]);
+      I1[e] += (unsigned long long)__float2uint_rn(D1[e]);
       D0[e] = 0.f; D1[e] = 0.f;
+    }
+  };
+  auto reduce = [&]() {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int a = g + (e >> 1) * 8, b = 2 * j + (e & 1);
+      if (a <= 8 && a <= b) atomicAdd(&red[9 + a * 9 - a * (a - 1) / 2 + (b - a)], (double)I0[e]);
+      if (a <= 8 && j == 0) {
+        if ((e & 1) == 0) atomicAdd(&red[9 + a * 9 - a * (a - 1) / 2 + (8 - a)], (double)I1[e]);   // G[a][8]
+        else atomicAdd(&red[a], (double)I1[e]);                                                         // S[a]
+      }
     }
   };
   const int spr = (Wo + 31) >> 5, nseg = Ho * spr;
@@ -993,6 +1004,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 8) first_gram_mma_kernel(const 
     }
   }
   flush();
+  reduce();   // (per-lane totals stay below 2^53 for any image this kernel accepts: exact in fp64)
   __syncthreads();
   if (threadIdx.x < 54) atomicAdd(&gram[threadIdx.x], red[threadIdx.x]);
 }
