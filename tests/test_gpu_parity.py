@@ -1496,3 +1496,24 @@ def test_dropout_scales_kernel_statistics_and_counters():
     net.eval()
     assert r._step_randoms(4, torch.device(DEV), False) == {}
     assert int(net.model[0][1].num_batches_tracked) == 5
+
+
+def test_steps_from_host_equals_step_and_handles_a_ragged_last_batch():
+    """DataParallelTrainer.steps_from_host: pinned host batches copied straight into the graph's two input slots give the same
+    parameters as feeding device batches to `step`, including a last batch of another size (eager fallback)."""
+    imgs = [O.synth_images(4, 96, 128, seed=s) for s in range(4)] + [O.synth_images(2, 96, 128, seed=9)]
+    labs = [O.synth_labels(4, 12, 16, 7, 10, seed=s) for s in range(4)] + [O.synth_labels(2, 12, 16, 7, 10, seed=9)]
+    net_a, tr_a = _make_trainer()
+    net_b, tr_b = _make_trainer()
+    tr_a.enable_cuda_graph(imgs[0].to(DEV), labs[0].to(DEV), slots=2)
+    tr_b.enable_cuda_graph(imgs[0].to(DEV), labs[0].to(DEV))
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in zip(imgs, labs)]
+    la = [float(l.detach()) for l in tr_a.steps_from_host(iter(host))]
+    lb = [float(tr_b.step(x.to(DEV), y.to(DEV)).detach()) for x, y in zip(imgs, labs)]
+    assert len(la) == len(lb) == 5 and tr_a.step_count == tr_b.step_count == 5
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 1e-2 * abs(b), (la, lb)
+    assert abs(la[0] - lb[0]) <= 1e-5 * abs(lb[0])
+    # (after five Adam steps sign flips of ~0 gradients have spread: compared by norm, as in the multi-rank check)
+    drift = float((tr_a.flat_p - tr_b.flat_p).norm() / tr_b.flat_p.norm())
+    assert drift < 2e-3, drift

@@ -201,7 +201,6 @@ class DataParallelTrainer:
 
     def optimizer_step(self) -> None:
         self.step_count += 1
-        b1, b2 = self.betas
         with torch.cuda.device(self.flat_p.device):
             self._adamw_host()
 
@@ -334,24 +333,38 @@ class DataParallelTrainer:
                 ev.record(copy)
                 ready_ev[slot] = ev
 
+        def fits(batch):
+            return batch is not None and tuple(batch[0].shape) == tuple(self._static_imgs.shape) and \
+                tuple(batch[1].shape) == tuple(self._static_labels.shape)
+
         it = iter(batches)
         nxt = next(it, None)
         slot = 0
-        if nxt is not None:
+        if fits(nxt):
             ev0 = torch.cuda.Event()
             ev0.record(cur)
             free_ev = [ev0] * nslot                     # earlier work on the main stream may still read the slots
             issue(0, nxt)
         while nxt is not None:
+            if not fits(nxt):
+                # a batch of another shape (the ragged last batch of an epoch): eager step, no prefetch
+                yield self.step(nxt[0].to(dev, non_blocking=True), nxt[1].to(dev, non_blocking=True))
+                nxt = next(it, None)
+                if fits(nxt):
+                    ev0 = torch.cuda.Event()
+                    ev0.record(cur)
+                    free_ev[slot] = ev0
+                    issue(slot, nxt)
+                continue
             nxt2 = next(it, None)
-            if nxt2 is not None and nslot > 1:
+            if fits(nxt2) and nslot > 1:
                 issue((slot + 1) % nslot, nxt2)         # overlaps with the replay below
             cur.wait_event(ready_ev[slot])
             loss = self.step_static(slot)
             ev = torch.cuda.Event()
             ev.record(cur)
             free_ev[slot] = ev
-            if nxt2 is not None and nslot == 1:
+            if fits(nxt2) and nslot == 1:
                 issue(0, nxt2)
             yield loss
             nxt = nxt2
