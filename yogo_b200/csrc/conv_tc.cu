@@ -97,6 +97,10 @@ struct TcParams {
   // offsets inside a stage in 16-byte descriptor units and the K-step mask; ebeg[g] = first entry of group g
   uint32_t tab_a[27], tab_b[27], tab_km[27], tab_hi[27];   // tab_hi: high descriptor word of A (SBO = box row pitch)
   int ebeg[TC_MAX_GROUPS + 1];
+  // W-folded layers (structural-zero K steps, one group, resident weights): the MMAs of a K chunk as one flat host-built
+  // list (A offset | B offset << 16, 16-byte units), so the issue loop is load - add - issue instead of a per-tap mask walk
+  int flat_on, flat_n[2];
+  uint32_t flat_ab[2][36];
   int shift_exp[TC_MAX_GROUPS];   // experiment (option bit 12): extra A start offset in bytes per group
   int io_f32;  // the epilogue reads `saved` and writes `out` / `preact` as fp32 (split-bf16 "x3" convolutions of fp32 tensors, see x3.cu)
   int debug;   // profiling knobs (tools/bench_conv.py): 1 = no global stores, 2 = no MMA issue, 4 = epilogue skips TMEM loads and math, 8 = no TMA loads, 16 = MMA-warp cycle counters -> g_tc_dbg
@@ -246,6 +250,13 @@ __device__ __forceinline__ void umma_bf16_lh_p(uint32_t d_tmem, uint32_t a_lo, u
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(hi), "r"(accum), "r"(leader)
       : "memory");
 }
+// v * 0.01 where `bit` of `word` is clear (LeakyReLU backward from the producer's sign bits), v otherwise
+__device__ __forceinline__ float mul_slope_if_clear(float v, uint32_t word, uint32_t bit) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.eq.u32 p, t, 0;\n\t@p mul.f32 %0, %0, 0f3C23D70A;\n\t}"
+      : "+f"(v) : "r"(word), "r"(bit));
+  return v;
+}
+
 __device__ __forceinline__ void umma_bf16_lh2_p(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                                 uint32_t idesc, uint32_t accum, uint32_t leader) {
   asm volatile(
@@ -674,6 +685,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const uint32_t ast = desc0_lo + (uint32_t)stage * stage_units;
           const uint32_t bst = b_resident ? bres0_lo + (uint32_t)kc * tap_units : ast + a_units;
           const int e1 = p.ebeg[g0 + gpi];
+          if (!CTA2 && p.flat_on) {
+            // measured on the W-folded 16-channel layer: the mask walk below cost ~80 cycles per 48-cycle MMA
+            const int nf = (p.debug & 2) ? 0 : p.flat_n[kc];
+            const uint32_t a_hi = p.tab_hi[0];
+#pragma unroll 6
+            for (int i = 0; i < nf; ++i) {
+              const uint32_t ab = p.flat_ab[kc][i];
+              umma_bf16_lh2_p(d_tmem, ast + (ab & 0xFFFFu), a_hi, bres0_lo + (ab >> 16), desc_hi, idesc, started, leader);
+              started = 1u;
+            }
+          } else
           for (int e = p.ebeg[g0]; e < e1; ++e) {
             // descriptors advance by 32 bytes (2 units of 16 B) per K step
             const uint32_t ad0 = ast + p.tab_a[e], bd0 = bst + p.tab_b[e], a_hi = p.tab_hi[e];
@@ -867,6 +889,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         bf16* orow = out + pix * e_OC + nt * BN;
         unsigned long long* mrow = e_mask_out ? reinterpret_cast<unsigned long long*>(
             reinterpret_cast<unsigned char*>(e_mask_out) + ((pix * e_OC + nt * BN) >> 3)) : nullptr;
+        const float slope1 = e_act == YG_ACT_LRELU ? 0.01f : 1.f;
+        const float2 slope2 = make_float2(slope1, slope1);
         for (int j = jb; j < j_end; j += 4) {
           unsigned long long mb64 = 0ull;
 #pragma unroll
@@ -876,28 +900,47 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             tmem_ld16(taddr0 + (uint32_t)(jq * 16), ra);
             tmem_ld16(taddr0 + (uint32_t)(jq * 16 + 16), rb);
             const int c0 = nt * BN + jq * 16;
-            float v[32], k[32];
+            // packed fp32 arithmetic (FADD2 / FMUL2: two IEEE operations per issue slot, same results as the scalar
+            // forms): the epilogue warps are bound by their issue slots, not by the fp32 pipe
+            float2 v[16], k[16];
             {
               const float4* k4 = reinterpret_cast<const float4*>(s_k1 + c0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; k[4*i] = t4.x; k[4*i+1] = t4.y; k[4*i+2] = t4.z; k[4*i+3] = t4.w; }
+              for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; k[2*i] = make_float2(t4.x, t4.y); k[2*i+1] = make_float2(t4.z, t4.w); }
             }
             tmem_ld_wait32(ra, rb);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(ra[i]) + k[i]; v[16 + i] = __uint_as_float(rb[i]) + k[16 + i]; }
-            if (e_act == YG_ACT_LRELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
+            for (int i = 0; i < 8; ++i) {
+              v[i] = __fadd2_rn(make_float2(__uint_as_float(ra[2*i]), __uint_as_float(ra[2*i+1])), k[i]);
+              v[8 + i] = __fadd2_rn(make_float2(__uint_as_float(rb[2*i]), __uint_as_float(rb[2*i+1])), k[8 + i]);
             }
-            if (e_dropscale) {
-              const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+            {
+              // no activation = slope 1 (max(v, 1 * v) is v): no branch, so no register shuffling where the two flavours would meet
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
+              for (int i = 0; i < 16; ++i) {
+                const float2 t = __fmul2_rn(v[i], slope2);
+                v[i].x = fmaxf(v[i].x, t.x); v[i].y = fmaxf(v[i].y, t.y);
+              }
+            }
+            if (ds_smem) {   // (two copies: a pointer that may be shared or global costs generic loads and their address setup)
+              const float4* k4 = reinterpret_cast<const float4*>(s_ds + half * 256 + c0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 t4 = k4[i];
+                v[2*i] = __fmul2_rn(v[2*i], make_float2(t4.x, t4.y)); v[2*i+1] = __fmul2_rn(v[2*i+1], make_float2(t4.z, t4.w));
+              }
+            } else if (e_dropscale) {
+              const float4* k4 = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 t4 = __ldg(k4 + i);
+                v[2*i] = __fmul2_rn(v[2*i], make_float2(t4.x, t4.y)); v[2*i+1] = __fmul2_rn(v[2*i+1], make_float2(t4.z, t4.w));
+              }
             }
             __align__(16) uint32_t ob32[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(v[i].x, v[i].y);
               ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
             }
             if (e_mask_out) {
@@ -937,22 +980,36 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           uint32_t word = mk[0];
 #pragma unroll
           for (int w = 1; w < 8; ++w) word = (wi == w) ? mk[w] : word;
-          float v[32];
+          float2 v[16];
           tmem_ld_wait32(ra, rb);
+          // slope where the sign bit is clear: a predicated multiply (x * 1 is x, so skipping it changes nothing), then the
+          // Dropout2d scales as packed multiplies - 2.5 issue slots per element instead of 4 (bit test, select, two multiplies)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = __uint_as_float(ra[i]) * (((word >> i) & 1u) ? 1.f : 0.01f);
-            v[16 + i] = __uint_as_float(rb[i]) * (((word >> (16 + i)) & 1u) ? 1.f : 0.01f);
+          for (int i = 0; i < 8; ++i) {
+            v[i] = make_float2(mul_slope_if_clear(__uint_as_float(ra[2*i]), word, 1u << (2*i)),
+                               mul_slope_if_clear(__uint_as_float(ra[2*i+1]), word, 1u << (2*i+1)));
+            v[8 + i] = make_float2(mul_slope_if_clear(__uint_as_float(rb[2*i]), word, 1u << (16 + 2*i)),
+                                   mul_slope_if_clear(__uint_as_float(rb[2*i+1]), word, 1u << (16 + 2*i+1)));
           }
-          if (e_dropscale) {
-            const float4* k4 = reinterpret_cast<const float4*>(ds_smem ? s_ds + half * 256 + c0 : dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+          if (ds_smem) {   // (two copies: a pointer that may be shared or global costs generic loads and their address setup)
+            const float4* k4 = reinterpret_cast<const float4*>(s_ds + half * 256 + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float4 t4 = k4[i]; v[4*i] *= t4.x; v[4*i+1] *= t4.y; v[4*i+2] *= t4.z; v[4*i+3] *= t4.w; }
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = k4[i];
+              v[2*i] = __fmul2_rn(v[2*i], make_float2(t4.x, t4.y)); v[2*i+1] = __fmul2_rn(v[2*i+1], make_float2(t4.z, t4.w));
+            }
+          } else if (e_dropscale) {
+            const float4* k4 = reinterpret_cast<const float4*>(dsrow + (e_OC == e_OCr ? c0 : c0 - fdiv(c0, p.fd_ocr) * e_OCr));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = __ldg(k4 + i);
+              v[2*i] = __fmul2_rn(v[2*i], make_float2(t4.x, t4.y)); v[2*i+1] = __fmul2_rn(v[2*i+1], make_float2(t4.z, t4.w));
+            }
           }
           __align__(16) uint32_t ob32[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[i].x, v[i].y);
             ob32[i] = *reinterpret_cast<const uint32_t*>(&pk);
           }
           if (valid && !(e_dbg & 1)) {
@@ -2245,6 +2302,30 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
         }
         p.ebeg[gi + 1] = e;
       }
+    }
+  }
+  p.flat_on = 0;
+  if (!(g_tc_options & (1 << 22)) && p.b_resident && !p.cta2 && p.ncls == 1 && p.cls[0].ng == 1 && p.kchunks <= 2) {
+    const int ksteps = KCc / 16, ne = p.ebeg[p.cls[0].g0 + 1];
+    const uint32_t tap_units = (uint32_t)p.b_tap_bytes >> 4;
+    bool masked = false;
+    for (int e = p.ebeg[p.cls[0].g0]; e < ne; ++e) masked = masked || p.tab_km[e] != 0xFFFFFFFFu;
+    if (masked && p.cls[0].g0 == 0) {
+      bool fits = true;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        int n = 0;
+        for (int e = 0; e < ne; ++e) {
+          const unsigned km = p.tab_km[e] == 0xFFFFFFFFu ? (1u << ksteps) - 1u : (p.tab_km[e] >> (kc * ksteps)) & ((1u << ksteps) - 1u);
+          for (int k = 0; k < ksteps; ++k) {
+            if (!((km >> k) & 1u)) continue;
+            const uint32_t a = p.tab_a[e] + 2u * k, b = p.tab_b[e] + (uint32_t)kc * tap_units + 2u * k;
+            if (n >= 36 || a > 0xFFFFu || b > 0xFFFFu) { fits = false; break; }
+            p.flat_ab[kc][n++] = a | (b << 16);
+          }
+        }
+        p.flat_n[kc] = n;
+      }
+      p.flat_on = fits ? 1 : 0;
     }
   }
   p.error_flag = g_error_flag;
