@@ -97,10 +97,13 @@ struct TcParams {
   // offsets inside a stage in 16-byte descriptor units and the K-step mask; ebeg[g] = first entry of group g
   uint32_t tab_a[27], tab_b[27], tab_km[27], tab_hi[27];   // tab_hi: high descriptor word of A (SBO = box row pitch)
   int ebeg[TC_MAX_GROUPS + 1];
-  // W-folded layers (structural-zero K steps, one group, resident weights): the MMAs of a K chunk as one flat host-built
-  // list (A offset | B offset << 16, 16-byte units), so the issue loop is load - add - issue instead of a per-tap mask walk
-  int flat_on, flat_n[2];
-  uint32_t flat_ab[2][36];
+  // The same table flattened to one word per MMA (A offset | B offset << 16, 16-byte units; K steps with structurally zero
+  // weights of W-folded layers left out), so the issue loop is load - add - issue instead of a per-tap mask walk.
+  // flat_rng[L][g] = first MMA of group g in list L; W-folded layers have one list per K chunk (L = kc, at most 2),
+  // everything else one list for all chunks.
+  int flat_on, flat_perkc;
+  int flat_rng[2][TC_MAX_GROUPS + 1];
+  uint32_t flat_ab[108];
   int shift_exp[TC_MAX_GROUPS];   // experiment (option bit 12): extra A start offset in bytes per group
   int io_f32;  // the epilogue reads `saved` and writes `out` / `preact` as fp32 (split-bf16 "x3" convolutions of fp32 tensors, see x3.cu)
   int debug;   // profiling knobs (tools/bench_conv.py): 1 = no global stores, 2 = no MMA issue, 4 = epilogue skips TMEM loads and math, 8 = no TMA loads, 16 = MMA-warp cycle counters -> g_tc_dbg
@@ -685,14 +688,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const uint32_t ast = desc0_lo + (uint32_t)stage * stage_units;
           const uint32_t bst = b_resident ? bres0_lo + (uint32_t)kc * tap_units : ast + a_units;
           const int e1 = p.ebeg[g0 + gpi];
-          if (!CTA2 && p.flat_on) {
+          if (p.flat_on) {
             // measured on the W-folded 16-channel layer: the mask walk below cost ~80 cycles per 48-cycle MMA
-            const int nf = (p.debug & 2) ? 0 : p.flat_n[kc];
-            const uint32_t a_hi = p.tab_hi[0];
-#pragma unroll 6
-            for (int i = 0; i < nf; ++i) {
-              const uint32_t ab = p.flat_ab[kc][i];
-              umma_bf16_lh2_p(d_tmem, ast + (ab & 0xFFFFu), a_hi, bres0_lo + (ab >> 16), desc_hi, idesc, started, leader);
+            const int L = p.flat_perkc ? kc : 0;
+            const int i0 = p.flat_rng[L][g0], i1 = (p.debug & 2) ? i0 : p.flat_rng[L][g0 + gpi];
+            const uint32_t a_hi = p.tab_hi[p.ebeg[g0]];
+#pragma unroll 4
+            for (int i = i0; i < i1; ++i) {
+              const uint32_t ab = p.flat_ab[i];
+              if (CTA2) umma2_bf16_lh2_p(d_tmem, ast + (ab & 0xFFFFu), a_hi, bst + (ab >> 16), desc_hi, idesc, started, leader);
+              else umma_bf16_lh2_p(d_tmem, ast + (ab & 0xFFFFu), a_hi, bst + (ab >> 16), desc_hi, idesc, started, leader);
               started = 1u;
             }
           } else
@@ -2305,28 +2310,34 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
     }
   }
   p.flat_on = 0;
-  if (!(g_tc_options & (1 << 22)) && p.b_resident && !p.cta2 && p.ncls == 1 && p.cls[0].ng == 1 && p.kchunks <= 2) {
-    const int ksteps = KCc / 16, ne = p.ebeg[p.cls[0].g0 + 1];
-    const uint32_t tap_units = (uint32_t)p.b_tap_bytes >> 4;
-    bool masked = false;
-    for (int e = p.ebeg[p.cls[0].g0]; e < ne; ++e) masked = masked || p.tab_km[e] != 0xFFFFFFFFu;
-    if (masked && p.cls[0].g0 == 0) {
-      bool fits = true;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        int n = 0;
-        for (int e = 0; e < ne; ++e) {
-          const unsigned km = p.tab_km[e] == 0xFFFFFFFFu ? (1u << ksteps) - 1u : (p.tab_km[e] >> (kc * ksteps)) & ((1u << ksteps) - 1u);
+  if (!(g_tc_options & (1 << 22))) {
+    const int ksteps = KCc / 16;
+    bool masked = false, ok = true;
+    for (int e = 0; e < p.ebeg[ngroups_all]; ++e) masked = masked || p.tab_km[e] != 0xFFFFFFFFu;
+    // every MMA of a pipeline item shares the high A descriptor word of the item's first entry
+    for (int c = 0; c < p.ncls && ok; ++c)
+      for (int g0 = p.cls[c].g0; g0 < p.cls[c].g0 + p.cls[c].ng; g0 += p.cls[c].gpi)
+        for (int e = p.ebeg[g0]; e < p.ebeg[std::min(g0 + p.cls[c].gpi, ngroups_all)]; ++e) ok = ok && p.tab_hi[e] == p.tab_hi[p.ebeg[g0]];
+    const int nlists = masked ? p.kchunks : 1;
+    if (nlists > 2) ok = false;
+    int n = 0;
+    for (int L = 0; L < nlists && ok; ++L) {
+      for (int g = 0; g < ngroups_all && ok; ++g) {
+        p.flat_rng[L][g] = n;
+        for (int e = p.ebeg[g]; e < p.ebeg[g + 1] && ok; ++e) {
+          const unsigned km = p.tab_km[e] == 0xFFFFFFFFu ? (1u << ksteps) - 1u : (p.tab_km[e] >> (L * ksteps)) & ((1u << ksteps) - 1u);
           for (int k = 0; k < ksteps; ++k) {
             if (!((km >> k) & 1u)) continue;
-            const uint32_t a = p.tab_a[e] + 2u * k, b = p.tab_b[e] + (uint32_t)kc * tap_units + 2u * k;
-            if (n >= 36 || a > 0xFFFFu || b > 0xFFFFu) { fits = false; break; }
-            p.flat_ab[kc][n++] = a | (b << 16);
+            const uint32_t a = p.tab_a[e] + 2u * k, b = p.tab_b[e] + 2u * k;
+            if (n >= 108 || a > 0xFFFFu || b > 0xFFFFu) { ok = false; break; }
+            p.flat_ab[n++] = a | (b << 16);
           }
         }
-        p.flat_n[kc] = n;
       }
-      p.flat_on = fits ? 1 : 0;
+      p.flat_rng[L][ngroups_all] = n;
     }
+    p.flat_perkc = masked ? 1 : 0;
+    p.flat_on = ok ? 1 : 0;
   }
   p.error_flag = g_error_flag;
   p.debug = (g_tc_options >> 7) & 31;
