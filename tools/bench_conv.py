@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from yogo_b200 import _lib as L  # noqa: E402
+if os.environ.get("YOGO_B200_LIB_ALT"):   # A/B runs of two builds on the same box
+    L.LIB_PATH = os.environ["YOGO_B200_LIB_ALT"]
 
 # base_model layers 2..7: (H, W, Cin, Cout, stride)
 LAYERS = {2: (386, 516, 16, 32, 1), 3: (386, 516, 32, 64, 2), 4: (193, 258, 64, 128, 1), 5: (193, 258, 128, 128, 2),
