@@ -100,6 +100,7 @@ def main():
                 rec["mma_warp_cycles_per_item"] = {k: round(float(d[:, i].mean() / items), 1)
                                                    for i, k in enumerate(["wait_tempty", "wait_full", "issue", "commit", "rest"])}
                 rec["items_per_cta"] = items
+                rec["mma_warp_loop_entry_exit_cycles"] = [round(float(d[:, 6].mean())), round(float(d[:, 7].mean())), round(float(d[:, 7].max()))]
                 tiles = max(d[:, 14].mean(), 1.0)
                 rec["epi_warp_cycles_per_tile"] = {k: round(float(d[:, 8 + i].mean() / tiles), 1)
                                                    for i, k in enumerate(["wait_tfull", "ld_wait", "pre", "math", "store", "rest"])}

@@ -473,6 +473,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   // parameters inside a role is warp-uniform (uniform registers feed UTCHMMA / UTMALDG directly)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int BN = p.BN;
+  const long long t_kernel0 = (p.debug & 16) ? clock64() : 0;
 
   // CTA pair: rank 0 (leader) issues the MMAs for both; every barrier the MMA warp waits on lives in the leader
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
@@ -667,6 +668,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool prof = (p.debug & 16) != 0;
     const uint32_t leader = elect_one();
     long long c_tempty = 0, c_full = 0, c_issue = 0, c_commit = 0, c_rest = 0, c_items = 0, tprev = clock64();
+    const long long t_loop0 = tprev;
     for (int tile = blockIdx.x; tile < total_tiles && cta_rank == 0; tile += gridDim.x) {   // pair: the leader issues
       long long ta = 0;
       if (prof) ta = clock64();
@@ -745,6 +747,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (prof && lane == 0 && blockIdx.x < 256) {
       unsigned long long* d = g_tc_dbg + blockIdx.x * 16;
       d[0] = c_tempty; d[1] = c_full; d[2] = c_issue; d[3] = c_commit; d[4] = c_rest; d[5] = c_items;
+      d[6] = (unsigned long long)(t_loop0 - t_kernel0); d[7] = (unsigned long long)(clock64() - t_kernel0);   // loop entry, loop exit
     }
   } else if (warp == PW + 9) {
     // ===================================================================== L2 prefetch warp
