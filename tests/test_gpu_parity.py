@@ -44,6 +44,20 @@ def test_loss_matches_reference_golden(golden_dir, case):
     np.testing.assert_allclose(pred.grad.cpu().numpy(), z[f"{case}_dpred"], rtol=1e-3, atol=2e-6)
 
 
+def test_loss_and_grad_equals_the_autograd_route(golden_dir):
+    # the trainer's direct route: same kernel launch, gradient handed over without the autograd `grad_out * dpred` pass
+    z = _load(golden_dir, "loss.npz")
+    pred = torch.from_numpy(z["loss1_pred"]).to(DEV).requires_grad_(True)
+    label = torch.from_numpy(z["loss1_label"]).to(DEV)
+    loss_fn = yogo_b200.YOGOLoss().to(DEV)
+    loss, comps = loss_fn(pred, label)
+    loss.backward()
+    loss2, comps2, dpred = loss_fn.loss_and_grad(pred.detach(), label)
+    assert loss2.item() == loss.item()
+    assert dict(comps2) == dict(comps)
+    assert torch.equal(dpred, pred.grad)
+
+
 def test_loss_full_size_vs_oracle_and_scaling_property():
     # BASELINE size: 12,513 cells per image, 300 labels per image
     N = 8

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_cg_kernel(T* __restrict__ g,
 // MODE 1: sum(g), sum(g * xhat) with xhat = (y - mean) * invstd (BatchNorm backward).  One streaming pass at HBM speed
 // (cheaper than a 31-shuffle transpose-reduce per 16-column chunk in the epilogue of the producing convolution).
 // Thread t owns the 8-channel group t % (C/8) and pixels t / (C/8) + k * stride.
-template <typename T, int MODE>
+template <typename T, int MODE, int U = 4>
 __global__ void __launch_bounds__(256) bn_colsums_kernel(const T* __restrict__ a, const T* __restrict__ y, long long npix, int C,
                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                                          double* __restrict__ sums) {
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) bn_colsums_kernel(const T* __restrict__ a
   }
   if (pl < lanes) {
     constexpr int V = (int)(sizeof(T) * 8 / 16);
-    constexpr int U = 4;   // independent 16-byte loads in flight per thread; the per-thread summation order is unchanged
+    // U independent 16-byte loads in flight per thread; the per-thread summation order is unchanged
     const long long pstride = (long long)gridDim.x * lanes;
     for (long long px0 = (long long)blockIdx.x * lanes + pl; px0 < npix; px0 += U * pstride) {
       __align__(16) T av[U][8];
@@ -380,10 +380,12 @@ static int bn_colsums(const void* a, const void* y, int dtype, long long npix, i
   if (npix == 0) return YG_OK;
   const int lanes = 256 / (C / 8);
   long long want = (npix + lanes - 1) / lanes;
-  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  // two blocks per SM: measured best on 205 MB tensors (fewer blocks = fewer fp64 atomics per address at the end; 8 per SM: 47.5 / 74.4 us,
+  // 2 per SM with 8 loads in flight for the statistics pass: 39.4 / 68.3 us = 5.2 / 6.0 TB/s)
+  const int blocks = (int)(want < 148 * 2 ? want : 148 * 2);
   const size_t sm = (size_t)lanes * 2 * C * sizeof(float);   // <= 256/(C/8) * 2C * 4 = 16 KB
   if (dtype == YG_BF16) {
-    if (mode == 0) bn_colsums_kernel<bf16, 0><<<blocks, 256, sm, st>>>((const bf16*)a, nullptr, npix, C, nullptr, nullptr, sums);
+    if (mode == 0) bn_colsums_kernel<bf16, 0, 8><<<blocks, 256, sm, st>>>((const bf16*)a, nullptr, npix, C, nullptr, nullptr, sums);
     else bn_colsums_kernel<bf16, 1><<<blocks, 256, sm, st>>>((const bf16*)a, (const bf16*)y, npix, C, mean, invstd, sums);
   } else {
     if (mode == 0) bn_colsums_kernel<float, 0><<<blocks, 256, sm, st>>>((const float*)a, nullptr, npix, C, nullptr, nullptr, sums);

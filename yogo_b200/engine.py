@@ -144,6 +144,14 @@ class Runner:
         self.input_scale: Optional[float] = None
 
     # ---------------------------------------------------------------- helpers
+    def _zeros64(self, n: int, dev) -> torch.Tensor:
+        a = getattr(self, "_arena64", None)
+        if a is not None and a.device == dev and self._arena64_pos + n <= a.numel():
+            out = a[self._arena64_pos:self._arena64_pos + n]
+            self._arena64_pos += n
+            return out
+        return torch.zeros(n, dtype=torch.float64, device=dev)
+
     def _step_randoms(self, N: int, device, want_grad: bool) -> Dict[int, torch.Tensor]:
         """Dropout2d keep-scales of every training-mode Dropout2d block and the `num_batches_tracked += 1` of every
         training-mode BatchNorm, in ONE launch (csrc/input.cu: Philox keyed by a seed drawn once from torch's generator and a
@@ -220,6 +228,12 @@ class Runner:
             raise RuntimeError(f"expected input with {plan.blocks[0].cin} channels, got {Cx}")
         saved = {"x": x, "x_code": x_code, "blocks": [], "N": N, "dtype": dt}
         self._scales = self._step_randoms(N, dev, want_grad)
+        # every fp64 accumulator of the step (BatchNorm statistics forward, BatchNorm sums backward) comes zeroed from one arena:
+        # one fill launch per step instead of one per BatchNorm layer and direction
+        need64 = (sum(4 * b.cout for b in plan.blocks if b.bn is not None)
+                  if (want_grad or any(b.bn is not None and b.bn.training for b in plan.blocks)) else 0)
+        self._arena64 = torch.zeros(need64, dtype=torch.float64, device=dev) if need64 else None
+        self._arena64_pos = 0
         cur: Optional[torch.Tensor] = None  # NHWC activation
         h, w = H, W
         for i, blk in enumerate(plan.blocks):
@@ -285,7 +299,7 @@ class Runner:
                         L.check(lib.yg_conv_first_gram(x.data_ptr(), x_code, N, h, w, blk.stride, gram.data_ptr(), st))
                         rec["gram"] = gram
                     if bn_train:
-                        stats = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                        stats = self._zeros64(2 * blk.cout, dev)
                         y_raw = None if first_direct else torch.empty_like(out)
                         if use_gram:
                             if "gram" not in rec:
@@ -398,7 +412,7 @@ class Runner:
                 # conv output.  With 8-channel-aligned rows the two BN sums come from the streaming pass (yg_bn_bwd_sums),
                 # which keeps the epilogue on its straight-line path; otherwise it reduces them itself.
                 if blk.cout % 8 != 0:
-                    sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                    sums = self._zeros64(2 * blk.cout, dev)
                 ep = L.BwdEpilogue(rec["saved"].data_ptr(), blk.act, L.ptr(rec["dropscale"]),
                                    rec["scale"].data_ptr(), rec["shift"].data_ptr(), rec["mean"].data_ptr(),
                                    rec["invstd"].data_ptr(), L.ptr(sums))
@@ -478,7 +492,7 @@ class Runner:
                     done(blk.conv.weight, blk.conv.bias, blk.bn.weight, blk.bn.bias)
                     continue
                 if blk.bn is not None:
-                    sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                    sums = self._zeros64(2 * blk.cout, dev)
                     ep1 = L.BwdEpilogue(None, blk.act, L.ptr(rec["dropscale"]), rec["scale"].data_ptr(),
                                         rec["shift"].data_ptr(), rec["mean"].data_ptr(), rec["invstd"].data_ptr(),
                                         sums.data_ptr())
@@ -520,7 +534,7 @@ class Runner:
                 dgam = gbuf(blk.bn.weight)
                 dbet = gbuf(blk.bn.bias)
                 if sums is None:
-                    sums = torch.zeros(2 * blk.cout, dtype=torch.float64, device=dev)
+                    sums = self._zeros64(2 * blk.cout, dev)
                     L.check(lib.yg_bn_bwd_sums(g.data_ptr(), rec["saved"].data_ptr(), dcode, N, ho * wo, blk.cout,
                                                rec["mean"].data_ptr(), rec["invstd"].data_ptr(), sums.data_ptr(), st))
                 L.check(lib.yg_bn_bwd_apply(g.data_ptr(), rec["saved"].data_ptr(), dcode, N, ho * wo, blk.cout,

@@ -181,8 +181,13 @@ class DataParallelTrainer:
         self._bucket_pending = [0] * len(self.buckets)
         self._comm_events = []
         out = self.net(imgs)
-        loss, _ = self.loss_fn(out, labels)
-        loss.backward()
+        if isinstance(self.loss_fn, YOGOLoss):
+            # the kernel already produced d(loss)/d(out): feed it to the network's backward directly (no `ones * grad` pass)
+            loss, _, dout = self.loss_fn.loss_and_grad(out, labels)
+            torch.autograd.backward(out, dout)
+        else:
+            loss, _ = self.loss_fn(out, labels)
+            loss.backward()
         if self.world > 1:
             cur = torch.cuda.current_stream()
             for ev in self._comm_events:

@@ -63,23 +63,28 @@ class _LazyFloats(dict):
         return dict.__repr__(self)
 
 
+@L.on_device(lambda pred, *a: pred)
+def _launch(pred, label, weights, need_grad):
+    """One launch of the fused kernel: (out4 = [loss, iou, objectness, classification], d(loss)/d(pred) or None)."""
+    lib = L.lib()
+    N, D, Sy, Sx = pred.shape
+    pred_c = pred.detach().contiguous().float()
+    label_c = label.detach().contiguous().float()
+    out4 = torch.empty(4, dtype=torch.float32, device=pred.device)
+    dpred = torch.empty_like(pred_c) if need_grad else None
+    nbytes = lib.yg_yogo_loss_workspace(N, Sy, Sx)
+    ws = L.workspace.get("loss", nbytes, pred.device)
+    no_obj, iou_w, cls_w, smooth = weights
+    L.check(lib.yg_yogo_loss_fwd_bwd(pred_c.data_ptr(), label_c.data_ptr(), out4.data_ptr(), L.ptr(dpred),
+                                     N, D - 5, Sy, Sx, no_obj, iou_w, cls_w, smooth, ws.data_ptr(), nbytes,
+                                     L.stream()))
+    return out4, dpred
+
+
 class _LossFunction(torch.autograd.Function):
     @staticmethod
-    @L.on_device(lambda ctx, pred, *a: pred)
     def forward(ctx, pred, label, weights, out4_holder):
-        lib = L.lib()
-        N, D, Sy, Sx = pred.shape
-        pred_c = pred.detach().contiguous().float()
-        label_c = label.detach().contiguous().float()
-        out4 = torch.empty(4, dtype=torch.float32, device=pred.device)
-        need_grad = pred.requires_grad
-        dpred = torch.empty_like(pred_c) if need_grad else None
-        nbytes = lib.yg_yogo_loss_workspace(N, Sy, Sx)
-        ws = L.workspace.get("loss", nbytes, pred.device)
-        no_obj, iou_w, cls_w, smooth = weights
-        L.check(lib.yg_yogo_loss_fwd_bwd(pred_c.data_ptr(), label_c.data_ptr(), out4.data_ptr(), L.ptr(dpred),
-                                         N, D - 5, Sy, Sx, no_obj, iou_w, cls_w, smooth, ws.data_ptr(), nbytes,
-                                         L.stream()))
+        out4, dpred = _launch(pred, label, weights, pred.requires_grad)
         ctx.dpred = dpred
         out4_holder.append(out4)
         return out4[0].clone()
@@ -118,6 +123,24 @@ class YOGOLoss(torch.nn.modules.loss._Loss):
     def forward(self, pred_batch: torch.Tensor, label_batch: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, float]]:
         """pred (N, 5+C, Sy, Sx), label (N, 6, Sy, Sx) = [mask, x1, y1, x2, y2, class].
         Returns (loss, {"iou_loss", "objectness_loss", "classification_loss"})."""
+        self._check(pred_batch, label_batch)
+        holder: list = []
+        loss = _LossFunction.apply(pred_batch, label_batch, self._weights(), holder)
+        return loss, _LazyFloats(holder[0])
+
+    def loss_and_grad(self, pred_batch: torch.Tensor, label_batch: torch.Tensor):
+        """(loss, components, d(loss)/d(pred)) from the same single launch, without an autograd node.  The trainer hands
+        the gradient straight to the network's backward: through autograd, `loss.backward()` first fills a tensor with the
+        incoming gradient 1 and multiplies the 38 MB gradient by it (two extra launches per step)."""
+        self._check(pred_batch, label_batch)
+        out4, dpred = _launch(pred_batch, label_batch, self._weights(), True)
+        return out4[0], _LazyFloats(out4), dpred
+
+    def _weights(self):
+        return (float(self.no_obj_weight), float(self.iou_weight), float(self.classify_weight), float(self.label_smoothing))
+
+    @staticmethod
+    def _check(pred_batch, label_batch) -> None:
         if pred_batch.ndim != 4 or label_batch.ndim != 4:
             raise ValueError("pred and label must be 4-d (N, C, Sy, Sx)")
         if pred_batch.shape[0] != label_batch.shape[0] or pred_batch.shape[2:] != label_batch.shape[2:]:
@@ -127,8 +150,3 @@ class YOGOLoss(torch.nn.modules.loss._Loss):
             raise RuntimeError("label must have 6 channels and pred 5 + num_classes")
         L.require_cuda(pred_batch, "YOGOLoss pred")
         L.require_cuda(label_batch, "YOGOLoss label")
-        holder: list = []
-        weights = (float(self.no_obj_weight), float(self.iou_weight), float(self.classify_weight),
-                   float(self.label_smoothing))
-        loss = _LossFunction.apply(pred_batch, label_batch, weights, holder)
-        return loss, _LazyFloats(holder[0])
