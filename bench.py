@@ -409,6 +409,9 @@ def run_ours(args):
     net.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     if args.dtype == "fp32" and args.fp32_x3:
         yogo_b200.set_fp32_tensor_cores(True)   # split-bf16 convolutions of fp32 tensors on the tensor cores (csrc/x3.cu)
+    if args.tc_or:   # experiment knob: extra option bits of the conv engine (include/yogo_b200.h, yg_set_tc_options) for A/B runs of the whole step
+        from yogo_b200 import _lib as _L
+        _L.check(_L.lib().yg_set_tc_options(_L.lib().yg_get_tc_options() | args.tc_or))
     net.train()
     loss_fn = yogo_b200.YOGOLoss().to(dev)
     trainer = DataParallelTrainer(net, loss_fn, total_steps=10000, overlap=bool(args.overlap))
@@ -704,6 +707,7 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-GPU comparator (N = 1)")
     ap.add_argument("--graph", type=int, default=1, help="replay the whole step from a CUDA graph")
     ap.add_argument("--fp32-x3", type=int, default=1, help="--dtype fp32: run the convolutions as split-bf16 x3 on the tensor cores")
+    ap.add_argument("--tc-or", type=int, default=0, help="OR these bits into the conv engine's option word (A/B experiments)")
     ap.add_argument("--overlap", type=int, default=1, help="N > 1: all-reduce gradient buckets on a side stream while backward continues")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1088,6 +1088,44 @@ def test_conv_outputs_stay_inside_their_buffers(shape):
     assert bool(torch.isfinite(dx.float()).all()) and bool(torch.isfinite(dw).all())
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 64, 16, 32, 1), (2, 39, 36, 64, 128, 1), (2, 41, 38, 32, 64, 2), (2, 37, 36, 128, 128, 2),
+                                   (2, 33, 24, 128, 128, 1), (1, 38, 40, 48, 96, 1)])
+def test_flat_mma_issue_list_is_bit_identical_to_the_table_walk(shape):
+    """The MMA warp issues from a flat host-built list (one word per MMA, structurally zero K steps of W-folded layers left out);
+    option bit 22 restores the per-tap table walk.  Same MMAs in the same order: forward and dgrad outputs must be bit-identical
+    (W-folded, CTA-pair, stride-2 parity-class and streamed-weight configurations)."""
+    import ctypes as C
+    N, H, W, Cin, Cout, s = shape
+    lib = L.lib()
+    g = torch.Generator().manual_seed(sum(shape))
+    dt = torch.bfloat16
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+    x = torch.randn(N, H, W, Cin, generator=g).to(DEV).to(dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(DEV)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).to(dt)
+    xmask = torch.randint(0, 255, (N * H * W * Cin // 8,), generator=g, dtype=torch.uint8).to(DEV)
+    outs = []
+    base = lib.yg_get_tc_options()
+    try:
+        for bit in (0, 1 << 22):
+            L.check(lib.yg_set_tc_options(base | bit))
+            y = torch.zeros(N, Ho, Wo, Cout, dtype=dt, device=DEV)
+            m = torch.zeros(y.numel() // 8, dtype=torch.uint8, device=DEV)
+            ep = L.FwdEpilogue(None, b.data_ptr(), L.ACT_LRELU, None, None, None, m.data_ptr())
+            L.check(lib.yg_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(ep), L.stream()))
+            dx = torch.zeros(N, H, W, Cin, dtype=dt, device=DEV)
+            be = L.BwdEpilogue(x.data_ptr(), L.ACT_LRELU, None, None, None, None, None, None, xmask.data_ptr())
+            L.check(lib.yg_conv_dgrad(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, N, H, W, Cin, Cout, 3, s, C.byref(be), L.stream()))
+            torch.cuda.synchronize()
+            outs.append((y, m, dx))
+    finally:
+        L.check(lib.yg_set_tc_options(base))
+    assert bool(outs[0][0].float().abs().sum() > 0) and bool(outs[0][2].float().abs().sum() > 0)
+    for a, b_ in zip(outs[0], outs[1]):
+        assert torch.equal(a, b_)
+
+
 FULL_LAYERS = [
     # (N, H, W, Cin, Cout, stride): every 3x3 layer of base_model / double_filters at the 772x1032 geometry
     (3, 386, 516, 16, 32, 1), (3, 386, 516, 32, 64, 2), (3, 193, 258, 64, 128, 1), (3, 193, 258, 128, 128, 2),
