@@ -54,7 +54,8 @@ int yg_get_conv_impl(void);
  * bit 19 = no merged row taps (one N = 192 MMA) in the 64-input-channel wgrad, bit 20 = stride-2 wgrad fetches the dz tile once
  * per parity group instead of once per tile, bit 21 = fp32 tensors as split-bf16 "x3" convolutions on the tensor cores
  * (csrc/x3.cu; off by default: the exact SIMT kernels are the fp32 parity path), bit 22 = MMA issue by the per-tap table walk
- * instead of the flat host-built list (same MMAs in the same order; slower). */
+ * instead of the flat host-built list (same MMAs in the same order; slower), bits 24-26 = A-operand pipeline depth of the
+ * tcgen05 conv engine: 0 = at most 4 stages (default), 1..6 = at most 2..7, 7 = every stage that fits in shared memory. */
 int yg_set_tc_options(int options);
 int yg_get_tc_options(void);
 /* profiling hook: copies n (<= 2048) cycle counters written by the engine's MMA warps (8 per CTA) to host memory. */

@@ -2273,6 +2273,14 @@ static int launch_engine(TcMaps& maps, TcParams& p, int KCc, int mode, int max_r
   const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
   int nst = (TC_SMEM_BUDGET - p.resb_bytes) / stage_bytes;
   if (nst > 16) nst = 16;
+  // Four stages at most: deeper A pipelines are not faster anywhere and measurably slower where the producer can run far ahead
+  // (same box, ms: L3 dgrad 0.350 with every stage that fits, 0.331 / 0.325 / 0.323 with 6 / 4 / 3; CTA-pair L4 dgrad 0.439 /
+  // 0.439 / 0.428 / 0.429).  Option bits 24-26: 1..6 = cap at 2..7 stages, 7 = no cap.
+  {
+    const int capsel = (g_tc_options >> 24) & 7;
+    const int cap = capsel == 0 ? 4 : (capsel == 7 ? 16 : capsel + 1);
+    if (nst > cap) nst = cap;
+  }
   if (nst < 2) {
     set_error("tcgen05 conv: stage of %d bytes does not fit twice in shared memory", stage_bytes);
     return YG_ERR_INVALID;
