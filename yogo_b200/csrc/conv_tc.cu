@@ -2869,17 +2869,21 @@ __global__ void pack_head_weights_kernel(const float* __restrict__ w, bf16* __re
 
 __global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int D, int Cin,
                                          int BNW, int n_mtiles, int nunits, int nslices, float clip) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [d][ci]
+  // one warp per [d][ci] element: the lanes stride over the ~148 slices (independent loads in flight instead of one serial
+  // chain per thread), then a fixed shuffle tree - the order of the summation does not depend on the launch
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= D * Cin) return;
   const int ci = i % Cin, d = i / Cin;
   const int nt = ci / BNW;
   const int unit = 0 + 1 * (0 + n_mtiles * nt);
   float acc = 0.f;
-  for (int sl = 0; sl < nslices; ++sl) {
+  for (int sl = lane; sl < nslices; sl += 32) {
     const size_t cta = (size_t)unit + (size_t)nunits * sl;
     acc += partial[((cta * 3 + 0) * 128 + d) * BNW + (ci % BNW)];
   }
-  dw[i] = clampf(acc, clip);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) dw[i] = clampf(acc, clip);
 }
 
 bool head_bwd_tc_supported(int Cin, int D) {
@@ -3091,7 +3095,7 @@ int head_bwd_tc(const void* dt, const void* x, const float* w, void* dx, float* 
     if (kb == 64) HW_LAUNCH(64); else if (kb == 32) HW_LAUNCH(32); else HW_LAUNCH(16);
 #undef HW_LAUNCH
     YG_LAUNCH_CHECK("wgrad_tc_kernel(head)");
-    head_wgrad_reduce_kernel<<<cdiv((long long)D * Cin, 256), 256, 0, st>>>((const float*)ws, dw, D, Cin, p.BNW,
+    head_wgrad_reduce_kernel<<<cdiv((long long)D * Cin * 32, 256), 256, 0, st>>>((const float*)ws, dw, D, Cin, p.BNW,
                                                                             p.n_mtiles, p.nunits, p.nslices, clip);
     YG_LAUNCH_CHECK("head_wgrad_reduce");
   }
