@@ -207,8 +207,15 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_cg_kernel(T* __restrict__ g, const T* __restrict__ y, long long npix, int C,
                                                               double M, const double* __restrict__ sums,
                                                               const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                              const float* __restrict__ invstd, int batch_stats) {
+                                                              const float* __restrict__ invstd, int batch_stats,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, float clip) {
   extern __shared__ float kc[];  // [3][C]: A, B, K (same constants as bn_bwd_apply_kernel)
+  if (blockIdx.x == 0) {   // the parameter gradients are the two sums themselves (bn_param_grad_kernel in the same launch)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = clampf((float)sums[c], clip);
+      if (dgamma) dgamma[c] = clampf((float)sums[C + c], clip);
+    }
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float m1 = batch_stats ? (float)(sums[c] / M) : 0.f, m2 = batch_stats ? (float)(sums[C + c] / M) : 0.f;
     const float gi = (gamma ? gamma[c] : 1.f) * invstd[c];
@@ -427,10 +434,11 @@ extern "C" int yg_bn_bwd_apply(void* g, const void* y, int dtype, int N, int HW,
       long long want = cdiv(cdiv(npix, (long long)lanes), 4LL);
       const int blocks_cg = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
       if (dtype == YG_BF16)
-        bn_bwd_apply_cg_kernel<bf16><<<blocks_cg, 256, sm, st>>>((bf16*)g, (const bf16*)y, npix, C, M, sums, gamma, mean, invstd, batch_stats);
+        bn_bwd_apply_cg_kernel<bf16><<<blocks_cg, 256, sm, st>>>((bf16*)g, (const bf16*)y, npix, C, M, sums, gamma, mean, invstd, batch_stats, dgamma, dbeta, clip);
       else
-        bn_bwd_apply_cg_kernel<float><<<blocks_cg, 256, sm, st>>>((float*)g, (const float*)y, npix, C, M, sums, gamma, mean, invstd, batch_stats);
+        bn_bwd_apply_cg_kernel<float><<<blocks_cg, 256, sm, st>>>((float*)g, (const float*)y, npix, C, M, sums, gamma, mean, invstd, batch_stats, dgamma, dbeta, clip);
       YG_LAUNCH_CHECK("bn_bwd_apply");
+      return YG_OK;
     } else
     if (dtype == YG_BF16)
       bn_bwd_apply_kernel<bf16><<<blocks, 256, sm, st>>>((bf16*)g, (const bf16*)y, total, C, M, sums, gamma, mean, invstd, batch_stats);

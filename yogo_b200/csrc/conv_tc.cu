@@ -1970,31 +1970,32 @@ wgrad_tc_kernel(const __grid_constant__ TwMaps maps, const __grid_constant__ TwP
   if (warp == PW) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// d(bias)[co] = sum over the CTAs that share the M tile and over the W-fold sub-pixels q of the bias-column
-// partials [cta][128]  (cta = unit + nunits * slice, unit = s + ncols * (mtile + n_mtiles * ntile))
-__global__ void wgrad_bias_reduce_kernel(const float* __restrict__ part, float* __restrict__ dbias, int Cout, int g,
-                                         int ncols, int n_mtiles, int nunits, int grid, float clip) {
-  // one warp per output channel: the lanes stride over the CTAs (independent loads in flight), then a shuffle reduction
-  const int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (co >= Cout) return;
-  float acc = 0.f;
-  for (int b = lane; b < grid; b += 32) {
-    const int mt = ((b % nunits) / ncols) % n_mtiles;
-    for (int q = 0; q < g; ++q) {
-      const int cof = q * Cout + co;
-      if (cof / 128 == mt) acc += part[(size_t)b * 128 + cof % 128];
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) dbias[co] = clampf(acc, clip);
-}
-
 // Sums the per-CTA partials in a fixed order.  The kernel ran on (possibly W-folded) dimensions Coutf = g*Cout,
 // Cinf = g*Cin; a real weight (co, ci, r, s) collects every folded position (q, pi, s') with
 // s = g*(s'-1) + pi - q + 1 (g = 1: the identity).
+// The blocks from nb_w on sum d(bias) (same launch: one kernel less per layer):
+// d(bias)[co] = sum over the CTAs that share the M tile and over the W-fold sub-pixels q of the bias-column
+// partials [cta][128]  (cta = unit + nunits * slice, unit = s + ncols * (mtile + n_mtiles * ntile))
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
-                                       int g, int BNW, int n_mtiles, int nunits, int nslices, float clip) {
+                                       int g, int BNW, int n_mtiles, int nunits, int nslices, float clip, int nb_w,
+                                       const float* __restrict__ bias_part, float* __restrict__ dbias, int ncols, int grid_ctas) {
+  if ((int)blockIdx.x >= nb_w) {
+    // one warp per output channel: the lanes stride over the CTAs (independent loads in flight), then a shuffle reduction
+    const int co = (((int)blockIdx.x - nb_w) * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (co >= Cout) return;
+    float acc = 0.f;
+    for (int b = lane; b < grid_ctas; b += 32) {
+      const int mt = ((b % nunits) / ncols) % n_mtiles;
+      for (int q = 0; q < g; ++q) {
+        const int cof = q * Cout + co;
+        if (cof / 128 == mt) acc += bias_part[(size_t)b * 128 + cof % 128];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dbias[co] = clampf(acc, clip);
+    return;
+  }
   // thread order [co][r][s][ci] (ci fastest): a warp reads consecutive floats of a partial row; the OIHW store is strided but tiny.
   // The per-element summation order (fold position, then slice) is fixed, so the result does not depend on this mapping.
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2209,13 +2210,11 @@ const int prodw = (kb <= 32 && nst >= 3 && (g_tc_options & 2)) ? 1 : 0;
 #undef TW_LAUNCH
   YG_LAUNCH_CHECK("wgrad_tc_kernel");
   const long long nw = (long long)Cout_r * Cin_r * 9;
-  wgrad_tc_reduce_kernel<<<cdiv(nw, 256), 256, 0, st>>>((const float*)ws, dw, Cout_r, Cin_r, fg, p.BNW, p.n_mtiles,
-                                                        p.nunits, p.nslices, clip);
+  const int nb_w = (int)cdiv(nw, 256), nb_b = bias_col ? (int)cdiv(Cout_r * 32, 256) : 0;
+  wgrad_tc_reduce_kernel<<<nb_w + nb_b, 256, 0, st>>>((const float*)ws, dw, Cout_r, Cin_r, fg, p.BNW, p.n_mtiles, p.nunits, p.nslices,
+                                                      clip, nb_w, p.bias_partial, dbias, p.ncols, grid);
   YG_LAUNCH_CHECK("wgrad_tc_reduce");
-  if (bias_col) {
-    wgrad_bias_reduce_kernel<<<cdiv(Cout_r * 32, 256), 256, 0, st>>>(p.bias_partial, dbias, Cout_r, fg, p.ncols, p.n_mtiles, p.nunits, grid, clip);
-    YG_LAUNCH_CHECK("wgrad_bias_reduce");
-  } else if (dbias) {
+  if (!bias_col && dbias) {
     float* part = (float*)((char*)ws + (size_t)grid * 3 * 128 * p.BNW * sizeof(float));
     const long long npix = (long long)N * Ho * Wo_r;   // the bias gradient is taken on the real (unfolded) view
     const int nblk = (int)(npix < COLSUM_BLOCKS ? npix : COLSUM_BLOCKS);
